@@ -1,0 +1,1116 @@
+/*
+ * zerodop_oracle.c -- TEST INFRASTRUCTURE ONLY (see zerodop_oracle.h).
+ *
+ * Line-by-line CPU restatement of the ISCE2 zero-Doppler topozero / geo2rdr path.
+ * Build:  gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC
+ * (no FMA contraction: the reference is Fortran/C built for generic x86-64, which
+ * has no fused multiply-add, so every product and sum rounds separately).
+ *
+ * All citations are relative to /root/reference.
+ */
+#include "zerodop_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ */
+/* linalg3: components/isceobj/Util/Library/linalg3/src/linalg3Module.F */
+/* ------------------------------------------------------------------ */
+static inline void v_cross(const double *u, const double *v, double *w) /* :37-76 */
+{
+    double w0 = u[1] * v[2] - u[2] * v[1];
+    double w1 = u[2] * v[0] - u[0] * v[2];
+    double w2 = u[0] * v[1] - u[1] * v[0];
+    w[0] = w0; w[1] = w1; w[2] = w2;
+}
+static inline double v_dot(const double *v, const double *w) /* :78-115 */
+{
+    return v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+}
+static inline double v_norm(const double *v) /* :256-292 */
+{
+    return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+}
+static inline void v_unit(const double *v, double *u) /* :338-382: leaves u untouched if |v| == 0 */
+{
+    double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (n != 0) {
+        double a = v[0] / n, b = v[1] / n, c = v[2] / n;
+        u[0] = a; u[1] = b; u[2] = c;
+    }
+}
+/* matvec with Fortran r_t(i,j) stored row-major m[3*i+j] : :212-254 */
+static inline void m_vec(const double *m, const double *v, double *w)
+{
+    double w0 = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+    double w1 = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+    double w2 = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    w[0] = w0; w[1] = w1; w[2] = w2;
+}
+
+/* ------------------------------------------------------------------ */
+/* geometry                                                            */
+/* ------------------------------------------------------------------ */
+/* components/isceobj/Util/Library/geometry/src/latlon.F:44-71 */
+void orc_latlon(double r_a, double r_e2, double *r_v, double *r_llh, int i_type)
+{
+    if (i_type == 1) { /* LLH_2_XYZ :44-49 */
+        double sl = sin(r_llh[0]);
+        double r_re = r_a / sqrt(1.0 - r_e2 * (sl * sl));
+        r_v[0] = (r_re + r_llh[2]) * cos(r_llh[0]) * cos(r_llh[1]);
+        r_v[1] = (r_re + r_llh[2]) * cos(r_llh[0]) * sin(r_llh[1]);
+        r_v[2] = (r_re * (1.0 - r_e2) + r_llh[2]) * sin(r_llh[0]);
+    } else { /* XYZ_2_LLH :51-71 */
+        double r_q2 = (r_v[0] * r_v[0] + r_v[1] * r_v[1]);
+        double r_q3 = r_a * r_a;
+        double r_e4 = r_e2 * r_e2;
+        double r_p = r_q2 / r_q3;
+        double r_q = (1.0 - r_e2) * (r_v[2] * r_v[2]) / r_q3;
+        double r_r = (r_p + r_q - r_e4) / 6.0;
+        double r_s = (r_e4 * r_p * r_q) / (4.0 * (r_r * r_r * r_r));
+        double r_t = pow(1.0 + r_s + sqrt(r_s * (2.0 + r_s)), 1.0 / 3.0);
+        double r_u = r_r * (1.0 + r_t + 1.0 / r_t);
+        double r_rv = sqrt(r_u * r_u + r_e4 * r_q);
+        double r_w = r_e2 * (r_u + r_rv - r_q) / (2.0 * r_rv);
+        double r_k = sqrt(r_u + r_rv + r_w * r_w) - r_w;
+        double r_d = r_k * sqrt(r_q2) / (r_k + r_e2);
+        r_llh[0] = atan2(r_v[2], r_d);
+        r_llh[1] = atan2(r_v[1], r_v[0]);
+        r_llh[2] = (r_k + r_e2 - 1.0) * sqrt(r_d * r_d + r_v[2] * r_v[2]) / r_k;
+    }
+}
+
+/* components/isceobj/Util/Library/geometry/src/curvature.F:26-64 */
+double orc_reast(double a, double e2, double lat)
+{
+    double s = sin(lat);
+    return a / sqrt(1.0 - e2 * (s * s));
+}
+double orc_rnorth(double a, double e2, double lat)
+{
+    double s = sin(lat);
+    return (a * (1.0 - e2)) / pow(1.0 - e2 * (s * s), 1.5);
+}
+double orc_rdir(double a, double e2, double hdg, double lat)
+{
+    double re = orc_reast(a, e2, lat);
+    double rn = orc_rnorth(a, e2, lat);
+    double c = cos(hdg), s = sin(hdg);
+    return (re * rn) / (re * (c * c) + rn * (s * s));
+}
+
+/* components/isceobj/Util/Library/geometry/src/tcnbasis.F:26-39 */
+void orc_tcnbasis(const double *pos, const double *vel, double a, double e2, double *r_t, double *r_c, double *r_n)
+{
+    double llh[3], tmp[3], p[3] = {pos[0], pos[1], pos[2]};
+    orc_latlon(a, e2, p, llh, 2);
+    double lat = llh[0], lon = llh[1];
+    r_n[0] = -cos(lat) * cos(lon);
+    r_n[1] = -cos(lat) * sin(lon);
+    r_n[2] = -sin(lat);
+    v_cross(r_n, vel, tmp);
+    v_unit(tmp, r_c);
+    v_cross(r_c, r_n, tmp);
+    v_unit(tmp, r_t);
+}
+
+/* components/isceobj/Util/Library/geometry/src/enubasis.F:39-60; m[3*i+j] = r_enumat(i+1,j+1) */
+void orc_enubasis(double r_lat, double r_lon, double *m)
+{
+    double clt = cos(r_lat), slt = sin(r_lat), clo = cos(r_lon), slo = sin(r_lon);
+    m[0 * 3 + 1] = -slt * clo; m[1 * 3 + 1] = -slt * slo; m[2 * 3 + 1] = clt;   /* north */
+    m[0 * 3 + 0] = -slo;       m[1 * 3 + 0] = clo;        m[2 * 3 + 0] = 0.0;   /* east  */
+    m[0 * 3 + 2] = clt * clo;  m[1 * 3 + 2] = clt * slo;  m[2 * 3 + 2] = slt;   /* up    */
+}
+
+/* components/isceobj/Util/Library/geometry/src/radar_to_xyz.F:49-92 */
+double orc_radar_to_xyz(double a, double e2, double plat, double plon, double phdg, double *mat, double *ov)
+{
+    double clt = cos(plat), slt = sin(plat), clo = cos(plon), slo = sin(plon);
+    double chg = cos(phdg), shg = sin(phdg);
+    mat[0] = clt * clo;
+    mat[1] = -shg * slo - slt * clo * chg;
+    mat[2] = slo * chg - slt * clo * shg;
+    mat[3] = clt * slo;
+    mat[4] = clo * shg - slt * slo * chg;
+    mat[5] = -clo * chg - slt * slo * shg;
+    mat[6] = slt;
+    mat[7] = clt * chg;
+    mat[8] = clt * shg;
+    double radcur = orc_rdir(a, e2, phdg, plat);
+    double llh[3] = {plat, plon, 0.0}, p[3];
+    orc_latlon(a, e2, p, llh, 1);
+    double up[3] = {clt * clo, clt * slo, slt};
+    for (int i = 0; i < 3; i++) ov[i] = p[i] - radcur * up[i];
+    return radcur;
+}
+
+/* components/isceobj/Util/Library/geometry/src/convert_sch_to_xyz.F:63-72 (XYZ_2_SCH branch) */
+void orc_xyz_to_sch(const double *mat, const double *ov, double radcur, const double *xyz, double *sch)
+{
+    double t[3], s[3], llh[3], minv[9];
+    /* lincomb(1, xyz, -1, ov) : linalg3Module.F:117-159 */
+    for (int i = 0; i < 3; i++) t[i] = 1.0 * xyz[i] + (-1.0) * ov[i];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) minv[3 * i + j] = mat[3 * j + i];
+    m_vec(minv, t, s);
+    orc_latlon(radcur, 0.0, s, llh, 2);
+    sch[0] = radcur * llh[1];
+    sch[1] = radcur * llh[0];
+    sch[2] = llh[2];
+}
+
+/* ------------------------------------------------------------------ */
+/* orbit: components/isceobj/Util/Library/orbit/src                    */
+/* ------------------------------------------------------------------ */
+/* orbitHermite.c:4-94 */
+static void orbit_hermite(double x[][3], double v[][3], const double *t, double time, double *xx, double *vv)
+{
+    double h[4], hdot[4], f0[4], f1[4], g0[4], g1[4], sum, product;
+    const int n1 = 4, n2 = 3;
+    for (int i = 0; i < n1; ++i) {
+        f1[i] = time - t[i];
+        sum = 0.0;
+        for (int j = 0; j < n1; ++j)
+            if (i != j) sum += 1.0 / (t[i] - t[j]);
+        f0[i] = 1.0 - 2.0 * (time - t[i]) * sum;
+    }
+    for (int i = 0; i < n1; ++i) {
+        product = 1.0;
+        for (int k = 0; k < n1; ++k)
+            if (k != i) product *= (time - t[k]) / (t[i] - t[k]);
+        h[i] = product;
+        sum = 0.0;
+        for (int j = 0; j < n1; ++j) {
+            product = 1.0;
+            for (int k = 0; k < n1; ++k)
+                if ((k != i) && (k != j)) product *= (time - t[k]) / (t[i] - t[k]);
+            if (j != i) sum += 1.0 / (t[i] - t[j]) * product;
+        }
+        hdot[i] = sum;
+    }
+    for (int i = 0; i < n1; ++i) {
+        g1[i] = h[i] + 2.0 * (time - t[i]) * hdot[i];
+        sum = 0.0;
+        for (int j = 0; j < n1; ++j)
+            if (i != j) sum += 1.0 / (t[i] - t[j]);
+        g0[i] = 2.0 * (f0[i] * hdot[i] - h[i] * sum);
+    }
+    for (int k = 0; k < n2; ++k) {
+        sum = 0.0;
+        for (int i = 0; i < n1; ++i) sum += (x[i][k] * f0[i] + v[i][k] * f1[i]) * h[i] * h[i];
+        xx[k] = sum;
+        sum = 0.0;
+        for (int i = 0; i < n1; ++i) sum += (x[i][k] * g0[i] + v[i][k] * g1[i]) * h[i];
+        vv[k] = sum;
+    }
+}
+
+/* orbit.c:175-234 interpolateWGS84Orbit */
+int orc_interp_hermite(const orc_orbit *orb, double tintp, double *opos, double *ovel)
+{
+    double pos[4][3], vel[4][3], t[4];
+    int i, j;
+    if (orb->nvec < 4) return 1;
+    for (i = 0; i < orb->nvec; i++)
+        if (orb->t[i] >= tintp) break;
+    i -= 2;
+    if (i < 0) i = 0;
+    if (i > orb->nvec - 4) i = orb->nvec - 4;
+    for (j = 0; j < 4; j++) {
+        t[j] = orb->t[i + j];
+        for (int k = 0; k < 3; k++) {
+            pos[j][k] = orb->pos[3 * (i + j) + k];
+            vel[j][k] = orb->vel[3 * (i + j) + k];
+        }
+    }
+    orbit_hermite(pos, vel, t, tintp, opos, ovel);
+    if ((tintp < orb->t[0]) || (tintp > orb->t[orb->nvec - 1])) return 1;
+    return 0;
+}
+
+/* orbit.c:236-314 interpolateLegendreOrbit */
+int orc_interp_legendre(const orc_orbit *orb, double tintp, double *opos, double *ovel)
+{
+    int i, j;
+    double pos[9][3], vel[9][3], t[9], trel, coeff, teller;
+    const double noemer[] = {40320.0, -5040.0, 1440.0, -720.0, 576.0, -720.0, 1440.0, -5040.0, 40320.0};
+    opos[0] = opos[1] = opos[2] = 0.0;
+    ovel[0] = ovel[1] = ovel[2] = 0.0;
+    if (orb->nvec < 9) return 1;
+    for (i = 0; i < orb->nvec; i++)
+        if (orb->t[i] >= tintp) break;
+    i -= 5;
+    if (i < 0) i = 0;
+    if (i > orb->nvec - 9) i = orb->nvec - 9;
+    for (j = 0; j < 9; j++) {
+        t[j] = orb->t[i + j];
+        for (int k = 0; k < 3; k++) {
+            pos[j][k] = orb->pos[3 * (i + j) + k];
+            vel[j][k] = orb->vel[3 * (i + j) + k];
+        }
+    }
+    trel = 8.0 * (tintp - t[0]) / (t[8] - t[0]);
+    teller = 1.0;
+    for (j = 0; j < 9; j++) teller *= (trel - j);
+    if (teller == 0.0) {
+        i = (int)trel;
+        for (j = 0; j < 3; j++) {
+            opos[j] = pos[i][j];
+            ovel[j] = vel[i][j];
+        }
+    } else {
+        for (i = 0; i < 9; i++) {
+            coeff = teller / noemer[i] / (trel - i);
+            for (j = 0; j < 3; j++) {
+                opos[j] += coeff * pos[i][j];
+                ovel[j] += coeff * vel[i][j];
+            }
+        }
+    }
+    if ((tintp < orb->t[0]) || (tintp > orb->t[orb->nvec - 1])) return 1;
+    return 0;
+}
+
+/* orbit.c:119-172 interpolateSCHOrbit (Lagrange over all state vectors) */
+int orc_interp_sch(const orc_orbit *orb, double tintp, double *opos, double *ovel)
+{
+    if (orb->nvec < 2) return 1;
+    if ((tintp < orb->t[0]) || (tintp > orb->t[orb->nvec - 1])) return 1;
+    opos[0] = opos[1] = opos[2] = 0.0;
+    ovel[0] = ovel[1] = ovel[2] = 0.0;
+    for (int i = 0; i < orb->nvec; i++) {
+        double frac = 1.0;
+        double t0 = orb->t[i];
+        for (int j = 0; j < orb->nvec; j++) {
+            if (i == j) continue;
+            double t1 = orb->t[j];
+            double num = t1 - tintp;
+            double den = t1 - t0;
+            frac *= num / den;
+        }
+        for (int k = 0; k < 3; k++) {
+            opos[k] += frac * orb->pos[3 * i + k];
+            ovel[k] += frac * orb->vel[3 * i + k];
+        }
+    }
+    return 0;
+}
+
+/* orbit.c:316-354 computeAcceleration (always Hermite) */
+int orc_compute_acceleration(const orc_orbit *orb, double tintp, double *acc)
+{
+    double xbef[3], vbef[3], xaft[3], vaft[3], temp;
+    acc[0] = acc[1] = acc[2] = 0.0;
+    temp = tintp - 0.01;
+    if (orc_interp_hermite(orb, temp, xbef, vbef) != 0) return 1;
+    temp = tintp + 0.01;
+    if (orc_interp_hermite(orb, temp, xaft, vaft) != 0) return 1;
+    for (int i = 0; i < 3; i++) acc[i] = (vaft[i] - vbef[i]) / 0.02;
+    return 0;
+}
+
+static int interp_orbit(int method, const orc_orbit *o, double t, double *p, double *v)
+{
+    if (method == ORC_HERMITE) return orc_interp_hermite(o, t, p, v);
+    if (method == ORC_SCH) return orc_interp_sch(o, t, p, v);
+    return orc_interp_legendre(o, t, p, v);
+}
+
+/* ------------------------------------------------------------------ */
+/* polynomials                                                         */
+/* ------------------------------------------------------------------ */
+/* components/isceobj/Util/Library/poly2d/src/poly2d.c:92-111 */
+double orc_eval_poly2d(const orc_poly2d *poly, double azi, double rng)
+{
+    double value = 0.0, scalex, scaley;
+    double xval = (rng - poly->mean_range) / (poly->norm_range);
+    double yval = (azi - poly->mean_azimuth) / (poly->norm_azimuth);
+    int i, j;
+    scaley = 1.0;
+    for (i = 0; i <= poly->azimuth_order; i++, scaley *= yval) {
+        scalex = 1.0;
+        for (j = 0; j <= poly->range_order; j++, scalex *= xval)
+            value += scalex * scaley * poly->coeffs[i * (poly->range_order + 1) + j];
+    }
+    return value;
+}
+
+/* components/isceobj/Util/Library/poly1d/src/poly1d.c:87-104 */
+double orc_eval_poly1d(const orc_poly1d *poly, double xin)
+{
+    double value = 0.0, scalex = 1.0;
+    double xval = (xin - poly->mean) / (poly->norm);
+    for (int i = 0; i <= poly->order; i++, scalex *= xval) value += scalex * poly->coeffs[i];
+    return value;
+}
+
+/* ------------------------------------------------------------------ */
+/* DEM interpolators.  DEM(ix,iy) with 1-based Fortran indices, lon (x) fastest. */
+/* ------------------------------------------------------------------ */
+#define DEM(ix, iy) dem[(size_t)((iy) - 1) * (size_t)nx + (size_t)((ix) - 1)]
+#define ORC_BADVALUE (-1000.0f) /* topozeroMethods.f:33 */
+
+/* components/isceobj/Util/src/uniform_interp.f90:13-44, called as bilinear(dy,dx,dem) (topozeroMethods.f:145) */
+static double bilinear(double x, double y, const float *dem, int nx)
+{
+    double x1 = floor(x), x2 = ceil(x), y1 = ceil(y), y2 = floor(y);
+    double q11 = DEM((int)y1, (int)x1);
+    double q12 = DEM((int)y2, (int)x1);
+    double q21 = DEM((int)y1, (int)x2);
+    double q22 = DEM((int)y2, (int)x2);
+    if (y1 == y2 && x1 == x2) return q11;
+    if (y1 == y2) return (x2 - x) / (x2 - x1) * q11 + (x - x1) / (x2 - x1) * q21;
+    if (x1 == x2) return (y2 - y) / (y2 - y1) * q11 + (y - y1) / (y2 - y1) * q12;
+    return q11 * (x2 - x) * (y2 - y) / ((x2 - x1) * (y2 - y1)) +
+           q21 * (x - x1) * (y2 - y) / ((x2 - x1) * (y2 - y1)) +
+           q12 * (x2 - x) * (y - y1) / ((x2 - x1) * (y2 - y1)) +
+           q22 * (x - x1) * (y - y1) / ((x2 - x1) * (y2 - y1));
+}
+
+/* uniform_interp.f90:123-130 DATA wt (column-major fill): wt(i,k) = WT_FLAT[(k-1)*16 + (i-1)] */
+static const double WT_FLAT[256] = {
+    1, 0, -3, 2, 0, 0, 0, 0, -3, 0, 9, -6, 2, 0, -6, 4,
+    0, 0, 0, 0, 0, 0, 0, 0, 3, 0, -9, 6, -2, 0, 6, -4,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 9, -6, 0, 0, -6, 4,
+    0, 0, 3, -2, 0, 0, 0, 0, 0, 0, -9, 6, 0, 0, 6, -4,
+    0, 0, 0, 0, 1, 0, -3, 2, -2, 0, 6, -4, 1, 0, -3, 2,
+    0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 3, -2, 1, 0, -3, 2,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -3, 2, 0, 0, 3, -2,
+    0, 0, 0, 0, 0, 0, 3, -2, 0, 0, -6, 4, 0, 0, 3, -2,
+    0, 1, -2, 1, 0, 0, 0, 0, 0, -3, 6, -3, 0, 2, -4, 2,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 3, -6, 3, 0, -2, 4, -2,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, 2, -2,
+    0, 0, -1, 1, 0, 0, 0, 0, 0, 0, 3, -3, 0, 0, -2, 2,
+    0, 0, 0, 0, 0, 1, -2, 1, 0, -2, 4, -2, 0, 1, -2, 1,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 2, -1, 0, 1, -2, 1,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 0, 0, -1, 1,
+    0, 0, 0, 0, 0, 0, -1, 1, 0, 0, 2, -2, 0, 0, -1, 1};
+
+/* uniform_interp.f90:112-200, called as bicubic(dy,dx,dem) (topozeroMethods.f:171).
+ * z(a,b) in the Fortran is dem(lon=a, lat=b); differences of two real*4 samples are real*4. */
+static double bicubic(double x, double y, const float *dem, int nx)
+{
+    int x1 = (int)floor(x), x2 = (int)ceil(x), y1 = (int)floor(y), y2 = (int)ceil(y);
+    double zz[4], dzdx[4], dzdy[4], dzdxy[4], q[16], cl[16], c[4][4];
+    float f;
+    zz[0] = DEM(y1, x1);
+    zz[3] = DEM(y2, x1);
+    zz[1] = DEM(y1, x2);
+    zz[2] = DEM(y2, x2);
+    f = DEM(y1, x1 + 1) - DEM(y1, x1 - 1); dzdx[0] = f / 2.0;
+    f = DEM(y1, x2 + 1) - DEM(y1, x2 - 1); dzdx[1] = f / 2.0;
+    f = DEM(y2, x2 + 1) - DEM(y2, x2 - 1); dzdx[2] = f / 2.0;
+    f = DEM(y2, x1 + 1) - DEM(y2, x1 - 1); dzdx[3] = f / 2.0;
+    f = DEM(y1 + 1, x1) - DEM(y1 - 1, x1);         dzdy[0] = f / 2.0;
+    f = DEM(y1 + 1, x2 + 1) - DEM(y1 - 1, x2);     dzdy[1] = f / 2.0; /* :152 typo kept */
+    f = DEM(y2 + 1, x2 + 1) - DEM(y2 - 1, x2);     dzdy[2] = f / 2.0; /* :153 typo kept */
+    f = DEM(y2 + 1, x1 + 1) - DEM(y2 - 1, x1);     dzdy[3] = f / 2.0; /* :154 typo kept */
+    f = DEM(y1 + 1, x1 + 1) - DEM(y1 - 1, x1 + 1); f = f - DEM(y1 + 1, x1 - 1); f = f + DEM(y1 - 1, x1 - 1);
+    dzdxy[0] = 0.25 * f;
+    f = DEM(y2 + 1, x1 + 1) - DEM(y2 - 1, x1 + 1); f = f - DEM(y2 + 1, x1 - 1); f = f + DEM(y2 - 1, x1 - 1);
+    dzdxy[3] = 0.25 * f;
+    f = DEM(y1 + 1, x2 + 1) - DEM(y1 - 1, x2 + 1); f = f - DEM(y1 + 1, x2 - 1); f = f + DEM(y1 - 1, x2 - 1);
+    dzdxy[1] = 0.25 * f;
+    f = DEM(y2 + 1, x2 + 1) - DEM(y2 - 1, x2 + 1); f = f - DEM(y2 + 1, x2 - 1); f = f + DEM(y2 - 1, x2 - 1);
+    dzdxy[2] = 0.25 * f;
+    for (int i = 0; i < 4; i++) {
+        q[i] = zz[i];
+        q[i + 4] = dzdx[i];
+        q[i + 8] = dzdy[i];
+        q[i + 12] = dzdxy[i];
+    }
+    for (int i = 0; i < 16; i++) {
+        double qq = 0.0;
+        for (int k = 0; k < 16; k++) qq = qq + WT_FLAT[k * 16 + i] * q[k];
+        cl[i] = qq;
+    }
+    int l = 0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) c[i][j] = cl[l++];
+    double t = (x - x1), u = (y - y1), r = 0.0;
+    for (int i = 3; i >= 0; i--) r = t * r + ((c[i][3] * u + c[i][2]) * u + c[i][1]) * u + c[i][0];
+    return r;
+}
+
+/* components/isceobj/Util/src/spline.f:15-33 */
+static void initspline(const double *Y, int N, double *R, double *Q)
+{
+    /* 0-based arrays hold the Fortran 1-based entries at [k-1] */
+    Q[0] = 0.0;
+    R[0] = 0.0;
+    for (int K = 2; K <= N - 1; K++) {
+        double P = Q[K - 2] / 2 + 2;
+        Q[K - 1] = -0.5 / P;
+        R[K - 1] = (3 * (Y[K] - 2 * Y[K - 1] + Y[K - 2]) - R[K - 2] / 2) / P;
+    }
+    R[N - 1] = 0.0;
+    for (int K = N - 1; K >= 2; K--) R[K - 1] = Q[K - 1] * R[K] + R[K - 1];
+}
+/* spline.f:5-13 */
+static int ifrac(double r)
+{
+    int i = (int)r;
+    if (r >= 0) return i;
+    if (r == i) return i;
+    return i - 1;
+}
+/* spline.f:36-54 */
+static double spline(double X, const double *Y, int N, const double *R)
+{
+    if (X < 1) return Y[0] + (X - 1) * (Y[1] - Y[0] - R[1] / 6);
+    if (X > N) return Y[N - 1] + (X - N) * (Y[N - 1] - Y[N - 2] + R[N - 2] / 6);
+    int J = ifrac(X);
+    double XX = X - J;
+    /* Fortran reads Y(J+1), R(J+1): J == N only when X == N exactly; not reachable from interp2DSpline */
+    return Y[J - 1] + XX * ((Y[J] - Y[J - 1] - R[J - 1] / 3 - R[J] / 6) + XX * (R[J - 1] / 2 + XX * (R[J] - R[J - 1]) / 6));
+}
+/* spline.f:58-117 interp2DSpline(order, nx=ny_dem, ny=nx_dem, z, x=dy, y=dx) as called at topozeroMethods.f:276 */
+static float interp2dspline(int order, const float *dem, int nx /*lon count*/, int ny /*lat count*/, double x /*lat idx*/, double y /*lon idx*/)
+{
+    double A[20], R[20], Q[20], HC[20];
+    int I0, J0;
+    int lodd = (order / 2) * 2 != order;
+    if (lodd) {
+        I0 = (int)(y - 0.5);
+        J0 = (int)(x - 0.5);
+    } else {
+        I0 = (int)y;
+        J0 = (int)x;
+    }
+    I0 = I0 - order / 2 + 1;
+    J0 = J0 - order / 2 + 1;
+    for (int I = 1; I <= order; I++) {
+        int INDI = I0 + I;
+        if (INDI < 1) INDI = 1;
+        if (INDI > nx) INDI = nx; /* Fortran local "ny" == lon count */
+        for (int J = 1; J <= order; J++) {
+            int INDJ = J0 + J;
+            if (INDJ < 1) INDJ = 1;
+            if (INDJ > ny) INDJ = ny; /* Fortran local "nx" == lat count */
+            A[J - 1] = DEM(INDI, INDJ);
+        }
+        initspline(A, order, R, Q);
+        HC[I - 1] = spline(x - J0, A, order, R);
+    }
+    initspline(HC, order, R, Q);
+    double temp = spline(y - I0, HC, order, R);
+    return (float)temp;
+}
+
+/* topozeroMethods.f:123-247 wrappers (window checks -> BADVALUE) */
+float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x, double f_y, int nx, int ny)
+{
+    double dx = i_x + f_x, dy = i_y + f_y;
+    switch (method) {
+    case ORC_BILINEAR: /* :123-147 */
+        if ((i_x < 1) || (i_x >= nx)) return ORC_BADVALUE;
+        if ((i_y < 1) || (i_y >= ny)) return ORC_BADVALUE;
+        return (float)bilinear(dy, dx, dem, nx);
+    case ORC_BICUBIC: /* :149-172 */
+        if ((i_x < 2) || (i_x >= (nx - 1))) return ORC_BADVALUE;
+        if ((i_y < 2) || (i_y >= (ny - 1))) return ORC_BADVALUE;
+        return (float)bicubic(dy, dx, dem, nx);
+    case ORC_BIQUINTIC: /* :174-198 */
+        if ((i_x < 3) || (i_x >= (nx - 2))) return ORC_BADVALUE;
+        if ((i_y < 3) || (i_y >= (ny - 2))) return ORC_BADVALUE;
+        return interp2dspline(6, dem, nx, ny, dy, dx);
+    case ORC_NEAREST: { /* :200-220 */
+        int ix = (int)lround(i_x + f_x), iy = (int)lround(i_y + f_y);
+        if ((ix < 1) || (ix > nx)) return ORC_BADVALUE;
+        if ((iy < 1) || (iy > ny)) return ORC_BADVALUE;
+        return DEM(ix, iy);
+    }
+    default:
+        return NAN; /* SINC / AKIMA not restated yet */
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* sort / search: components/zerodop/topozero/src/topozero.f90:910-963 */
+/* ------------------------------------------------------------------ */
+void orc_insertion_sort(double *a, double *b, double *c, int num)
+{
+    for (int i = 2; i <= num; i++) {
+        int j = i - 1;
+        double ta = a[i - 1], tb = b[i - 1], tc = c[i - 1];
+        while (j >= 1 && a[j - 1] > ta) {
+            a[j] = a[j - 1];
+            b[j] = b[j - 1];
+            c[j] = c[j - 1];
+            j--;
+        }
+        a[j] = ta;
+        b[j] = tb;
+        c[j] = tc;
+    }
+}
+
+/* returns the reference's 1-based index */
+int orc_binarysearch(const double *array, int length, double val)
+{
+    int left = 1, right = length, middle;
+    for (;;) {
+        if (left > right) break;
+        /* nint((left+right)/2.0): half rounds away from zero */
+        middle = (left + right + 1) / 2;
+        if (left == (right - 1)) return left;
+        else if (array[middle - 1] <= val) left = middle;
+        else if (array[middle - 1] > val) right = middle;
+        else return left; /* NaN key: the Fortran would spin forever; bail out */
+        if (left == right) return left; /* length==1 guard (Fortran would spin) */
+    }
+    return left;
+}
+
+/* ------------------------------------------------------------------ */
+/* topo: components/zerodop/topozero/src/topozero.f90:5-907             */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    double xyzsat[3], velsat[3], vhat[3], that[3], chat[3], nhat[3];
+    double llhsat[3];
+    double vmag, height, rcurv;
+    double mat[9], ov[3];
+} line_state;
+
+static void setup_line(const orc_topo_params *p, const orc_orbit *orb, double tline, line_state *s)
+{
+    /* :378-424 (stat ignored, :378) */
+    interp_orbit(p->orbitmethod, orb, tline, s->xyzsat, s->velsat);
+    v_unit(s->velsat, s->vhat);
+    s->vmag = v_norm(s->velsat);
+    orc_latlon(p->major, p->e2, s->xyzsat, s->llhsat, 2);
+    s->height = s->llhsat[2];
+    orc_tcnbasis(s->xyzsat, s->velsat, p->major, p->e2, s->that, s->chat, s->nhat);
+    s->rcurv = orc_radar_to_xyz(p->major, p->e2, s->llhsat[0], s->llhsat[1], p->peghdg, s->mat, s->ov);
+}
+
+/* range-sphere solve :495-519 ; returns delta and xyz */
+static inline void solve_xyz(const orc_topo_params *p, const line_state *s, double rng, double dopfact, double zsch,
+                             double *costheta_o, double *sintheta_o, double *delta, double *xyz)
+{
+    double aa = s->height + s->rcurv;
+    double bb = s->rcurv + zsch;
+    double costheta = 0.5 * ((aa / rng) + (rng / aa) - (bb / aa) * (bb / rng));
+    double sintheta = sqrt(1.0 - costheta * costheta);
+    double gamm = costheta * rng;
+    double alpha = (dopfact - gamm * v_dot(s->nhat, s->vhat)) / v_dot(s->vhat, s->that);
+    double beta = -p->ilrl * sqrt(rng * rng * sintheta * sintheta - alpha * alpha);
+    for (int i = 0; i < 3; i++) {
+        delta[i] = gamm * s->nhat[i] + alpha * s->that[i] + beta * s->chat[i];
+        xyz[i] = s->xyzsat[i] + delta[i];
+    }
+    *costheta_o = costheta;
+    *sintheta_o = sintheta;
+}
+
+int orc_topo(const orc_topo_params *p, const float *dem_full, const orc_orbit *orb,
+             const orc_poly2d *dopp, const orc_poly2d *slrng, const double *rho_image,
+             int line0, int nlines,
+             double *olat, double *olon, double *ohgt, float *olos, float *oinc, int8_t *omaskimg,
+             orc_topo_result *res, int nthreads)
+{
+    const int width = p->width, length = p->length;
+    const int owidth = 2 * width + 1; /* :134-135 */
+    const double pi = 4.0 * atan(1.0); /* fortranUtils.f90:38-41 */
+    const double r2d = 180.0 / pi;
+    const double MIN_H = -500.0, MAX_H = 9000.0, MARGIN = 0.15; /* topozeroState.f:74-75 */
+    const double hgts[2] = {MIN_H, MAX_H};
+    const int method = p->method;
+    double min_lat = 10000., max_lat = -10000., min_lon = 10000., max_lon = -10000.;
+    long long totalconv = 0, total_iters = 0;
+    int rc = 0;
+
+    if (p->orbitmethod == ORC_LEGENDRE ? orb->nvec < 9 : orb->nvec < 4) return -2; /* :104-131 'stop' */
+    if (method != ORC_BILINEAR && method != ORC_BICUBIC && method != ORC_BIQUINTIC && method != ORC_NEAREST) return -3;
+    if (!slrng && !rho_image) return -4;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+
+    double *lat = malloc(sizeof(double) * width), *lon = malloc(sizeof(double) * width);
+    double *z = malloc(sizeof(double) * width), *zsch = malloc(sizeof(double) * width);
+    double *rho = malloc(sizeof(double) * width), *dopline = malloc(sizeof(double) * width);
+    float *distance = malloc(sizeof(float) * width);
+    float *losang = malloc(sizeof(float) * 2 * width), *incang = malloc(sizeof(float) * 2 * width);
+    float *elevang = malloc(sizeof(float) * width);
+    int *converge = malloc(sizeof(int) * width);
+    int8_t *mask = NULL, *omask = NULL;
+    double *orng = NULL, *ctrack = NULL, *oview = NULL;
+    if (omaskimg) {
+        omask = malloc(owidth);
+        mask = malloc(width);
+        orng = malloc(sizeof(double) * owidth);
+        ctrack = malloc(sizeof(double) * owidth);
+        oview = malloc(sizeof(double) * owidth);
+    }
+    float *dem = NULL;
+
+    /* ---- bbox of interest :192-263 ---- */
+    line_state st;
+    for (int pixel = 1; pixel <= width; pixel++) { /* getLine(..., line=1) */
+        dopline[pixel - 1] = orc_eval_poly2d(dopp, 0.0, (double)(pixel - 1));
+        rho[pixel - 1] = rho_image ? rho_image[pixel - 1] : orc_eval_poly2d(slrng, 0.0, (double)(pixel - 1));
+    }
+    for (int line = 1; line <= 2; line++) {
+        double tline = p->t0 + (line - 1) * p->nazlooks * (length - 1.0) / p->prf;
+        double xs[3], vs[3];
+        int stat = interp_orbit(p->orbitmethod, orb, tline, xs, vs);
+        if (stat != 0) break; /* :204-207 prints and exits the loop */
+        setup_line(p, orb, tline, &st);
+        for (int ind = 1; ind <= 2; ind++) {
+            int pixel = (ind - 1) * (width - 1) + 1;
+            double rng = rho[pixel - 1];
+            double dopfact = (0.5 * p->wvl * dopline[pixel - 1] / st.vmag) * rng;
+            for (int iter = 0; iter < 2; iter++) {
+                double llh[3];
+                if (rng <= (st.llhsat[2] - hgts[iter] + 1.0)) {
+                    llh[0] = st.llhsat[0]; llh[1] = st.llhsat[1]; llh[2] = st.llhsat[2];
+                } else {
+                    double ct, sn, delta[3], xyz[3];
+                    solve_xyz(p, &st, rng, dopfact, hgts[iter], &ct, &sn, delta, xyz);
+                    orc_latlon(p->major, p->e2, xyz, llh, 2);
+                }
+                min_lat = fmin(min_lat, llh[0] * r2d);
+                max_lat = fmax(max_lat, llh[0] * r2d);
+                min_lon = fmin(min_lon, llh[1] * r2d);
+                max_lon = fmax(max_lon, llh[1] * r2d);
+            }
+        }
+    }
+    min_lon -= MARGIN; max_lon += MARGIN; min_lat -= MARGIN; max_lat += MARGIN;
+
+    /* ---- usable part of the DEM :281-320 ---- */
+    double umin_lon = fmax(min_lon, p->firstlon);
+    double umax_lon = fmin(max_lon, p->firstlon + (p->idemwidth - 1) * p->deltalon);
+    double umax_lat = fmin(max_lat, p->firstlat);
+    double umin_lat = fmax(min_lat, p->firstlat + (p->idemlength - 1) * p->deltalat);
+    int ustartx = (int)((umin_lon - p->firstlon) / p->deltalon) + 1;
+    if (ustartx < 1) ustartx = 1;
+    int uendx = (int)((umax_lon - p->firstlon) / p->deltalon + 0.5) + 1;
+    if (uendx > p->idemwidth) uendx = p->idemwidth;
+    int ustarty = (int)((umax_lat - p->firstlat) / p->deltalat) + 1;
+    if (ustarty < 1) ustarty = 1;
+    int uendy = (int)((umin_lat - p->firstlat) / p->deltalat + 0.5) + 1;
+    if (uendy > p->idemlength) ustarty = p->idemlength; /* :314 typo kept */
+    const double ufirstlon = p->firstlon + p->deltalon * (ustartx - 1);
+    const double ufirstlat = p->firstlat + p->deltalat * (ustarty - 1);
+    const int udemwidth = uendx - ustartx + 1;
+    const int udemlength = uendy - ustarty + 1;
+    if (udemwidth < 2 || udemlength < 2 || uendy > p->idemlength) { rc = -5; goto done; }
+
+    /* ---- crop :333-345 ---- */
+    dem = malloc(sizeof(float) * (size_t)udemwidth * (size_t)udemlength);
+    float demmax = -INFINITY;
+    for (int j = 1; j <= udemlength; j++) {
+        const float *src = dem_full + (size_t)(j + ustarty - 2) * (size_t)p->idemwidth + (size_t)(ustartx - 1);
+        float *dst = dem + (size_t)(j - 1) * (size_t)udemwidth;
+        memcpy(dst, src, sizeof(float) * (size_t)udemwidth);
+        for (int i = 0; i < udemwidth; i++)
+            if (dst[i] > demmax) demmax = dst[i];
+    }
+    const int nx = udemwidth, ny = udemlength;
+    const float fny1 = (float)(udemlength - 1), fnx1 = (float)(udemwidth - 1);
+
+    min_lat = 10000.; max_lat = -10000.; min_lon = 10000.; max_lon = -10000.; /* :357-360 */
+
+    if (line0 < 0) line0 = 0;
+    if (nlines < 0 || line0 + nlines > length) nlines = length - line0;
+
+    for (int line = line0 + 1; line <= line0 + nlines; line++) { /* :365 */
+        const double tline = p->t0 + p->nazlooks * (line - 1.0) / p->prf; /* :371 */
+        setup_line(p, orb, tline, &st);
+        /* :406,414 sequential line reads of the polynomial accessors: row = line-1, col = pixel-1 */
+        for (int pixel = 1; pixel <= width; pixel++) {
+            dopline[pixel - 1] = orc_eval_poly2d(dopp, (double)(line - 1), (double)(pixel - 1));
+            rho[pixel - 1] = rho_image ? rho_image[(size_t)(line - 1) * width + pixel - 1]
+                                       : orc_eval_poly2d(slrng, (double)(line - 1), (double)(pixel - 1));
+        }
+        for (int i = 0; i < width; i++) { /* :425-436 */
+            converge[i] = 0;
+            z[i] = 0.;
+            zsch[i] = 0.;
+            lat[i] = ufirstlat + 0.5 * p->deltalat * udemlength;
+            lon[i] = ufirstlon + 0.05 * p->deltalon * udemwidth;
+        }
+
+        const int niter = p->numiter + p->extraiter + 1;
+        for (int iter = 1; iter <= niter; iter++) { /* :458 */
+            long long conv_here = 0, iters_here = 0;
+#pragma omp parallel for schedule(static) reduction(+ : conv_here, iters_here)
+            for (int pixel = 1; pixel <= width; pixel++) { /* :472-596 */
+                const int k = pixel - 1;
+                double rng = rho[k];
+                double dopfact = (0.5 * p->wvl * dopline[k] / st.vmag) * rng;
+                if (converge[k] == 0) {
+                    double llh_prev[3], xyz_prev[3], llh[3], xyz[3], delta[3], sch[3], ct, sn;
+                    iters_here++;
+                    llh_prev[0] = lat[k] / r2d;
+                    llh_prev[1] = lon[k] / r2d;
+                    llh_prev[2] = z[k];
+                    solve_xyz(p, &st, rng, dopfact, zsch[k], &ct, &sn, delta, xyz);
+                    orc_latlon(p->major, p->e2, xyz, llh, 2);
+                    lat[k] = llh[0] * r2d;
+                    lon[k] = llh[1] * r2d;
+                    float demlat = (float)((lat[k] - ufirstlat) / p->deltalat + 1);
+                    float demlon = (float)((lon[k] - ufirstlon) / p->deltalon + 1);
+                    if (demlat < 1) demlat = 1;
+                    if (demlat > fny1) demlat = fny1;
+                    if (demlon < 1) demlon = 1;
+                    if (demlon > fnx1) demlon = fnx1;
+                    int idemlat = (int)demlat, idemlon = (int)demlon;
+                    double fraclat = (double)(float)(demlat - (float)idemlat);
+                    double fraclon = (double)(float)(demlon - (float)idemlon);
+                    z[k] = orc_interp_dem(method, dem, idemlon, idemlat, fraclon, fraclat, nx, ny);
+                    if (z[k] < -500.0) z[k] = -500.0;
+                    llh[0] = lat[k] / r2d;
+                    llh[1] = lon[k] / r2d;
+                    llh[2] = z[k];
+                    orc_latlon(p->major, p->e2, xyz, llh, 1);
+                    orc_xyz_to_sch(st.mat, st.ov, st.rcurv, xyz, sch);
+                    zsch[k] = sch[2];
+                    distance[k] = (float)(sqrt((xyz[0] - st.xyzsat[0]) * (xyz[0] - st.xyzsat[0]) +
+                                               (xyz[1] - st.xyzsat[1]) * (xyz[1] - st.xyzsat[1]) +
+                                               (xyz[2] - st.xyzsat[2]) * (xyz[2] - st.xyzsat[2])) - rng);
+                    if (fabs((double)distance[k]) <= p->thresh) {
+                        zsch[k] = sch[2];
+                        converge[k] = 1;
+                        conv_here++;
+                    } else if (iter > (p->numiter + 1)) { /* :572-593 */
+                        orc_latlon(p->major, p->e2, xyz_prev, llh_prev, 1);
+                        xyz[0] = 0.5 * (xyz_prev[0] + xyz[0]);
+                        xyz[1] = 0.5 * (xyz_prev[1] + xyz[1]);
+                        xyz[2] = 0.5 * (xyz_prev[2] + xyz[2]);
+                        orc_latlon(p->major, p->e2, xyz, llh, 2);
+                        lat[k] = llh[0] * r2d;
+                        lon[k] = llh[1] * r2d;
+                        z[k] = llh[2];
+                        orc_xyz_to_sch(st.mat, st.ov, st.rcurv, xyz, sch);
+                        zsch[k] = sch[2];
+                        distance[k] = (float)(sqrt((xyz[0] - st.xyzsat[0]) * (xyz[0] - st.xyzsat[0]) +
+                                                   (xyz[1] - st.xyzsat[1]) * (xyz[1] - st.xyzsat[1]) +
+                                                   (xyz[2] - st.xyzsat[2]) * (xyz[2] - st.xyzsat[2])) - rng);
+                    }
+                }
+            }
+            totalconv += conv_here;
+            total_iters += iters_here;
+        }
+
+        /* ---- final computation :607-708 ---- */
+#pragma omp parallel for schedule(static)
+        for (int pixel = 1; pixel <= width; pixel++) {
+            const int k = pixel - 1;
+            double rng = rho[k];
+            double dopfact = (0.5 * p->wvl * dopline[k] / st.vmag) * rng;
+            double llh[3], xyz[3], delta[3], costheta, sintheta;
+            solve_xyz(p, &st, rng, dopfact, zsch[k], &costheta, &sintheta, delta, xyz);
+            orc_latlon(p->major, p->e2, xyz, llh, 2);
+            lat[k] = llh[0] * r2d;
+            lon[k] = llh[1] * r2d;
+            z[k] = llh[2];
+            distance[k] = (float)(sqrt((xyz[0] - st.xyzsat[0]) * (xyz[0] - st.xyzsat[0]) +
+                                       (xyz[1] - st.xyzsat[1]) * (xyz[1] - st.xyzsat[1]) +
+                                       (xyz[2] - st.xyzsat[2]) * (xyz[2] - st.xyzsat[2])) - rng);
+            double enumat[9], enu[3];
+            orc_enubasis(llh[0], llh[1], enumat);
+            /* xyz2enu = transpose(enumat); enu = matmul(xyz2enu, delta) */
+            for (int i = 0; i < 3; i++)
+                enu[i] = enumat[0 * 3 + i] * delta[0] + enumat[1 * 3 + i] * delta[1] + enumat[2 * 3 + i] * delta[2];
+            double cosalpha = fabs(enu[2]) / v_norm(enu);
+            losang[2 * k] = (float)(acos(cosalpha) * r2d);
+            losang[2 * k + 1] = (float)((atan2(-enu[1], -enu[0]) - 0.5 * pi) * r2d);
+            elevang[k] = (float)(acos(costheta) * r2d);
+            zsch[k] = rng * sintheta; /* ctrack stored in zsch :662 */
+
+            float demlat = (float)((lat[k] - ufirstlat) / p->deltalat + 1);
+            float demlon = (float)((lon[k] - ufirstlon) / p->deltalon + 1);
+            if (demlat < 2) demlat = 2;
+            if (demlat > fny1) demlat = fny1;
+            if (demlon < 2) demlon = 2;
+            if (demlon > fnx1) demlon = fnx1;
+            int idemlat = (int)demlat, idemlon = (int)demlon;
+            double fraclat = (double)(float)(demlat - (float)idemlat);
+            double fraclon = (double)(float)(demlon - (float)idemlon);
+            double aa = orc_interp_dem(method, dem, idemlon - 1, idemlat, fraclon, fraclat, nx, ny);
+            double bb = orc_interp_dem(method, dem, idemlon + 1, idemlat, fraclon, fraclat, nx, ny);
+            double gamm = lat[k] / r2d;
+            double alpha = (bb - aa) * r2d / (2.0 * orc_reast(p->major, p->e2, gamm) * p->deltalon);
+            aa = orc_interp_dem(method, dem, idemlon, idemlat - 1, fraclon, fraclat, nx, ny);
+            bb = orc_interp_dem(method, dem, idemlon, idemlat + 1, fraclon, fraclat, nx, ny);
+            double beta = (bb - aa) * r2d / (2.0 * orc_rnorth(p->major, p->e2, gamm) * p->deltalat);
+            double en = v_norm(enu);
+            enu[0] = enu[0] / en; enu[1] = enu[1] / en; enu[2] = enu[2] / en;
+            costheta = (enu[0] * alpha + enu[1] * beta - enu[2]) / sqrt(1.0 + alpha * alpha + beta * beta);
+            incang[2 * k + 1] = (float)(acos(costheta) * r2d);
+            double n_img[3], n_img_enu[3], n_trg_enu[3], tmp[3];
+            v_cross(delta, st.velsat, n_img);
+            v_unit(n_img, n_img);
+            for (int i = 0; i < 3; i++) tmp[i] = -p->ilrl * n_img[i];
+            for (int i = 0; i < 3; i++)
+                n_img_enu[i] = enumat[0 * 3 + i] * tmp[0] + enumat[1 * 3 + i] * tmp[1] + enumat[2 * 3 + i] * tmp[2];
+            n_trg_enu[0] = -alpha; n_trg_enu[1] = -beta; n_trg_enu[2] = 1.0;
+            double cospsi = v_dot(n_trg_enu, n_img_enu) / (v_norm(n_trg_enu) * v_norm(n_img_enu));
+            incang[2 * k] = (float)(acos(cospsi) * r2d);
+        }
+
+        /* :712-726 */
+        for (int i = 0; i < width; i++) {
+            if (lat[i] < min_lat) min_lat = lat[i];
+            if (lat[i] > max_lat) max_lat = lat[i];
+            if (lon[i] < min_lon) min_lon = lon[i];
+            if (lon[i] > max_lon) max_lon = lon[i];
+        }
+        const size_t orow = (size_t)(line - 1 - line0);
+        memcpy(olat + orow * width, lat, sizeof(double) * width);
+        memcpy(olon + orow * width, lon, sizeof(double) * width);
+        memcpy(ohgt + orow * width, z, sizeof(double) * width);
+        if (olos)
+            for (int i = 0; i < width; i++) { /* BIL on disk: BILAccessor.cpp:11-37 */
+                olos[orow * 2 * width + i] = losang[2 * i];
+                olos[orow * 2 * width + width + i] = losang[2 * i + 1];
+            }
+        if (oinc)
+            for (int i = 0; i < width; i++) {
+                oinc[orow * 2 * width + i] = incang[2 * i];
+                oinc[orow * 2 * width + width + i] = incang[2 * i + 1];
+            }
+
+        /* ---- layover / shadow mask :729-880 ---- */
+        if (omaskimg) {
+            double cmin = zsch[0], cmax = zsch[0];
+            for (int i = 1; i < width; i++) {
+                if (zsch[i] < cmin) cmin = zsch[i];
+                if (zsch[i] > cmax) cmax = zsch[i];
+            }
+            const double ctrackmin = cmin - demmax, ctrackmax = cmax + demmax;
+            const double dctrack = (ctrackmax - ctrackmin) / (owidth - 1.0);
+            orc_insertion_sort(zsch, lat, lon, width); /* :735 */
+#pragma omp parallel for schedule(static)
+            for (int pixel = 1; pixel <= owidth; pixel++) { /* :745-782 */
+                double aa = ctrackmin + (pixel - 1) * dctrack;
+                ctrack[pixel - 1] = aa;
+                int it = orc_binarysearch(zsch, width, aa);
+                if (it == width) it = width - 1;
+                if (it == 0) it = 1;
+                double fraclat = (aa - zsch[it - 1]) / (zsch[it] - zsch[it - 1]);
+                float demlat = (float)(lat[it - 1] + fraclat * (lat[it] - lat[it - 1])); /* real*4 :755 */
+                float demlon = (float)(lon[it - 1] + fraclat * (lon[it] - lon[it - 1]));
+                double llh[3], xyz[3];
+                llh[0] = demlat / r2d;
+                llh[1] = demlon / r2d;
+                demlat = (float)((demlat - ufirstlat) / p->deltalat + 1);
+                demlon = (float)((demlon - ufirstlon) / p->deltalon + 1);
+                if (demlat < 2) demlat = 2;
+                if (demlat > fny1) demlat = fny1;
+                if (demlon < 2) demlon = 2;
+                if (demlon > fnx1) demlon = fnx1;
+                int idemlat = (int)demlat, idemlon = (int)demlon;
+                fraclat = (double)(float)(demlat - (float)idemlat);
+                double fraclon = (double)(float)(demlon - (float)idemlon);
+                llh[2] = orc_interp_dem(method, dem, idemlon, idemlat, fraclon, fraclat, nx, ny);
+                orc_latlon(p->major, p->e2, xyz, llh, 1);
+                xyz[0] = xyz[0] - st.xyzsat[0]; xyz[1] = xyz[1] - st.xyzsat[1]; xyz[2] = xyz[2] - st.xyzsat[2];
+                double bb = v_norm(xyz);
+                orng[pixel - 1] = bb;
+                aa = fabs(st.nhat[0] * xyz[0] + st.nhat[1] * xyz[1] + st.nhat[2] * xyz[2]);
+                oview[pixel - 1] = acos(aa / bb) * r2d;
+            }
+            orc_insertion_sort(orng, ctrack, oview, owidth); /* :787 */
+            memset(mask, 0, width);
+            memset(omask, 0, owidth);
+            double aa = elevang[0]; /* :791-809 shadow */
+            for (int pixel = 2; pixel <= width; pixel++) {
+                double bb = elevang[pixel - 1];
+                if (bb <= aa) mask[pixel - 1] = 1; else aa = bb;
+            }
+            aa = elevang[width - 1];
+            for (int pixel = width - 1; pixel >= 1; pixel--) {
+                double bb = elevang[pixel - 1];
+                if (bb >= aa) mask[pixel - 1] = 1; else aa = bb;
+            }
+            aa = ctrack[0]; /* :834-852 layover; forward loop bound is width (not owidth) as in the reference */
+            for (int pixel = 2; pixel <= width; pixel++) {
+                double bb = ctrack[pixel - 1];
+                if ((bb <= aa) && (omask[pixel - 1] < 2)) omask[pixel - 1] = omask[pixel - 1] + 2; else aa = bb;
+            }
+            aa = ctrack[owidth - 1];
+            for (int pixel = owidth - 1; pixel >= 1; pixel--) {
+                double bb = ctrack[pixel - 1];
+                if ((bb >= aa) && (omask[pixel - 1] < 2)) omask[pixel - 1] = omask[pixel - 1] + 2; else aa = bb;
+            }
+            for (int pixel = 1; pixel <= owidth; pixel++) { /* :855-865 */
+                if (omask[pixel - 1] > 0) {
+                    int id = orc_binarysearch(rho, width, orng[pixel - 1]);
+                    if ((id >= 1) && (id <= width))
+                        if (mask[id - 1] < omask[pixel - 1]) mask[id - 1] = mask[id - 1] + omask[pixel - 1];
+                }
+            }
+            memcpy(omaskimg + orow * width, mask, width);
+        }
+    }
+
+    if (res) {
+        res->min_lat = min_lat; res->max_lat = max_lat; res->min_lon = min_lon; res->max_lon = max_lon;
+        res->totalconv = totalconv; res->total_iters = total_iters;
+        res->ustartx = ustartx; res->ustarty = ustarty; res->udemwidth = udemwidth; res->udemlength = udemlength;
+        res->ufirstlat = ufirstlat; res->ufirstlon = ufirstlon; res->demmax = demmax;
+    }
+done:
+    free(lat); free(lon); free(z); free(zsch); free(rho); free(dopline); free(distance);
+    free(losang); free(incang); free(elevang); free(converge);
+    free(mask); free(omask); free(orng); free(ctrack); free(oview); free(dem);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* geo2rdr: components/zerodop/geo2rdr/src/geo2rdr.f90:1-423            */
+/* ------------------------------------------------------------------ */
+int orc_geo2rdr(const orc_geo_params *p, const double *latimg, const double *lonimg, const double *hgtimg,
+                const orc_orbit *orb, const orc_poly1d *dopAcc,
+                int line0, int nlines,
+                double *oazt, double *orgm, double *oazoff, double *orgoff,
+                orc_geo_result *res, int nthreads)
+{
+    const double pi = 4.0 * atan(1.0);
+    const double sol = 299792458.0; /* fortranUtils.f90:43-46 */
+    const double deg2rad = pi / 180.0;
+    const float BAD_VALUE = -999999.0f; /* :59-60 */
+    const int demwidth = p->demwidth;
+
+    if (p->orbitmethod == ORC_LEGENDRE ? orb->nvec < 9 : orb->nvec < 4) return -2;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    /* :118-133 */
+    const double tstart = p->t0;
+    const double dtaz = p->nazlooks / p->prf;
+    const double tend = p->t0 + (p->length - 1) * dtaz;
+    const double tmid = 0.5 * (tstart + tend);
+    const double rngstart = p->rho0;
+    const double dmrg = p->nrnglooks * p->drho;
+    const double rngend = p->rho0 + (p->width - 1) * dmrg;
+
+    /* doppler polynomials :161-189 */
+    double fd_c[64], fdd_c[64];
+    if (dopAcc->order > 62) return -6;
+    orc_poly1d fdvsrng = {dopAcc->order, p->rho0 + dopAcc->mean * p->drho, dopAcc->norm * p->drho, fd_c};
+    for (int k = 1; k <= dopAcc->order + 1; k++) {
+        double temp = dopAcc->coeffs[k - 1];
+        temp = temp * p->prf;
+        fd_c[k - 1] = temp;
+    }
+    orc_poly1d fddotvsrng;
+    fddotvsrng.coeffs = fdd_c;
+    if (fdvsrng.order == 0) {
+        fddotvsrng.order = 0;
+        fddotvsrng.mean = 0.0; /* initPoly1D leaves mean/norm unset; 0-order eval ignores xval */
+        fddotvsrng.norm = 1.0;
+        fdd_c[0] = 0.0;
+    } else {
+        fddotvsrng.order = fdvsrng.order - 1;
+        fddotvsrng.mean = fdvsrng.mean;
+        fddotvsrng.norm = fdvsrng.norm;
+        for (int k = 1; k <= dopAcc->order; k++) {
+            double temp = fd_c[k];
+            temp = k * temp / fdvsrng.norm;
+            fdd_c[k - 1] = temp;
+        }
+    }
+
+    /* :194-208 */
+    double xyz_mid[3], vel_mid[3], acc_mid[3];
+    if (interp_orbit(p->orbitmethod, orb, tmid, xyz_mid, vel_mid) != 0) return -7;
+    if (orc_compute_acceleration(orb, tmid, acc_mid) != 0) return -8;
+
+    if (line0 < 0) line0 = 0;
+    if (nlines < 0 || line0 + nlines > p->demlength) nlines = p->demlength - line0;
+
+    long long numOutside = 0, cnt = 0, conv = 0, total_iters = 0;
+    for (int line = line0 + 1; line <= line0 + nlines; line++) { /* :215 */
+        const size_t row = (size_t)(line - 1) * demwidth;
+        const size_t orow = (size_t)(line - 1 - line0) * demwidth;
+#pragma omp parallel for schedule(static) reduction(+ : numOutside, cnt, conv, total_iters)
+        for (int pixel = 1; pixel <= demwidth; pixel++) {
+            double azt = BAD_VALUE, rgm = BAD_VALUE, rgoff = BAD_VALUE, azoff = BAD_VALUE; /* :217-221 */
+            double llh[3], xyz[3], satx[3], satv[3], sata[3], dr[3];
+            double tline, tprev = 0, rngpix = 0;
+            int outside = 0;
+            llh[0] = latimg[row + pixel - 1] * deg2rad;
+            llh[1] = lonimg[row + pixel - 1] * deg2rad;
+            llh[2] = hgtimg[row + pixel - 1];
+            orc_latlon(p->major, p->e2, xyz, llh, 1);
+            tline = tmid;
+            for (int i = 0; i < 3; i++) { satx[i] = xyz_mid[i]; satv[i] = vel_mid[i]; sata[i] = acc_mid[i]; }
+            for (int k = 1; k <= 51; k++) { /* :259-305 */
+                total_iters++;
+                tprev = tline;
+                for (int i = 0; i < 3; i++) dr[i] = xyz[i] - satx[i];
+                rngpix = v_norm(dr);
+                double dopfact = v_dot(dr, satv);
+                double fdop = 0.5 * p->wvl * orc_eval_poly1d(&fdvsrng, rngpix);
+                double fdopder = 0.5 * p->wvl * orc_eval_poly1d(&fddotvsrng, rngpix);
+                double fn = dopfact - fdop * rngpix;
+                double c1 = (0.0 * v_dot(sata, dr) - v_dot(satv, satv));
+                double c2 = (fdop / rngpix + fdopder);
+                double fnprime = c1 + c2 * dopfact;
+                tline = tline - fn / fnprime;
+                int stat = interp_orbit(p->orbitmethod, orb, tline, satx, satv);
+                if (stat != 0) {
+                    tline = BAD_VALUE;
+                    rngpix = BAD_VALUE;
+                    break;
+                }
+                if (fabs(tline - tprev) < 5.0e-9) {
+                    conv++;
+                    break;
+                }
+            }
+            if (tline < tstart) outside = 1;
+            else if (tline > tend) outside = 1;
+            else {
+                for (int i = 0; i < 3; i++) dr[i] = xyz[i] - satx[i];
+                rngpix = v_norm(dr);
+                if (rngpix < rngstart) outside = 1;
+                else if (rngpix > rngend) outside = 1;
+                else if (p->bistatic) { /* :331-368 */
+                    tline = tline + 2.0 * rngpix / sol;
+                    if (tline < tstart) outside = 1;
+                    else if (tline > tend) outside = 1;
+                    else {
+                        int stat = interp_orbit(p->orbitmethod, orb, tline, satx, satv);
+                        if (stat != 0) { tline = BAD_VALUE; rngpix = BAD_VALUE; }
+                        if (tline == BAD_VALUE) outside = 1;
+                        else {
+                            for (int i = 0; i < 3; i++) dr[i] = xyz[i] - satx[i];
+                            rngpix = v_norm(dr);
+                            if (rngpix < rngstart) outside = 1;
+                            else if (rngpix > rngend) outside = 1;
+                        }
+                    }
+                }
+            }
+            if (outside) numOutside++;
+            else { /* :370-376 */
+                cnt++;
+                rgm = rngpix;
+                azt = tline;
+                rgoff = ((rngpix - rngstart) / dmrg) - 1.0 * (pixel - 1);
+                azoff = ((tline - tstart) / dtaz) - 1.0 * (line - 1);
+            }
+            if (oazt) oazt[orow + pixel - 1] = azt;
+            if (orgm) orgm[orow + pixel - 1] = rgm;
+            if (oazoff) oazoff[orow + pixel - 1] = azoff;
+            if (orgoff) orgoff[orow + pixel - 1] = rgoff;
+        }
+    }
+    if (res) {
+        res->num_outside = numOutside; res->num_valid = cnt; res->num_conv = conv; res->total_iters = total_iters;
+    }
+    return 0;
+}

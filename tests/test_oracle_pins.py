@@ -1,0 +1,229 @@
+"""Pin the CPU oracle (oracle/zerodop_oracle.c) before it is trusted as the checker.
+
+Three independent anchors:
+ 1. known answers held by the reference's own tests (test_ellipsoid.py, geometry/test/test.c, test_orbit.py);
+ 2. the reference's own C sources compiled unchanged into oracle/_ref (bit-exact comparison, skipped where
+    /root/reference was never mounted and no prebuilt _ref exists);
+ 3. golden vectors produced by importing the reference's Python Orbit/Ellipsoid code
+    (tests/golden/make_golden.py -> ref_python_vectors.json), including whole-path single-point
+    rdr2geo / geo2rdr solutions.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+A = 6378137.0
+E2 = 0.0066943799901
+
+
+# ---------------------------------------------------------------- 1. reference known answers
+def test_kat_llh_to_xyz():
+    # test/components/isceobj/Planet/test_ellipsoid.py:35-40 (assertAlmostEqual places=2)
+    xyz = orc.latlon_to_xyz([math.radians(40.15), math.radians(-104.97), 2119.0], A, E2)
+    ans = [-1261499.8108277766, -4717861.0677524200, 4092096.6400047773]
+    assert np.allclose(xyz, ans, atol=5e-3)
+    llh = orc.xyz_to_latlon(xyz, A, E2)
+    assert abs(math.degrees(llh[0]) - 40.15) < 1e-11 and abs(math.degrees(llh[1]) + 104.97) < 1e-11
+    assert abs(llh[2] - 2119.0) < 1e-8
+
+
+def test_kat_radii():
+    # components/isceobj/Util/Library/geometry/test/test.c:30-82 and test_ellipsoid.py:48-57
+    L = orc.lib()
+    lat = math.radians(40.0)
+    assert abs(L.orc_reast(A, E2, lat) - 6386976.165976) < 1e-3
+    assert abs(L.orc_rnorth(A, E2, lat) - 6361815.825934) < 1e-3
+    assert abs(L.orc_rdir(A, E2, math.radians(90.0), lat) - 6386976.165976) < 1e-3
+    assert abs(L.orc_rdir(A, E2, 0.0, lat) - 6361815.825934) < 1e-3
+
+
+def _toy_orbit(quadratic):
+    # components/isceobj/Orbit/test/test_orbit.py:21-56: 10 vectors, 60 s apart
+    t = np.arange(10) * 60.0
+    if not quadratic:
+        pos = np.array([[1.0 + i, 2.0 + i, 3.0 + i] for i in range(10)])
+        vel = np.full((10, 3), 1.0 / 60.0)
+    else:
+        rate = 0.1
+        pos = np.array([[1.0 + rate * i * i, 2.0 + rate * i * i, 3.0 + rate * i * i] for i in range(10)])
+        vel = np.array([[2.0 * rate * i / 60.0] * 3 for i in range(10)])
+    return orc.Orbit(t, pos, vel)
+
+
+def test_kat_toy_orbits():
+    # test_orbit.py:72-99
+    stat, p, _ = _toy_orbit(False).interp(90.0, "HERMITE")
+    assert stat == 0 and np.allclose(p, [2.5, 3.5, 4.5], atol=1e-5)
+    stat, p, _ = _toy_orbit(True).interp(90.0, "HERMITE")
+    assert np.allclose(p, [1.225, 2.225, 3.225], atol=1e-5)
+    stat, p, _ = _toy_orbit(False).interp(210.0, "LEGENDRE")
+    assert np.allclose(p, [4.5, 5.5, 6.5], atol=1e-5)
+    stat, p, _ = _toy_orbit(True).interp(210.0, "LEGENDRE")
+    assert np.allclose(p, [2.225, 3.225, 4.225], atol=1e-5)
+    # outside the span: Hermite/Legendre still extrapolate but flag stat=1 (orbit.c:224-233)
+    stat, p, _ = _toy_orbit(False).interp(-5.0, "HERMITE")
+    assert stat == 1 and np.all(np.isfinite(p))
+    stat, _, _ = _toy_orbit(False).interp(-5.0, "SCH")
+    assert stat == 1
+
+
+# ---------------------------------------------------------------- 2. reference C sources, bit-exact
+class _COrbit(C.Structure):
+    # components/isceobj/Util/Library/orbit/include/orbit.h:30-38
+    _fields_ = [("nVectors", C.c_int), ("yyyymmdd", C.c_char * 256), ("position", C.POINTER(C.c_double)),
+                ("velocity", C.POINTER(C.c_double)), ("UTCtime", C.POINTER(C.c_double)), ("basis", C.c_int)]
+
+
+class _CPoly2d(C.Structure):
+    _fields_ = [("rangeOrder", C.c_int), ("azimuthOrder", C.c_int), ("meanRange", C.c_double),
+                ("meanAzimuth", C.c_double), ("normRange", C.c_double), ("normAzimuth", C.c_double),
+                ("coeffs", C.POINTER(C.c_double))]
+
+
+class _CPoly1d(C.Structure):
+    _fields_ = [("order", C.c_int), ("mean", C.c_double), ("norm", C.c_double), ("coeffs", C.POINTER(C.c_double))]
+
+
+@pytest.fixture(scope="module")
+def reflib():
+    orc.build()
+    if not os.path.exists(orc.REF_LIB_PATH):
+        pytest.skip("oracle/_ref not built (reference tree never mounted here)")
+    L = C.CDLL(orc.REF_LIB_PATH)
+    for f in (L.interpolateWGS84Orbit, L.interpolateLegendreOrbit, L.interpolateSCHOrbit):
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(_COrbit), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.computeAcceleration.restype = C.c_int
+    L.computeAcceleration.argtypes = [C.POINTER(_COrbit), C.c_double, C.POINTER(C.c_double)]
+    L.evalPoly2d.restype = C.c_double
+    L.evalPoly2d.argtypes = [C.POINTER(_CPoly2d), C.c_double, C.c_double]
+    L.evalPoly1d.restype = C.c_double
+    L.evalPoly1d.argtypes = [C.POINTER(_CPoly1d), C.c_double]
+    return L
+
+
+def test_orbit_bit_exact_vs_reference_c(reflib, golden):
+    rows = np.array(golden["orbit_rsc"])
+    o = orc.Orbit(rows[:, 0], rows[:, 1:4], rows[:, 4:7])
+    co = _COrbit(len(rows), b"", o.pos.ctypes.data_as(C.POINTER(C.c_double)),
+                 o.vel.ctypes.data_as(C.POINTER(C.c_double)), o.t.ctypes.data_as(C.POINTER(C.c_double)), 1)
+    rng = np.random.default_rng(1)
+    ts = np.concatenate([rng.uniform(59020.0, 59180.0, 400), rows[:, 0], [59030.0 - 1e-9, 59170.0 + 1e-9]])
+    for name, fn in (("HERMITE", reflib.interpolateWGS84Orbit), ("LEGENDRE", reflib.interpolateLegendreOrbit),
+                     ("SCH", reflib.interpolateSCHOrbit)):
+        for tq in ts:
+            p = np.zeros(3)
+            v = np.zeros(3)
+            s_ref = fn(C.byref(co), float(tq), p.ctypes.data_as(C.POINTER(C.c_double)),
+                       v.ctypes.data_as(C.POINTER(C.c_double)))
+            s, po, vo = o.interp(tq, name)
+            assert s == s_ref, (name, tq)
+            if name == "SCH" and s_ref != 0:
+                continue  # outputs untouched by the reference in that case
+            assert np.array_equal(p, po) and np.array_equal(v, vo), (name, tq)
+    for tq in ts[:50]:
+        a = np.zeros(3)
+        s_ref = reflib.computeAcceleration(C.byref(co), float(tq), a.ctypes.data_as(C.POINTER(C.c_double)))
+        s, ao = o.acceleration(tq)
+        assert s == s_ref
+        if s == 0:
+            assert np.array_equal(a, ao)
+
+
+def test_poly_bit_exact_vs_reference_c(reflib):
+    rng = np.random.default_rng(2)
+    for az_o, rg_o in [(0, 0), (0, 1), (0, 3), (2, 3), (3, 2)]:
+        c = rng.normal(size=(az_o + 1, rg_o + 1)) * 10.0 ** rng.integers(-8, 3, size=(az_o + 1, rg_o + 1))
+        mine = orc.Poly2D(c, 1200.5, 300.25, 2500.0, 700.0)
+        ref = _CPoly2d(rg_o, az_o, 1200.5, 300.25, 2500.0, 700.0, mine.coeffs.ctypes.data_as(C.POINTER(C.c_double)))
+        for _ in range(100):
+            a, r = rng.uniform(0, 1500), rng.uniform(0, 25000)
+            assert mine(a, r) == reflib.evalPoly2d(C.byref(ref), a, r)
+    for order in (0, 1, 3, 5):
+        c = rng.normal(size=order + 1)
+        mine = orc.Poly1D(c, 850000.0, 20000.0)
+        ref = _CPoly1d(order, 850000.0, 20000.0, mine.coeffs.ctypes.data_as(C.POINTER(C.c_double)))
+        for _ in range(100):
+            x = rng.uniform(8e5, 9e5)
+            assert mine(x) == reflib.evalPoly1d(C.byref(ref), x)
+
+
+# ---------------------------------------------------------------- 3. golden vectors from the reference Python
+def test_golden_ellipsoid(golden):
+    a, e2 = golden["ellipsoid"]["a"], golden["ellipsoid"]["e2"]
+    assert a == A and e2 == E2
+    for e in golden["llh_to_xyz"]:
+        llh = e["llh"]
+        xyz = orc.latlon_to_xyz([math.radians(llh[0]), math.radians(llh[1]), llh[2]], a, e2)
+        assert np.allclose(xyz, e["xyz"], rtol=0, atol=2e-8)
+    for e in golden["xyz_to_llh"]:
+        llh = orc.xyz_to_latlon(e["xyz"], a, e2)
+        assert abs(math.degrees(llh[0]) - e["llh"][0]) < 1e-12
+        assert abs(math.degrees(llh[1]) - e["llh"][1]) < 1e-12
+        assert abs(llh[2] - e["llh"][2]) < 2e-8
+    L = orc.lib()
+    for e in golden["radii"]:
+        lat = math.radians(e["lat_deg"])
+        assert abs(L.orc_reast(a, e2, lat) - e["east"]) < 1e-7
+        assert abs(L.orc_rnorth(a, e2, lat) - e["north"]) < 1e-7
+        assert abs(L.orc_rdir(a, e2, math.radians(e["hdg_deg"]), lat) - e["dir"]) < 1e-7
+
+
+def test_golden_orbit_interp(golden):
+    rows = np.array(golden["orbit_rsc"])
+    o = orc.Orbit(rows[:, 0], rows[:, 1:4], rows[:, 4:7])
+    n = 0
+    for e in golden["interp"]:
+        if e["hermite"] is not None:
+            s, p, v = o.interp(e["t"], "HERMITE")
+            # the Python path feeds times relative to the first vector: agreement is to rounding, not bit-exact
+            assert np.allclose(p, e["hermite"]["pos"], rtol=0, atol=5e-8)
+            assert np.allclose(v, e["hermite"]["vel"], rtol=0, atol=1e-8)
+            n += 1
+        if e["legendre"] is not None:
+            s, p, v = o.interp(e["t"], "LEGENDRE")
+            # Orbit.py's Legendre picks its 9-vector window differently from orbit.c:260-267 (which the oracle
+            # follows bit-exactly, see test above), so the two agree only to the interpolation error (~1e-4 m)
+            assert np.allclose(p, e["legendre"]["pos"], rtol=0, atol=1e-3)
+            assert np.allclose(v, e["legendre"]["vel"], rtol=0, atol=1e-5)
+            n += 1
+    assert n >= 10
+
+
+def _flat_dem(lat0, lon0, h, half=0.6, spacing=1.0 / 1200):
+    n = int(2 * half / spacing) + 1
+    dem = np.full((n, n), h, np.float32)
+    return dem, lat0 + half, lon0 - half, -spacing, spacing
+
+
+def test_golden_rdr2geo_and_geo2rdr(golden):
+    """Whole-path pin: the reference's own single-point rdr2geo (Orbit.py:834-916) solves the same range-sphere /
+    SCH-height iteration as topozero.f90 at a constant height; geo2rdr (Orbit.py:1000-1057) solves the same
+    zero-Doppler Newton as geo2rdr.f90 (to the 1 us resolution of Python datetimes)."""
+    rows = np.array(golden["orbit_rsc"])
+    for e in golden["rdr2geo"]:
+        h = e["height"]
+        dem, flat, flon, dlat, dlon = _flat_dem(e["llh"][0], e["llh"][1], h)
+        for method in ("BILINEAR", "BICUBIC", "BIQUINTIC", "NEAREST"):
+            out = orc.topo(dem=dem, first_lat=flat, first_lon=flon, delta_lat=dlat, delta_lon=dlon,
+                           orbit_t=rows[:, 0], orbit_pos=rows[:, 1:4], orbit_vel=rows[:, 4:7], length=2, width=2,
+                           r0=e["rng"], dr=1.0, prf=1000.0, t0=e["t"], wvl=0.056, side=e["side"],
+                           peg_heading=math.radians(e["hdg_deg"]), thresh=1e-5, dem_method=method,
+                           want_mask=False)
+            assert abs(out["lat"][0, 0] - e["llh"][0]) < 2e-10, (method, out["lat"][0, 0], e["llh"][0])
+            assert abs(out["lon"][0, 0] - e["llh"][1]) < 2e-10
+            assert abs(out["hgt"][0, 0] - h) < 2e-5  # bounded by thresh
+        g = orc.geo2rdr(lat=np.array([[e["llh"][0]]]), lon=np.array([[e["llh"][1]]]), hgt=np.array([[h]]),
+                        orbit_t=rows[:, 0], orbit_pos=rows[:, 1:4], orbit_vel=rows[:, 4:7], length=200001, width=400001,
+                        r0=e["rng"] - 200000.0, dr=1.0, prf=1000.0, t0=e["t"] - 100.0, wvl=0.056)
+        # Python datetimes quantise the iterate to 1e-6 s
+        assert abs(g["azt"][0, 0] - e["geo2rdr_t"]) < 2e-6
+        assert abs(g["rgm"][0, 0] - e["geo2rdr_rng"]) < 1e-5
+        # and the oracle's own round trip closes far tighter
+        assert abs(g["azt"][0, 0] - e["t"]) < 2e-9
+        assert abs(g["rgm"][0, 0] - e["rng"]) < 1e-6
