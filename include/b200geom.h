@@ -1,0 +1,232 @@
+/*
+ * b200geom.h -- C ABI of libb200geom.so: the B200-native (sm_100a, hand-written FP64 CUDA)
+ * implementation of ISCE2's zero-Doppler radar-geometry hot path: topozero (rdr2geo) + geo2rdr.
+ *
+ * This is the drop-in boundary.  It replaces the two CPython extension modules the reference
+ * Component classes drive (all paths relative to the ISCE2 tree):
+ *
+ *   components/zerodop/topozero/bindings/topozeromodule.cpp:73-83    topo_Py(dem, dop, slrng)
+ *   components/zerodop/topozero/include/topozeromodule.h:117-155     the 31 set*_Py / get*_Py functions
+ *   components/zerodop/geo2rdr/bindings/geo2rdrmodule.cpp:72-88      geo2rdr_Py(lat, lon, hgt, az, rg, azoff, rgoff)
+ *   components/zerodop/geo2rdr/include/geo2rdrmodule.h:43-80         the 18 set*_Py functions
+ *
+ * Differences by design: no module-global state (the reference keeps every parameter in Fortran
+ * module variables, topozeroState.f:32-68 / geo2rdrState.F:28-67; here they travel in a params
+ * struct, so the library is re-entrant and can drive several GPUs from several threads), images
+ * are plain host pointers + sizes instead of uint64 DataAccessor handles, and errors come back
+ * as a status code + message instead of a Fortran `stop`.
+ *
+ * Only plain C types cross this boundary (no torch, no numpy, no CUDA types).  Every entry point
+ * returns B200_OK (0) or a negative B200_E* code and, if `err` is non-NULL, a NUL-terminated
+ * message.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * B200_ENODEVICE.
+ */
+#ifndef B200GEOM_H
+#define B200GEOM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GEOM_ABI_VERSION 1
+
+enum {
+    B200_OK = 0,
+    B200_EINVAL = -1,    /* bad argument (message says which) */
+    B200_ENODEVICE = -2, /* no usable CUDA device / bad device ordinal */
+    B200_ECUDA = -3,     /* CUDA runtime error (message carries cudaGetErrorString) */
+    B200_EORBIT = -4,    /* too few state vectors for the interpolation method, or scene centre outside the orbit */
+    B200_EDEM = -5,      /* DEM does not cover the scene */
+    B200_ENOMEM = -6
+};
+
+/* DEM interpolation ids == Topo.interpolationMethods (Topozero.py:46-51, topozeroMethods.f:30-32) */
+enum { B200_DEM_SINC = 0, B200_DEM_BILINEAR = 1, B200_DEM_BICUBIC = 2, B200_DEM_NEAREST = 3, B200_DEM_AKIMA = 4,
+       B200_DEM_BIQUINTIC = 5 };
+/* orbit interpolation ids == Topo.orbitInterpolationMethods (Topozero.py:53-55, topozeroState.f:77-78) */
+enum { B200_ORBIT_HERMITE = 0, B200_ORBIT_SCH = 1, B200_ORBIT_LEGENDRE = 2 };
+/* DEM sample types accepted (the reference reads any type through a 'FLOAT' caster, Topozero.py:380) */
+enum { B200_DEM_F32 = 0, B200_DEM_I16 = 1 };
+
+/* replaces cOrbit* given to setOrbit_Py (components/isceobj/Util/Library/orbit/include/orbit.h:30-38);
+ * rows as produced by Orbit.exportToC (Orbit.py:1060-1081): t = seconds of the reference day, ECEF m, m/s */
+typedef struct {
+    int nvec;
+    const double *t;   /* [nvec] */
+    const double *pos; /* [nvec][3] */
+    const double *vel; /* [nvec][3] */
+} b200_orbit;
+
+/* replaces the cPoly2d-backed accessor handles (dopAccessor / slrngAccessor of topo_Py):
+ * components/isceobj/Util/Library/poly2d/include/poly2d.h:25-34; evaluated at 0-based (row, col) */
+typedef struct {
+    int range_order, azimuth_order;
+    double mean_range, mean_azimuth, norm_range, norm_azimuth;
+    const double *coeffs; /* [(azimuth_order+1)][(range_order+1)] */
+} b200_poly2d;
+
+/* replaces cPoly1d* given to setDopplerAccessor_Py (poly1d.h:25-31) */
+typedef struct {
+    int order;
+    double mean, norm;
+    const double *coeffs; /* [order+1] */
+} b200_poly1d;
+
+/* ------------------------------------------------------------------------------------------ */
+/* topozero                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* One field per set*_Py of topozeromodule.h:117-155 (== module topozeroState) */
+typedef struct {
+    int numiter;         /* setNumberIterations_Py   (default 25, Topozero.py:140) */
+    int extraiter;       /* setSecondaryIterations_Py (10) */
+    double thresh;       /* setThreshold_Py (0.05 m) */
+    int dem_width;       /* setDemWidth_Py  */
+    int dem_length;      /* setDemLength_Py */
+    double first_lat;    /* setFirstLatitude_Py  (deg, north edge)  */
+    double first_lon;    /* setFirstLongitude_Py (deg, west edge)   */
+    double delta_lat;    /* setDeltaLatitude_Py  (deg, < 0)         */
+    double delta_lon;    /* setDeltaLongitude_Py (deg)              */
+    double major;        /* setEllipsoidMajorSemiAxis_Py            */
+    double e2;           /* setEllipsoidEccentricitySquared_Py      */
+    int length;          /* setLength_Py (radar lines)              */
+    int width;           /* setWidth_Py  (radar samples)            */
+    int nrnglooks;       /* setNumberRangeLooks_Py                  */
+    int nazlooks;        /* setNumberAzimuthLooks_Py                */
+    double peg_heading;  /* setPegHeading_Py (rad)                  */
+    double prf;          /* setPRF_Py                               */
+    double t0;           /* setSensingStart_Py (seconds of day)     */
+    double wvl;          /* setRadarWavelength_Py                   */
+    int look_side;       /* setLookSide_Py: -1 right, +1 left       */
+    int dem_method;      /* setMethod_Py       (B200_DEM_*)         */
+    int orbit_method;    /* setOrbitMethod_Py  (B200_ORBIT_*)       */
+    /* --- not in the reference: azimuth line block + device selection (multi-GPU sharding) --- */
+    int line0;           /* first radar line computed by this call (0-based) */
+    int nlines;          /* number of lines (<0: through the last line)      */
+    int device;          /* CUDA device ordinal                              */
+} b200_topo_params;
+
+/* replaces set{Latitude,Longitude,Height,Los,Inc,Mask}Pointer_Py: caller-owned HOST buffers holding the
+ * block's rows; any of los/inc/mask may be NULL (the reference's accessor==0).  Layout == the files the
+ * reference writes: lat/lon/hgt [nlines][width] double; los/inc [nlines][2][width] float (BIL,
+ * BILAccessor.cpp:11-37); mask [nlines][width] int8 (0 none, 1 shadow, 2 layover, 3 both). */
+typedef struct {
+    double *lat, *lon, *hgt;
+    float *los, *inc;
+    int8_t *mask;
+} b200_topo_outputs;
+
+typedef struct {
+    double min_lat, max_lat, min_lon, max_lon; /* get{Min,Max}imum{Lat,Long}itude_Py, over this block */
+    long long converged;                       /* the reference's 'Total convergence' print (topozero.f90:883) */
+    long long iterations;                      /* executed iteration bodies, summed over pixels */
+    int dem_x0, dem_y0, dem_nx, dem_ny;        /* 1-based crop origin + size actually used (topozero.f90:304-320) */
+    float dem_max;
+    float ms_setup;   /* device time: bbox + DEM upload/crop + per-line state */
+    float ms_kernels; /* device time: per-pixel solve (+ mask), CUDA events on the launch stream */
+    float ms_total;   /* wall time of the call, host<->device copies included */
+    int gpu_launches; /* kernels launched by this call */
+} b200_topo_result;
+
+/* The verb: topo_Py(demAccessor, dopAccessor, slrngAccessor).
+ * dem: whole DEM [dem_length][dem_width] of dem_dtype in host memory.  slrng: slant-range polynomial
+ * (Topozero.py:337-347) or NULL when rho_image ([length][width] double, the slantRangeFilename case) is given. */
+int b200_topo_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                  const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                  const b200_topo_outputs *out, b200_topo_result *res, char *err, size_t errlen);
+
+/* Device-resident form of the same path (used to time the kernels with inputs already in HBM, and by
+ * callers that consume the layers on the GPU): create uploads + prepares, execute launches the kernels,
+ * fetch copies the layers to the host. */
+typedef struct b200_topo_plan b200_topo_plan;
+int b200_topo_plan_create(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                          const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                          int want_los, int want_inc, int want_mask, b200_topo_plan **plan, char *err, size_t errlen);
+int b200_topo_plan_execute(b200_topo_plan *plan, float *ms_kernels, char *err, size_t errlen);
+int b200_topo_plan_fetch(b200_topo_plan *plan, const b200_topo_outputs *out, b200_topo_result *res, char *err,
+                         size_t errlen);
+/* device pointers of the resident layers (NULL if not requested): for chaining into geo2rdr on the GPU */
+int b200_topo_plan_device_layers(b200_topo_plan *plan, const double **lat, const double **lon, const double **hgt);
+void b200_topo_plan_destroy(b200_topo_plan *plan);
+
+/* ------------------------------------------------------------------------------------------ */
+/* geo2rdr                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* One field per set*_Py of geo2rdrmodule.h:43-80 (== module geo2rdrState) */
+typedef struct {
+    double major, e2;        /* setEllipsoid*_Py                       */
+    double drho;             /* setRangePixelSpacing_Py                */
+    double rho0;             /* setRangeFirstSample_Py                 */
+    double wvl;              /* setRadarWavelength_Py                  */
+    double t0;               /* setSensingStart_Py (seconds of day)    */
+    double prf;              /* setPRF_Py                              */
+    int length, width;       /* setLength_Py / setWidth_Py (radar grid) */
+    int look_side;           /* setLookSide_Py                         */
+    int nrnglooks, nazlooks; /* setNumber{Range,Azimuth}Looks_Py       */
+    int dem_width;           /* setDemWidth_Py  (samples of lat/lon/hgt) */
+    int dem_length;          /* setDemLength_Py (lines of lat/lon/hgt)   */
+    int bistatic;            /* setBistaticFlag_Py                     */
+    int orbit_method;        /* setOrbitMethod_Py                      */
+    /* --- not in the reference --- */
+    int line0, nlines;       /* block of lat/lon/hgt lines computed by this call */
+    int device;
+    int out_f32;             /* 1: outputs are float32 (Geo2rdr outputPrecision 'single': FLOAT image with a
+                                DOUBLE write caster, Geo2rdr.py:326-381), 0: float64 */
+} b200_geo_params;
+
+/* replaces the four output accessor handles of geo2rdr_Py (0 == NULL == not requested); host buffers
+ * [nlines][dem_width] of float or double according to out_f32; invalid pixels = -999999 (geo2rdr.f90:59-60) */
+typedef struct {
+    void *azt, *rgm, *azoff, *rgoff;
+} b200_geo_outputs;
+
+typedef struct {
+    long long num_outside, num_valid, num_converged; /* the three prints at geo2rdr.f90:407-409 */
+    long long iterations;                            /* Newton steps summed over pixels */
+    float ms_setup, ms_kernels, ms_total;
+    int gpu_launches;
+} b200_geo_result;
+
+/* The verb: geo2rdr_Py(lat, lon, hgt, az, rg, azoff, rgoff).  lat/lon in degrees, hgt in metres,
+ * [dem_length][dem_width] double in host memory (whole images; the block is selected by line0/nlines). */
+int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, const double *lon, const double *hgt,
+                     const b200_orbit *orbit, const b200_poly1d *dop, const b200_geo_outputs *out,
+                     b200_geo_result *res, char *err, size_t errlen);
+
+/* Device-resident form: lat/lon/hgt uploaded once (or borrowed from a topo plan on the same device), then any
+ * number of secondary orbits run against them (topsStack: one reference geometry x N dates). */
+typedef struct b200_geo_plan b200_geo_plan;
+int b200_geo_plan_create(const b200_geo_params *p, const double *lat, const double *lon, const double *hgt,
+                         b200_geo_plan **plan, char *err, size_t errlen);
+int b200_geo_plan_create_from_topo(const b200_geo_params *p, b200_topo_plan *topo, b200_geo_plan **plan, char *err,
+                                   size_t errlen);
+/* p may differ from the creation params in everything except dem_width/dem_length/line0/nlines/device */
+int b200_geo_plan_execute(b200_geo_plan *plan, const b200_geo_params *p, const b200_orbit *orbit,
+                          const b200_poly1d *dop, int want_azt, int want_rgm, int want_azoff, int want_rgoff,
+                          float *ms_kernels, char *err, size_t errlen);
+int b200_geo_plan_fetch(b200_geo_plan *plan, const b200_geo_outputs *out, b200_geo_result *res, char *err,
+                        size_t errlen);
+void b200_geo_plan_destroy(b200_geo_plan *plan);
+
+/* ------------------------------------------------------------------------------------------ */
+/* utilities                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+int b200_abi_version(void);
+int b200_device_count(void);                             /* 0 when no CUDA device is visible */
+int b200_device_name(int device, char *buf, size_t len); /* e.g. "NVIDIA B200" */
+void *b200_alloc_pinned(size_t bytes);                   /* page-locked host memory (fast H2D/D2H); NULL on failure */
+void b200_free_pinned(void *p);
+/* DFMA-saturating microbenchmark: measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per FMA) */
+int b200_fp64_peak(int device, double *tflops, char *err, size_t errlen);
+/* single-point primitives evaluated ON THE DEVICE (one thread), for known-answer tests of the device math:
+ * what: 0 = LLH(rad)->XYZ, 1 = XYZ->LLH(rad), 2 = Hermite orbit (in[0]=t; out = pos,vel),
+ *       3 = Legendre orbit, 4 = SCH orbit; orbit may be NULL for 0/1 */
+int b200_device_primitive(int device, int what, double a, double e2, const b200_orbit *orbit, const double *in,
+                          double *out, char *err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GEOM_H */

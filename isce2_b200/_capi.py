@@ -1,0 +1,430 @@
+"""Thin ctypes layer over the C ABI of libb200geom.so (include/b200geom.h).
+
+numpy arrays in, numpy arrays out; the GIL is released for the duration of every native call
+(ctypes.CDLL does that).  There is no CPU fallback here: if the CUDA library is missing or no
+device is visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200geom.so")
+
+B200_OK = 0
+ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "EORBIT", -5: "EDEM", -6: "ENOMEM"}
+DEM_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3, "AKIMA": 4, "BIQUINTIC": 5}
+ORBIT_METHODS = {"HERMITE": 0, "SCH": 1, "LEGENDRE": 2}
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb200geom: {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Orbit(C.Structure):
+    _fields_ = [("nvec", C.c_int), ("t", _dp), ("pos", _dp), ("vel", _dp)]
+
+
+class Poly2d(C.Structure):
+    _fields_ = [("range_order", C.c_int), ("azimuth_order", C.c_int), ("mean_range", C.c_double),
+                ("mean_azimuth", C.c_double), ("norm_range", C.c_double), ("norm_azimuth", C.c_double),
+                ("coeffs", _dp)]
+
+
+class Poly1d(C.Structure):
+    _fields_ = [("order", C.c_int), ("mean", C.c_double), ("norm", C.c_double), ("coeffs", _dp)]
+
+
+class TopoParams(C.Structure):
+    _fields_ = [("numiter", C.c_int), ("extraiter", C.c_int), ("thresh", C.c_double),
+                ("dem_width", C.c_int), ("dem_length", C.c_int),
+                ("first_lat", C.c_double), ("first_lon", C.c_double), ("delta_lat", C.c_double),
+                ("delta_lon", C.c_double), ("major", C.c_double), ("e2", C.c_double),
+                ("length", C.c_int), ("width", C.c_int), ("nrnglooks", C.c_int), ("nazlooks", C.c_int),
+                ("peg_heading", C.c_double), ("prf", C.c_double), ("t0", C.c_double), ("wvl", C.c_double),
+                ("look_side", C.c_int), ("dem_method", C.c_int), ("orbit_method", C.c_int),
+                ("line0", C.c_int), ("nlines", C.c_int), ("device", C.c_int)]
+
+
+class TopoOutputs(C.Structure):
+    _fields_ = [("lat", _dp), ("lon", _dp), ("hgt", _dp), ("los", _fp), ("inc", _fp), ("mask", C.POINTER(C.c_int8))]
+
+
+class TopoResult(C.Structure):
+    _fields_ = [("min_lat", C.c_double), ("max_lat", C.c_double), ("min_lon", C.c_double), ("max_lon", C.c_double),
+                ("converged", C.c_longlong), ("iterations", C.c_longlong),
+                ("dem_x0", C.c_int), ("dem_y0", C.c_int), ("dem_nx", C.c_int), ("dem_ny", C.c_int),
+                ("dem_max", C.c_float), ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_total", C.c_float),
+                ("gpu_launches", C.c_int)]
+
+
+class GeoParams(C.Structure):
+    _fields_ = [("major", C.c_double), ("e2", C.c_double), ("drho", C.c_double), ("rho0", C.c_double),
+                ("wvl", C.c_double), ("t0", C.c_double), ("prf", C.c_double),
+                ("length", C.c_int), ("width", C.c_int), ("look_side", C.c_int),
+                ("nrnglooks", C.c_int), ("nazlooks", C.c_int), ("dem_width", C.c_int), ("dem_length", C.c_int),
+                ("bistatic", C.c_int), ("orbit_method", C.c_int),
+                ("line0", C.c_int), ("nlines", C.c_int), ("device", C.c_int), ("out_f32", C.c_int)]
+
+
+class GeoOutputs(C.Structure):
+    _fields_ = [("azt", C.c_void_p), ("rgm", C.c_void_p), ("azoff", C.c_void_p), ("rgoff", C.c_void_p)]
+
+
+class GeoResult(C.Structure):
+    _fields_ = [("num_outside", C.c_longlong), ("num_valid", C.c_longlong), ("num_converged", C.c_longlong),
+                ("iterations", C.c_longlong), ("ms_setup", C.c_float), ("ms_kernels", C.c_float),
+                ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
+
+
+EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "b200_topo_plan_fetch",
+           "b200_topo_plan_device_layers", "b200_topo_plan_destroy", "b200_geo2rdr_run", "b200_geo_plan_create",
+           "b200_geo_plan_create_from_topo", "b200_geo_plan_execute", "b200_geo_plan_fetch", "b200_geo_plan_destroy",
+           "b200_abi_version", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
+           "b200_fp64_peak", "b200_device_primitive"]
+
+_lib = None
+
+
+def lib():
+    """Load libb200geom.so; raises (loudly) when the CUDA extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C isce2_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    err = [C.c_char_p, C.c_size_t]
+    L.b200_topo_run.argtypes = [C.POINTER(TopoParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly2d),
+                                C.POINTER(Poly2d), _dp, C.POINTER(TopoOutputs), C.POINTER(TopoResult)] + err
+    L.b200_topo_plan_create.argtypes = [C.POINTER(TopoParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly2d),
+                                        C.POINTER(Poly2d), _dp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + err
+    L.b200_topo_plan_execute.argtypes = [C.c_void_p, _fp] + err
+    L.b200_topo_plan_fetch.argtypes = [C.c_void_p, C.POINTER(TopoOutputs), C.POINTER(TopoResult)] + err
+    L.b200_topo_plan_device_layers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.b200_topo_plan_destroy.argtypes = [C.c_void_p]
+    L.b200_topo_plan_destroy.restype = None
+    L.b200_geo2rdr_run.argtypes = [C.POINTER(GeoParams), _dp, _dp, _dp, C.POINTER(Orbit), C.POINTER(Poly1d),
+                                   C.POINTER(GeoOutputs), C.POINTER(GeoResult)] + err
+    L.b200_geo_plan_create.argtypes = [C.POINTER(GeoParams), _dp, _dp, _dp, C.POINTER(C.c_void_p)] + err
+    L.b200_geo_plan_create_from_topo.argtypes = [C.POINTER(GeoParams), C.c_void_p, C.POINTER(C.c_void_p)] + err
+    L.b200_geo_plan_execute.argtypes = [C.c_void_p, C.POINTER(GeoParams), C.POINTER(Orbit), C.POINTER(Poly1d),
+                                        C.c_int, C.c_int, C.c_int, C.c_int, _fp] + err
+    L.b200_geo_plan_fetch.argtypes = [C.c_void_p, C.POINTER(GeoOutputs), C.POINTER(GeoResult)] + err
+    L.b200_geo_plan_destroy.argtypes = [C.c_void_p]
+    L.b200_geo_plan_destroy.restype = None
+    L.b200_device_name.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    L.b200_alloc_pinned.argtypes = [C.c_size_t]
+    L.b200_alloc_pinned.restype = C.c_void_p
+    L.b200_free_pinned.argtypes = [C.c_void_p]
+    L.b200_free_pinned.restype = None
+    L.b200_fp64_peak.argtypes = [C.c_int, _dp] + err
+    L.b200_device_primitive.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Orbit), _dp, _dp] + err
+    _lib = L
+    return L
+
+
+def _check(rc, errbuf):
+    if rc != B200_OK:
+        raise B200Error(rc, errbuf.value.decode(errors="replace"))
+
+
+def _errbuf():
+    return C.create_string_buffer(512)
+
+
+def device_count():
+    return int(lib().b200_device_count())
+
+
+def device_name(device=0):
+    b = C.create_string_buffer(256)
+    lib().b200_device_name(device, b, 256)
+    return b.value.decode()
+
+
+def fp64_peak(device=0):
+    v = C.c_double()
+    e = _errbuf()
+    _check(lib().b200_fp64_peak(device, C.byref(v), e, 512), e)
+    return v.value
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory allocated by the library (freed with the array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().b200_alloc_pinned(max(n, 1))
+    if not p:
+        raise MemoryError("b200_alloc_pinned failed")
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().b200_free_pinned(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p)
+    # keep the owner alive as long as any view of the buffer lives
+    buf._b200_owner = owner
+    return arr
+
+
+class _Keep:
+    """Holds numpy arrays alive while their pointers sit in ctypes structs."""
+
+    def __init__(self):
+        self.refs = []
+
+    def d(self, a):
+        a = np.ascontiguousarray(a, np.float64)
+        self.refs.append(a)
+        return a.ctypes.data_as(_dp)
+
+
+def make_orbit(keep, t, pos, vel):
+    t = np.ascontiguousarray(t, np.float64)
+    return Orbit(len(t), keep.d(t), keep.d(np.asarray(pos).reshape(-1, 3)), keep.d(np.asarray(vel).reshape(-1, 3)))
+
+
+def make_poly2d(keep, coeffs, mean_range=0.0, mean_azimuth=0.0, norm_range=1.0, norm_azimuth=1.0):
+    c = np.atleast_2d(np.asarray(coeffs, np.float64))
+    return Poly2d(c.shape[1] - 1, c.shape[0] - 1, mean_range, mean_azimuth, norm_range, norm_azimuth, keep.d(c))
+
+
+def make_poly1d(keep, coeffs, mean=0.0, norm=1.0):
+    c = np.asarray(coeffs, np.float64).ravel()
+    return Poly1d(len(c) - 1, mean, norm, keep.d(c))
+
+
+def _dem_arg(dem):
+    if dem.dtype == np.float32:
+        code = 0
+    elif dem.dtype == np.int16:
+        code = 1
+    else:
+        raise TypeError("DEM must be float32 or int16 (cast it first)")
+    if not dem.flags["C_CONTIGUOUS"]:
+        dem = np.ascontiguousarray(dem)
+    return dem, code
+
+
+def topo_params(*, dem_shape, first_lat, first_lon, delta_lat, delta_lon, length, width, prf, t0, wvl, side,
+                peg_heading, a=6378137.0, e2=0.0066943799901, dem_method="BILINEAR", orbit_method="HERMITE",
+                numiter=25, extraiter=10, thresh=0.05, nrnglooks=1, nazlooks=1, line0=0, nlines=-1, device=0):
+    return TopoParams(numiter, extraiter, thresh, dem_shape[1], dem_shape[0], first_lat, first_lon, delta_lat, delta_lon,
+                      a, e2, length, width, nrnglooks, nazlooks, peg_heading, prf, t0, wvl, side,
+                      DEM_METHODS[dem_method.upper()], ORBIT_METHODS[orbit_method.upper()], line0, nlines, device)
+
+
+def _result_dict(res):
+    return {k: getattr(res, k) for k, _ in res._fields_}
+
+
+class TopoPlan:
+    """Device-resident topo (b200_topo_plan_*)."""
+
+    def __init__(self, params, dem, orbit_t, orbit_pos, orbit_vel, doppler_coeffs, slrng_coeffs=None, rho_image=None,
+                 want_los=True, want_inc=False, want_mask=False, doppler_poly=None, slrng_poly=None):
+        L = lib()
+        self.keep = _Keep()
+        self.params = params
+        dem, code = _dem_arg(dem)
+        self.keep.refs.append(dem)
+        orb = make_orbit(self.keep, orbit_t, orbit_pos, orbit_vel)
+        dop = doppler_poly if doppler_poly is not None else make_poly2d(self.keep, doppler_coeffs)
+        slr = slrng_poly if slrng_poly is not None else (make_poly2d(self.keep, slrng_coeffs) if slrng_coeffs is not None else None)
+        rimg = self.keep.d(rho_image) if rho_image is not None else None
+        self.handle = C.c_void_p()
+        e = _errbuf()
+        _check(L.b200_topo_plan_create(C.byref(params), dem.ctypes.data_as(C.c_void_p), code, C.byref(orb), C.byref(dop),
+                                       C.byref(slr) if slr is not None else None, rimg, int(want_los), int(want_inc),
+                                       int(want_mask), C.byref(self.handle), e, 512), e)
+        self.want = (want_los, want_inc, want_mask)
+        n = params.length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+        self.nlines = n
+        self.width = params.width
+
+    def execute(self):
+        ms = C.c_float()
+        e = _errbuf()
+        _check(lib().b200_topo_plan_execute(self.handle, C.byref(ms), e, 512), e)
+        return ms.value
+
+    def fetch(self, out=None):
+        n, w = self.nlines, self.width
+        if out is None:
+            out = dict(lat=np.empty((n, w)), lon=np.empty((n, w)), hgt=np.empty((n, w)),
+                       los=np.empty((n, 2, w), np.float32) if self.want[0] else None,
+                       inc=np.empty((n, 2, w), np.float32) if self.want[1] else None,
+                       mask=np.empty((n, w), np.int8) if self.want[2] else None)
+        o = TopoOutputs(out["lat"].ctypes.data_as(_dp), out["lon"].ctypes.data_as(_dp), out["hgt"].ctypes.data_as(_dp),
+                        out["los"].ctypes.data_as(_fp) if out.get("los") is not None else None,
+                        out["inc"].ctypes.data_as(_fp) if out.get("inc") is not None else None,
+                        out["mask"].ctypes.data_as(C.POINTER(C.c_int8)) if out.get("mask") is not None else None)
+        res = TopoResult()
+        e = _errbuf()
+        _check(lib().b200_topo_plan_fetch(self.handle, C.byref(o), C.byref(res), e, 512), e)
+        out = dict(out)
+        out.update(_result_dict(res))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().b200_topo_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def topo_run(params, dem, orbit_t, orbit_pos, orbit_vel, doppler_coeffs, slrng_coeffs=None, rho_image=None,
+             want_los=True, want_inc=False, want_mask=False, out=None, doppler_poly=None, slrng_poly=None):
+    """One-shot b200_topo_run with host buffers.  Returns dict of arrays + result fields."""
+    L = lib()
+    keep = _Keep()
+    dem, code = _dem_arg(dem)
+    orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+    dop = doppler_poly if doppler_poly is not None else make_poly2d(keep, doppler_coeffs)
+    slr = slrng_poly if slrng_poly is not None else (make_poly2d(keep, slrng_coeffs) if slrng_coeffs is not None else None)
+    rimg = keep.d(rho_image) if rho_image is not None else None
+    n = params.length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+    w = params.width
+    if out is None:
+        out = dict(lat=np.empty((n, w)), lon=np.empty((n, w)), hgt=np.empty((n, w)),
+                   los=np.empty((n, 2, w), np.float32) if want_los else None,
+                   inc=np.empty((n, 2, w), np.float32) if want_inc else None,
+                   mask=np.empty((n, w), np.int8) if want_mask else None)
+    o = TopoOutputs(out["lat"].ctypes.data_as(_dp), out["lon"].ctypes.data_as(_dp), out["hgt"].ctypes.data_as(_dp),
+                    out["los"].ctypes.data_as(_fp) if out.get("los") is not None else None,
+                    out["inc"].ctypes.data_as(_fp) if out.get("inc") is not None else None,
+                    out["mask"].ctypes.data_as(C.POINTER(C.c_int8)) if out.get("mask") is not None else None)
+    res = TopoResult()
+    e = _errbuf()
+    _check(L.b200_topo_run(C.byref(params), dem.ctypes.data_as(C.c_void_p), code, C.byref(orb), C.byref(dop),
+                           C.byref(slr) if slr is not None else None, rimg, C.byref(o), C.byref(res), e, 512), e)
+    out = dict(out)
+    out.update(_result_dict(res))
+    return out
+
+
+def geo_params(*, length, width, dem_shape, r0, dr, prf, t0, wvl, side=-1, a=6378137.0, e2=0.0066943799901,
+               orbit_method="HERMITE", bistatic=False, nrnglooks=1, nazlooks=1, line0=0, nlines=-1, device=0,
+               out_f32=False):
+    return GeoParams(a, e2, dr, r0, wvl, t0, prf, length, width, side, nrnglooks, nazlooks, dem_shape[1], dem_shape[0],
+                     int(bool(bistatic)), ORBIT_METHODS[orbit_method.upper()], line0, nlines, device, int(bool(out_f32)))
+
+
+_GEO_KEYS = ("azt", "rgm", "azoff", "rgoff")
+
+
+def _geo_out(params, want, out):
+    n = params.dem_length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+    dt = np.float32 if params.out_f32 else np.float64
+    if out is None:
+        out = {k: (np.empty((n, params.dem_width), dt) if k in want else None) for k in _GEO_KEYS}
+    o = GeoOutputs(*[(out[k].ctypes.data_as(C.c_void_p) if out.get(k) is not None else None) for k in _GEO_KEYS])
+    return out, o
+
+
+def geo2rdr_run(params, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, doppler_coeffs=(0.0,), doppler_mean=0.0,
+                doppler_norm=1.0, want=_GEO_KEYS, out=None):
+    L = lib()
+    keep = _Keep()
+    orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+    dop = make_poly1d(keep, doppler_coeffs, doppler_mean, doppler_norm)
+    out, o = _geo_out(params, want, out)
+    res = GeoResult()
+    e = _errbuf()
+    _check(L.b200_geo2rdr_run(C.byref(params), keep.d(lat), keep.d(lon), keep.d(hgt), C.byref(orb), C.byref(dop),
+                              C.byref(o), C.byref(res), e, 512), e)
+    out = dict(out)
+    out.update(_result_dict(res))
+    return out
+
+
+class GeoPlan:
+    """Device-resident geo2rdr: reference geometry uploaded once, many secondary orbits run against it."""
+
+    def __init__(self, params, lat=None, lon=None, hgt=None, topo_plan=None):
+        L = lib()
+        self.keep = _Keep()
+        self.params = params
+        self.handle = C.c_void_p()
+        e = _errbuf()
+        if topo_plan is not None:
+            self.topo_plan = topo_plan  # keep the layers alive
+            _check(L.b200_geo_plan_create_from_topo(C.byref(params), topo_plan.handle, C.byref(self.handle), e, 512), e)
+            self.nlines = topo_plan.nlines
+        else:
+            _check(L.b200_geo_plan_create(C.byref(params), self.keep.d(lat), self.keep.d(lon), self.keep.d(hgt),
+                                          C.byref(self.handle), e, 512), e)
+            self.nlines = params.dem_length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+
+    def execute(self, params, orbit_t, orbit_pos, orbit_vel, doppler_coeffs=(0.0,), doppler_mean=0.0, doppler_norm=1.0,
+                want=_GEO_KEYS):
+        keep = _Keep()
+        orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+        dop = make_poly1d(keep, doppler_coeffs, doppler_mean, doppler_norm)
+        ms = C.c_float()
+        e = _errbuf()
+        self.last_params = params
+        self.last_want = tuple(want)
+        _check(lib().b200_geo_plan_execute(self.handle, C.byref(params), C.byref(orb), C.byref(dop),
+                                           *[int(k in want) for k in _GEO_KEYS], C.byref(ms), e, 512), e)
+        return ms.value
+
+    def fetch(self, out=None):
+        p = self.last_params
+        dt = np.float32 if p.out_f32 else np.float64
+        if out is None:
+            out = {k: (np.empty((self.nlines, p.dem_width), dt) if k in self.last_want else None) for k in _GEO_KEYS}
+        o = GeoOutputs(*[(out[k].ctypes.data_as(C.c_void_p) if out.get(k) is not None else None) for k in _GEO_KEYS])
+        res = GeoResult()
+        e = _errbuf()
+        _check(lib().b200_geo_plan_fetch(self.handle, C.byref(o), C.byref(res), e, 512), e)
+        out = dict(out)
+        out.update(_result_dict(res))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().b200_geo_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_primitive(what, vec3_or_t, a=6378137.0, e2=0.0066943799901, orbit=None, device=0):
+    keep = _Keep()
+    inp = np.zeros(3)
+    v = np.atleast_1d(np.asarray(vec3_or_t, np.float64))
+    inp[: len(v)] = v
+    out = np.zeros(7)
+    orb = make_orbit(keep, *orbit) if orbit is not None else None
+    e = _errbuf()
+    _check(lib().b200_device_primitive(device, what, a, e2, C.byref(orb) if orb is not None else None,
+                                       inp.ctypes.data_as(_dp), out.ctypes.data_as(_dp), e, 512), e)
+    return out

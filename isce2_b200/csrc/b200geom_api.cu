@@ -1,0 +1,871 @@
+// b200geom_api.cu -- host side of the C ABI declared in include/b200geom.h.
+//
+// Owns device memory, streams and events; prepares the per-scene constants the reference keeps in Fortran
+// module globals; launches the kernels of topo_kernels.cu / geo2rdr_kernels.cu.  No CPU fallback: every
+// compute entry point fails with B200_ENODEVICE when no CUDA device is usable.
+#include "../../include/b200geom.h"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "geo2rdr_kernels.cuh"
+#include "topo_kernels.cuh"
+
+using namespace b2;
+
+namespace {
+
+int fail(char *err, size_t errlen, int code, const char *fmt, ...)
+{
+    if (err && errlen) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(err, errlen, B200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int select_device(int device, char *err, size_t errlen)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(err, errlen, B200_ENODEVICE,
+                    "no CUDA device available (%s); libb200geom has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(err, errlen, B200_ENODEVICE, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    return B200_OK;
+}
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DeviceOrbit {
+    double *buf = nullptr;
+    OrbitView view{0, nullptr, nullptr, nullptr};
+};
+
+int upload_orbit(const b200_orbit *o, DeviceOrbit &d, cudaStream_t s, char *err, size_t errlen)
+{
+    const int n = o->nvec;
+    std::vector<double> h((size_t)n * 7);
+    memcpy(h.data(), o->t, sizeof(double) * n);
+    memcpy(h.data() + n, o->pos, sizeof(double) * 3 * n);
+    memcpy(h.data() + 4 * (size_t)n, o->vel, sizeof(double) * 3 * n);
+    CK(cudaMalloc(&d.buf, sizeof(double) * 7 * (size_t)n));
+    CK(cudaMemcpyAsync(d.buf, h.data(), sizeof(double) * 7 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s)); // h goes out of scope
+    d.view = OrbitView{n, d.buf, d.buf + n, d.buf + 4 * (size_t)n};
+    return B200_OK;
+}
+
+int check_orbit(const b200_orbit *o, int method, char *err, size_t errlen)
+{
+    if (!o || !o->t || !o->pos || !o->vel) return fail(err, errlen, B200_EINVAL, "orbit is NULL");
+    if (method != B200_ORBIT_HERMITE && method != B200_ORBIT_SCH && method != B200_ORBIT_LEGENDRE)
+        return fail(err, errlen, B200_EINVAL, "Undefined orbit interpolation method.");
+    // topozero.f90:104-131 / geo2rdr.f90:64-91
+    if (method == B200_ORBIT_LEGENDRE && o->nvec < 9)
+        return fail(err, errlen, B200_EORBIT, "Need atleast 9 state vectors for using legendre polynomial interpolation");
+    if (method == B200_ORBIT_HERMITE && o->nvec < 4)
+        return fail(err, errlen, B200_EORBIT, "Need atleast 4 state vectors for using hermite polynomial interpolation");
+    if (method == B200_ORBIT_SCH && o->nvec < 4)
+        return fail(err, errlen, B200_EORBIT, "Need atleast 4 state vectors for using SCH interpolation");
+    return B200_OK;
+}
+
+int fill_poly2d(const b200_poly2d *src, Poly2dDev &dst, const char *what, char *err, size_t errlen)
+{
+    if (!src || !src->coeffs) return fail(err, errlen, B200_EINVAL, "%s polynomial is NULL", what);
+    const int n = (src->range_order + 1) * (src->azimuth_order + 1);
+    if (src->range_order < 0 || src->azimuth_order < 0 || n > kMaxPoly2dCoeffs)
+        return fail(err, errlen, B200_EINVAL, "%s polynomial has %d coefficients (max %d)", what, n, kMaxPoly2dCoeffs);
+    dst.range_order = src->range_order;
+    dst.azimuth_order = src->azimuth_order;
+    dst.mean_range = src->mean_range;
+    dst.mean_azimuth = src->mean_azimuth;
+    dst.norm_range = src->norm_range;
+    dst.norm_azimuth = src->norm_azimuth;
+    memset(dst.c, 0, sizeof dst.c);
+    memcpy(dst.c, src->coeffs, sizeof(double) * n);
+    return B200_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// topozero
+// =================================================================================================
+struct b200_topo_plan {
+    b200_topo_params p{};
+    int line0 = 0, nlines = 0;
+    TopoConst C{};
+    DeviceOrbit orb;
+    float *d_dem = nullptr;
+    void *d_raw = nullptr;
+    int *d_maxkey = nullptr;
+    double *d_rho = nullptr;  // block rows of the slant-range image
+    double *d_rho0 = nullptr; // its first row (bbox stage)
+    LineState *d_states = nullptr;
+    TopoLayers layers{};
+    TopoStats *d_stats = nullptr;
+    MaskScratch scr{};
+    int mask_grid = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int dem_x0 = 0, dem_y0 = 0;
+    float dem_max = 0.f;
+    float ms_setup = 0.f, ms_kernels = 0.f;
+    int launches = 0;
+    bool executed = false;
+
+    ~b200_topo_plan()
+    {
+        cudaSetDevice(p.device);
+        cudaFree(orb.buf);
+        cudaFree(d_dem);
+        cudaFree(d_raw);
+        cudaFree(d_maxkey);
+        cudaFree(d_rho);
+        cudaFree(d_rho0);
+        cudaFree(d_states);
+        cudaFree(layers.lat);
+        cudaFree(layers.lon);
+        cudaFree(layers.hgt);
+        cudaFree(layers.los);
+        cudaFree(layers.inc);
+        cudaFree(layers.mask);
+        cudaFree(layers.ctrack);
+        cudaFree(layers.elev);
+        cudaFree(d_stats);
+        cudaFree(scr.key);
+        cudaFree(scr.idx);
+        cudaFree(scr.cs);
+        cudaFree(scr.lats);
+        cudaFree(scr.lons);
+        cudaFree(scr.rho);
+        cudaFree(scr.orng);
+        cudaFree(scr.ctr);
+        cudaFree(scr.ctr_sorted);
+        cudaFree(scr.oflag);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                           const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image, int want_los,
+                           int want_inc, int want_mask, char *err, size_t errlen)
+{
+    const b200_topo_params &p = pl->p;
+    int rc;
+    if (p.width < 2 || p.length < 1) return fail(err, errlen, B200_EINVAL, "bad radar grid %d x %d", p.length, p.width);
+    if (!dem) return fail(err, errlen, B200_EINVAL, "dem is NULL");
+    if (dem_dtype != B200_DEM_F32 && dem_dtype != B200_DEM_I16) return fail(err, errlen, B200_EINVAL, "bad dem_dtype %d", dem_dtype);
+    if (p.dem_method != B200_DEM_BILINEAR && p.dem_method != B200_DEM_BICUBIC && p.dem_method != B200_DEM_NEAREST &&
+        p.dem_method != B200_DEM_BIQUINTIC) {
+        if (p.dem_method == B200_DEM_SINC || p.dem_method == B200_DEM_AKIMA)
+            return fail(err, errlen, B200_EINVAL, "DEM interpolation method %d (SINC/AKIMA) is not implemented on the GPU yet",
+                        p.dem_method);
+        return fail(err, errlen, B200_EINVAL, "Undefined interpolation method.");
+    }
+    if ((rc = check_orbit(orbit, p.orbit_method, err, errlen)) != B200_OK) return rc;
+    if (!slrng && !rho_image)
+        return fail(err, errlen, B200_EINVAL, "Both the slant range accessor and starting range are zero"); // topozero.f90:156-159
+    if (p.prf <= 0 || p.nazlooks < 1 || p.nrnglooks < 1) return fail(err, errlen, B200_EINVAL, "bad prf / looks");
+
+    pl->line0 = p.line0 < 0 ? 0 : p.line0;
+    pl->nlines = (p.nlines < 0 || pl->line0 + p.nlines > p.length) ? p.length - pl->line0 : p.nlines;
+    if (pl->nlines <= 0) return fail(err, errlen, B200_EINVAL, "empty line block (line0=%d nlines=%d length=%d)", p.line0, p.nlines, p.length);
+
+    if ((rc = select_device(p.device, err, errlen)) != B200_OK) return rc;
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&pl->ev0));
+    CK(cudaEventCreate(&pl->ev1));
+    cudaStream_t s = pl->stream;
+    CK(cudaEventRecord(pl->ev0, s));
+
+    // ---- constants ----
+    TopoConst &C = pl->C;
+    C.elp = Ellipsoid{p.major, p.e2};
+    C.wvl = p.wvl;
+    C.thresh = p.thresh;
+    C.ilrl = p.look_side;
+    C.numiter = p.numiter;
+    C.extraiter = p.extraiter;
+    C.deltalat = p.delta_lat;
+    C.deltalon = p.delta_lon;
+    C.method = p.dem_method;
+    C.width = p.width;
+    C.length = p.length;
+    C.nazlooks = p.nazlooks;
+    C.t0 = p.t0;
+    C.prf = p.prf;
+    C.peghdg = p.peg_heading;
+    C.pi = 4.0 * atan(1.0); // fortranUtils.f90:38-41
+    C.r2d = 180.0 / C.pi;
+    C.orbit_method = p.orbit_method;
+    if ((rc = fill_poly2d(dop, C.dop, "doppler", err, errlen)) != B200_OK) return rc;
+    if (slrng) {
+        if ((rc = fill_poly2d(slrng, C.slr, "slant range", err, errlen)) != B200_OK) return rc;
+    } else {
+        memset(&C.slr, 0, sizeof C.slr);
+    }
+    spline6_make_table(C.spl);
+
+    if ((rc = upload_orbit(orbit, pl->orb, s, err, errlen)) != B200_OK) return rc;
+
+    if (rho_image) {
+        const size_t w = (size_t)p.width;
+        CK(cudaMalloc(&pl->d_rho0, sizeof(double) * w));
+        CK(cudaMemcpyAsync(pl->d_rho0, rho_image, sizeof(double) * w, cudaMemcpyHostToDevice, s));
+        CK(cudaMalloc(&pl->d_rho, sizeof(double) * w * pl->nlines));
+        CK(cudaMemcpyAsync(pl->d_rho, rho_image + (size_t)pl->line0 * w, sizeof(double) * w * pl->nlines,
+                           cudaMemcpyHostToDevice, s));
+    }
+
+    // ---- bbox of interest (topozero.f90:192-263) ----
+    double *d_bbox = nullptr;
+    double h_bbox[24];
+    CK(cudaMalloc(&d_bbox, sizeof h_bbox));
+    {
+        TopoConst Cb = C;
+        Cb.dem = DemView{nullptr, 0, 0};
+        Cb.rho_image = pl->d_rho0; // row 1 of the image, or NULL -> polynomial
+        launch_topo_bbox(Cb, pl->orb.view, d_bbox, s);
+        pl->launches++;
+    }
+    cudaError_t ce = cudaMemcpyAsync(h_bbox, d_bbox, sizeof h_bbox, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(d_bbox);
+    if (ce != cudaSuccess) return fail(err, errlen, B200_ECUDA, "bbox kernel failed: %s", cudaGetErrorString(ce));
+    double min_lat = 10000., max_lat = -10000., min_lon = 10000., max_lon = -10000.;
+    int nok = 0;
+    for (int i = 0; i < 8; i++) {
+        if (h_bbox[3 * i + 2] == 0.0) continue;
+        nok++;
+        min_lat = fmin(min_lat, h_bbox[3 * i]);
+        max_lat = fmax(max_lat, h_bbox[3 * i]);
+        min_lon = fmin(min_lon, h_bbox[3 * i + 1]);
+        max_lon = fmax(max_lon, h_bbox[3 * i + 1]);
+    }
+    if (nok == 0 || !(min_lat <= max_lat) || !(min_lon <= max_lon))
+        return fail(err, errlen, B200_EORBIT, "Error getting statevector for bounds computation");
+    const double MARGIN = 0.15; // topozeroState.f:74-75
+    min_lon -= MARGIN; max_lon += MARGIN; min_lat -= MARGIN; max_lat += MARGIN;
+
+    // ---- usable part of the DEM (topozero.f90:281-320), typo at :314 kept ----
+    const double firstlon = p.first_lon, firstlat = p.first_lat, deltalon = p.delta_lon, deltalat = p.delta_lat;
+    const int idemwidth = p.dem_width, idemlength = p.dem_length;
+    double umin_lon = fmax(min_lon, firstlon);
+    double umax_lon = fmin(max_lon, firstlon + (idemwidth - 1) * deltalon);
+    double umax_lat = fmin(max_lat, firstlat);
+    double umin_lat = fmax(min_lat, firstlat + (idemlength - 1) * deltalat);
+    int ustartx = (int)((umin_lon - firstlon) / deltalon) + 1;
+    if (ustartx < 1) ustartx = 1;
+    int uendx = (int)((umax_lon - firstlon) / deltalon + 0.5) + 1;
+    if (uendx > idemwidth) uendx = idemwidth;
+    int ustarty = (int)((umax_lat - firstlat) / deltalat) + 1;
+    if (ustarty < 1) ustarty = 1;
+    int uendy = (int)((umin_lat - firstlat) / deltalat + 0.5) + 1;
+    if (uendy > idemlength) ustarty = idemlength;
+    const int udemwidth = uendx - ustartx + 1, udemlength = uendy - ustarty + 1;
+    if (udemwidth < 2 || udemlength < 2 || uendy > idemlength || ustartx > idemwidth || ustarty > idemlength)
+        return fail(err, errlen, B200_EDEM, "DEM does not cover the scene: needs lon [%f,%f] lat [%f,%f]", min_lon, max_lon,
+                    min_lat, max_lat);
+    C.ufirstlon = firstlon + deltalon * (ustartx - 1);
+    C.ufirstlat = firstlat + deltalat * (ustarty - 1);
+    pl->dem_x0 = ustartx;
+    pl->dem_y0 = ustarty;
+
+    // ---- crop + float32 conversion + demmax (topozero.f90:333-345) ----
+    const size_t ncell = (size_t)udemwidth * (size_t)udemlength;
+    const size_t esz = dem_dtype == B200_DEM_I16 ? 2 : 4;
+    CK(cudaMalloc(&pl->d_dem, sizeof(float) * ncell));
+    CK(cudaMalloc(&pl->d_maxkey, sizeof(int)));
+    const char *src = (const char *)dem + ((size_t)(ustarty - 1) * (size_t)idemwidth + (size_t)(ustartx - 1)) * esz;
+    void *dst = pl->d_dem;
+    if (dem_dtype == B200_DEM_I16) {
+        CK(cudaMalloc(&pl->d_raw, esz * ncell));
+        dst = pl->d_raw;
+    }
+    CK(cudaMemcpy2DAsync(dst, (size_t)udemwidth * esz, src, (size_t)idemwidth * esz, (size_t)udemwidth * esz,
+                         (size_t)udemlength, cudaMemcpyHostToDevice, s));
+    {
+        int init = (int)0x80000000; // smaller than every order key
+        CK(cudaMemcpyAsync(pl->d_maxkey, &init, sizeof init, cudaMemcpyHostToDevice, s));
+        launch_dem_prepare(dst, dem_dtype, pl->d_dem, ncell, pl->d_maxkey, s);
+        pl->launches++;
+        int key = 0;
+        CK(cudaMemcpyAsync(&key, pl->d_maxkey, sizeof key, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        pl->dem_max = dem_max_decode(key);
+    }
+    if (pl->d_raw) {
+        cudaFree(pl->d_raw);
+        pl->d_raw = nullptr;
+    }
+    C.dem = DemView{pl->d_dem, udemwidth, udemlength};
+    C.rho_image = pl->d_rho ? pl->d_rho - (size_t)pl->line0 * (size_t)p.width : nullptr;
+
+    // ---- per-line state ----
+    CK(cudaMalloc(&pl->d_states, sizeof(LineState) * (size_t)pl->nlines));
+    launch_line_setup(C, pl->orb.view, pl->line0, pl->nlines, pl->d_states, s);
+    pl->launches++;
+
+    // ---- resident output layers ----
+    const size_t npix = (size_t)pl->nlines * (size_t)p.width;
+    CK(cudaMalloc(&pl->layers.lat, sizeof(double) * npix));
+    CK(cudaMalloc(&pl->layers.lon, sizeof(double) * npix));
+    CK(cudaMalloc(&pl->layers.hgt, sizeof(double) * npix));
+    if (want_los) CK(cudaMalloc(&pl->layers.los, sizeof(float) * 2 * npix));
+    if (want_inc) CK(cudaMalloc(&pl->layers.inc, sizeof(float) * 2 * npix));
+    if (want_mask) {
+        CK(cudaMalloc(&pl->layers.mask, npix));
+        CK(cudaMalloc(&pl->layers.ctrack, sizeof(double) * npix));
+        CK(cudaMalloc(&pl->layers.elev, sizeof(float) * npix));
+        const int ow = 2 * p.width + 1;
+        int P = 1;
+        while (P < ow) P <<= 1;
+        const int g = mask_grid_size(pl->nlines);
+        pl->mask_grid = g;
+        pl->scr.padded = P;
+        CK(cudaMalloc(&pl->scr.key, sizeof(double) * (size_t)g * P));
+        CK(cudaMalloc(&pl->scr.idx, sizeof(int) * (size_t)g * P));
+        CK(cudaMalloc(&pl->scr.cs, sizeof(double) * (size_t)g * p.width));
+        CK(cudaMalloc(&pl->scr.lats, sizeof(double) * (size_t)g * p.width));
+        CK(cudaMalloc(&pl->scr.lons, sizeof(double) * (size_t)g * p.width));
+        CK(cudaMalloc(&pl->scr.rho, sizeof(double) * (size_t)g * p.width));
+        CK(cudaMalloc(&pl->scr.orng, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.ctr, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.ctr_sorted, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.oflag, (size_t)g * ow));
+    }
+    CK(cudaMalloc(&pl->d_stats, sizeof(TopoStats)));
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->ms_setup, pl->ev0, pl->ev1));
+    return B200_OK;
+}
+
+extern "C" int b200_topo_plan_create(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                                     const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                                     int want_los, int want_inc, int want_mask, b200_topo_plan **plan, char *err,
+                                     size_t errlen)
+{
+    if (!p || !plan) return fail(err, errlen, B200_EINVAL, "params/plan is NULL");
+    *plan = nullptr;
+    b200_topo_plan *pl = new (std::nothrow) b200_topo_plan;
+    if (!pl) return fail(err, errlen, B200_ENOMEM, "out of host memory");
+    pl->p = *p;
+    int rc = topo_plan_build(pl, dem, dem_dtype, orbit, dop, slrng, rho_image, want_los, want_inc, want_mask, err, errlen);
+    if (rc != B200_OK) {
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return B200_OK;
+}
+
+extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, char *err, size_t errlen)
+{
+    if (!pl) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    TopoStats init;
+    init.min_lat = init.min_lon = 0x7fffffffffffffffLL;
+    init.max_lat = init.max_lon = (long long)0x8000000000000000ULL;
+    init.converged = init.iterations = 0;
+    CK(cudaMemcpyAsync(pl->d_stats, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->ev0, s));
+    if (launch_topo_pixels(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->d_stats, s) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the pixel kernel (method %d, %d lines)", pl->C.method, pl->nlines);
+    int launches = 1;
+    if (pl->layers.mask) {
+        if (launch_topo_mask(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->dem_max, pl->scr, pl->mask_grid, s) != 0)
+            return fail(err, errlen, B200_EINVAL, "cannot launch the mask kernel");
+        launches++;
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    if (!pl->executed) pl->launches += launches;
+    pl->executed = true;
+    if (ms_kernels) *ms_kernels = pl->ms_kernels;
+    return B200_OK;
+}
+
+extern "C" int b200_topo_plan_fetch(b200_topo_plan *pl, const b200_topo_outputs *out, b200_topo_result *res, char *err,
+                                    size_t errlen)
+{
+    if (!pl) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    if (!pl->executed) return fail(err, errlen, B200_EINVAL, "plan was not executed");
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    const size_t npix = (size_t)pl->nlines * (size_t)pl->p.width;
+    if (out) {
+        if (out->lat) CK(cudaMemcpyAsync(out->lat, pl->layers.lat, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
+        if (out->lon) CK(cudaMemcpyAsync(out->lon, pl->layers.lon, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
+        if (out->hgt) CK(cudaMemcpyAsync(out->hgt, pl->layers.hgt, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
+        if (out->los && pl->layers.los) CK(cudaMemcpyAsync(out->los, pl->layers.los, sizeof(float) * 2 * npix, cudaMemcpyDeviceToHost, s));
+        if (out->inc && pl->layers.inc) CK(cudaMemcpyAsync(out->inc, pl->layers.inc, sizeof(float) * 2 * npix, cudaMemcpyDeviceToHost, s));
+        if (out->mask && pl->layers.mask) CK(cudaMemcpyAsync(out->mask, pl->layers.mask, npix, cudaMemcpyDeviceToHost, s));
+    }
+    TopoStats st;
+    CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (res) {
+        res->min_lat = stats_decode(st.min_lat);
+        res->max_lat = stats_decode(st.max_lat);
+        res->min_lon = stats_decode(st.min_lon);
+        res->max_lon = stats_decode(st.max_lon);
+        res->converged = (long long)st.converged;
+        res->iterations = (long long)st.iterations;
+        res->dem_x0 = pl->dem_x0;
+        res->dem_y0 = pl->dem_y0;
+        res->dem_nx = pl->C.dem.nx;
+        res->dem_ny = pl->C.dem.ny;
+        res->dem_max = pl->dem_max;
+        res->ms_setup = pl->ms_setup;
+        res->ms_kernels = pl->ms_kernels;
+        res->ms_total = 0.f;
+        res->gpu_launches = pl->launches;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_topo_plan_device_layers(b200_topo_plan *pl, const double **lat, const double **lon, const double **hgt)
+{
+    if (!pl) return B200_EINVAL;
+    if (lat) *lat = pl->layers.lat;
+    if (lon) *lon = pl->layers.lon;
+    if (hgt) *hgt = pl->layers.hgt;
+    return B200_OK;
+}
+
+extern "C" void b200_topo_plan_destroy(b200_topo_plan *pl) { delete pl; }
+
+extern "C" int b200_topo_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                             const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                             const b200_topo_outputs *out, b200_topo_result *res, char *err, size_t errlen)
+{
+    if (!out || !out->lat || !out->lon || !out->hgt)
+        return fail(err, errlen, B200_EINVAL, "lat/lon/hgt output buffers are mandatory (Topozero.py:274-302)");
+    const double t0 = now_ms();
+    b200_topo_plan *pl = nullptr;
+    int rc = b200_topo_plan_create(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out->los != nullptr, out->inc != nullptr,
+                                   out->mask != nullptr, &pl, err, errlen);
+    if (rc != B200_OK) return rc;
+    rc = b200_topo_plan_execute(pl, nullptr, err, errlen);
+    if (rc == B200_OK) rc = b200_topo_plan_fetch(pl, out, res, err, errlen);
+    b200_topo_plan_destroy(pl);
+    if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
+    return rc;
+}
+
+// =================================================================================================
+// geo2rdr
+// =================================================================================================
+struct b200_geo_plan {
+    b200_geo_params p{};
+    int line0 = 0, nlines = 0;
+    double *d_lat = nullptr, *d_lon = nullptr, *d_hgt = nullptr;
+    bool owns_inputs = true;
+    void *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    int out_f32 = 1;
+    GeoStats *d_stats = nullptr;
+    GeoMid *d_mid = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float ms_setup = 0.f, ms_kernels = 0.f;
+    int launches = 0;
+    bool executed = false;
+    int want[4] = {0, 0, 0, 0};
+
+    ~b200_geo_plan()
+    {
+        cudaSetDevice(p.device);
+        if (owns_inputs) {
+            cudaFree(d_lat);
+            cudaFree(d_lon);
+            cudaFree(d_hgt);
+        }
+        for (void *q : d_out) cudaFree(q);
+        cudaFree(d_stats);
+        cudaFree(d_mid);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int geo_plan_common(b200_geo_plan *pl, char *err, size_t errlen)
+{
+    const b200_geo_params &p = pl->p;
+    if (p.dem_width < 1 || p.dem_length < 1) return fail(err, errlen, B200_EINVAL, "bad lat/lon/hgt grid %d x %d", p.dem_length, p.dem_width);
+    pl->line0 = p.line0 < 0 ? 0 : p.line0;
+    pl->nlines = (p.nlines < 0 || pl->line0 + p.nlines > p.dem_length) ? p.dem_length - pl->line0 : p.nlines;
+    if (pl->nlines <= 0) return fail(err, errlen, B200_EINVAL, "empty line block");
+    int rc = select_device(p.device, err, errlen);
+    if (rc != B200_OK) return rc;
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&pl->ev0));
+    CK(cudaEventCreate(&pl->ev1));
+    CK(cudaMalloc(&pl->d_stats, sizeof(GeoStats)));
+    CK(cudaMalloc(&pl->d_mid, sizeof(GeoMid)));
+    return B200_OK;
+}
+
+extern "C" int b200_geo_plan_create(const b200_geo_params *p, const double *lat, const double *lon, const double *hgt,
+                                    b200_geo_plan **plan, char *err, size_t errlen)
+{
+    if (!p || !plan) return fail(err, errlen, B200_EINVAL, "params/plan is NULL");
+    *plan = nullptr;
+    if (!lat || !lon || !hgt) return fail(err, errlen, B200_EINVAL, "lat/lon/hgt is NULL");
+    b200_geo_plan *pl = new (std::nothrow) b200_geo_plan;
+    if (!pl) return fail(err, errlen, B200_ENOMEM, "out of host memory");
+    pl->p = *p;
+    int rc = geo_plan_common(pl, err, errlen);
+    if (rc == B200_OK) {
+        const size_t npix = (size_t)pl->nlines * (size_t)p->dem_width, off = (size_t)pl->line0 * (size_t)p->dem_width;
+        auto up = [&](double **d, const double *h) -> int {
+            CK(cudaMalloc(d, sizeof(double) * npix));
+            CK(cudaMemcpyAsync(*d, h + off, sizeof(double) * npix, cudaMemcpyHostToDevice, pl->stream));
+            return B200_OK;
+        };
+        cudaEventRecord(pl->ev0, pl->stream);
+        rc = up(&pl->d_lat, lat);
+        if (rc == B200_OK) rc = up(&pl->d_lon, lon);
+        if (rc == B200_OK) rc = up(&pl->d_hgt, hgt);
+        if (rc == B200_OK) {
+            cudaEventRecord(pl->ev1, pl->stream);
+            cudaError_t e = cudaStreamSynchronize(pl->stream);
+            if (e != cudaSuccess) rc = fail(err, errlen, B200_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+            else cudaEventElapsedTime(&pl->ms_setup, pl->ev0, pl->ev1);
+        }
+    }
+    if (rc != B200_OK) {
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return B200_OK;
+}
+
+extern "C" int b200_geo_plan_create_from_topo(const b200_geo_params *p, b200_topo_plan *topo, b200_geo_plan **plan,
+                                              char *err, size_t errlen)
+{
+    if (!p || !plan || !topo) return fail(err, errlen, B200_EINVAL, "params/plan/topo is NULL");
+    *plan = nullptr;
+    if (!topo->executed) return fail(err, errlen, B200_EINVAL, "topo plan was not executed");
+    if (p->device != topo->p.device || p->dem_width != topo->p.width)
+        return fail(err, errlen, B200_EINVAL, "geo2rdr plan must live on the topo plan's device and share its width");
+    b200_geo_plan *pl = new (std::nothrow) b200_geo_plan;
+    if (!pl) return fail(err, errlen, B200_ENOMEM, "out of host memory");
+    pl->p = *p;
+    // the borrowed layers hold the topo plan's block of lines
+    pl->p.line0 = topo->line0;
+    pl->p.nlines = topo->nlines;
+    int rc = geo_plan_common(pl, err, errlen);
+    if (rc != B200_OK) {
+        delete pl;
+        return rc;
+    }
+    pl->owns_inputs = false;
+    pl->d_lat = topo->layers.lat;
+    pl->d_lon = topo->layers.lon;
+    pl->d_hgt = topo->layers.hgt;
+    *plan = pl;
+    return B200_OK;
+}
+
+extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *pp, const b200_orbit *orbit,
+                                     const b200_poly1d *dop, int want_azt, int want_rgm, int want_azoff, int want_rgoff,
+                                     float *ms_kernels, char *err, size_t errlen)
+{
+    if (!pl || !pp) return fail(err, errlen, B200_EINVAL, "plan/params is NULL");
+    const b200_geo_params &p = *pp;
+    int rc;
+    if ((rc = check_orbit(orbit, p.orbit_method, err, errlen)) != B200_OK) return rc;
+    if (!dop || !dop->coeffs || dop->order < 0 || dop->order + 1 > kMaxPoly1dCoeffs)
+        return fail(err, errlen, B200_EINVAL, "bad doppler polynomial");
+    if (p.dem_width != pl->p.dem_width) return fail(err, errlen, B200_EINVAL, "dem_width differs from the plan");
+    if (p.prf <= 0 || p.nazlooks < 1 || p.nrnglooks < 1) return fail(err, errlen, B200_EINVAL, "bad prf / looks");
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+
+    // ---- scalars of geo2rdr.f90:118-133 ----
+    GeoConst C{};
+    C.elp = Ellipsoid{p.major, p.e2};
+    C.wvl = p.wvl;
+    C.tstart = p.t0;
+    C.dtaz = p.nazlooks / p.prf;
+    C.tend = p.t0 + (p.length - 1) * C.dtaz;
+    C.tmid = 0.5 * (C.tstart + C.tend);
+    C.rngstart = p.rho0;
+    C.dmrg = p.nrnglooks * p.drho;
+    C.rngend = p.rho0 + (p.width - 1) * C.dmrg;
+    C.orbit_method = p.orbit_method;
+    C.bistatic = p.bistatic;
+    C.demwidth = p.dem_width;
+    const double pi = 4.0 * atan(1.0);
+    C.deg2rad = pi / 180.0;
+    C.sol = 299792458.0; // fortranUtils.f90:43-46
+    // ---- doppler-vs-range polynomial and its derivative (:161-189) ----
+    C.fd.order = dop->order;
+    C.fd.mean = p.rho0 + dop->mean * p.drho;
+    C.fd.norm = dop->norm * p.drho;
+    for (int k = 0; k <= dop->order; k++) C.fd.c[k] = dop->coeffs[k] * p.prf;
+    if (C.fd.order == 0) {
+        C.fdd.order = 0;
+        C.fdd.mean = 0.0;
+        C.fdd.norm = 1.0;
+        C.fdd.c[0] = 0.0;
+    } else {
+        C.fdd.order = C.fd.order - 1;
+        C.fdd.mean = C.fd.mean;
+        C.fdd.norm = C.fd.norm;
+        for (int k = 1; k <= dop->order; k++) C.fdd.c[k - 1] = k * C.fd.c[k] / C.fd.norm;
+    }
+
+    DeviceOrbit dorb;
+    if ((rc = upload_orbit(orbit, dorb, s, err, errlen)) != B200_OK) {
+        cudaFree(dorb.buf);
+        return rc;
+    }
+    struct Guard {
+        double *b;
+        ~Guard() { cudaFree(b); }
+    } guard{dorb.buf};
+
+    // ---- mid-scene state (:194-208) ----
+    CK(cudaEventRecord(pl->ev0, s));
+    launch_geo_setup(p.orbit_method, dorb.view, C.tmid, pl->d_mid, s);
+    GeoMid mid;
+    CK(cudaMemcpyAsync(&mid, pl->d_mid, sizeof mid, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (mid.stat_mid != 0) return fail(err, errlen, B200_EORBIT, "Cannot interpolate orbits at the center of scene.");
+    if (mid.stat_acc != 0) return fail(err, errlen, B200_EORBIT, "Cannot compute acceleration at the center of scene.");
+    C.xyz_mid = Vec3{mid.xyz[0], mid.xyz[1], mid.xyz[2]};
+    C.vel_mid = Vec3{mid.vel[0], mid.vel[1], mid.vel[2]};
+    C.acc_mid = Vec3{mid.acc[0], mid.acc[1], mid.acc[2]};
+
+    // ---- outputs ----
+    const int want[4] = {want_azt, want_rgm, want_azoff, want_rgoff};
+    const size_t npix = (size_t)pl->nlines * (size_t)p.dem_width;
+    const size_t esz = p.out_f32 ? 4 : 8;
+    for (int i = 0; i < 4; i++) {
+        if (pl->d_out[i] && (pl->out_f32 != p.out_f32 || !want[i])) {
+            cudaFree(pl->d_out[i]);
+            pl->d_out[i] = nullptr;
+        }
+        if (want[i] && !pl->d_out[i]) CK(cudaMalloc(&pl->d_out[i], esz * npix));
+        pl->want[i] = want[i];
+    }
+    pl->out_f32 = p.out_f32;
+    GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
+    CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
+    CK(cudaEventRecord(pl->ev0, s));
+    if (launch_geo2rdr(C, dorb.view, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    pl->launches = 2;
+    pl->executed = true;
+    if (ms_kernels) *ms_kernels = pl->ms_kernels;
+    return B200_OK;
+}
+
+extern "C" int b200_geo_plan_fetch(b200_geo_plan *pl, const b200_geo_outputs *out, b200_geo_result *res, char *err,
+                                   size_t errlen)
+{
+    if (!pl) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    if (!pl->executed) return fail(err, errlen, B200_EINVAL, "plan was not executed");
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    const size_t bytes = (size_t)pl->nlines * (size_t)pl->p.dem_width * (pl->out_f32 ? 4 : 8);
+    if (out) {
+        void *h[4] = {out->azt, out->rgm, out->azoff, out->rgoff};
+        for (int i = 0; i < 4; i++)
+            if (h[i] && pl->d_out[i]) CK(cudaMemcpyAsync(h[i], pl->d_out[i], bytes, cudaMemcpyDeviceToHost, s));
+    }
+    GeoStats st;
+    CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (res) {
+        res->num_outside = (long long)st.outside;
+        res->num_valid = (long long)st.valid;
+        res->num_converged = (long long)st.converged;
+        res->iterations = (long long)st.iterations;
+        res->ms_setup = pl->ms_setup;
+        res->ms_kernels = pl->ms_kernels;
+        res->ms_total = 0.f;
+        res->gpu_launches = pl->launches;
+    }
+    return B200_OK;
+}
+
+extern "C" void b200_geo_plan_destroy(b200_geo_plan *pl) { delete pl; }
+
+extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, const double *lon, const double *hgt,
+                                const b200_orbit *orbit, const b200_poly1d *dop, const b200_geo_outputs *out,
+                                b200_geo_result *res, char *err, size_t errlen)
+{
+    if (!out || (!out->azt && !out->rgm && !out->azoff && !out->rgoff))
+        return fail(err, errlen, B200_EINVAL, "No outputs requested from geo2rdr. Check again."); // Geo2rdr.py:271-274
+    const double t0 = now_ms();
+    b200_geo_plan *pl = nullptr;
+    int rc = b200_geo_plan_create(p, lat, lon, hgt, &pl, err, errlen);
+    if (rc != B200_OK) return rc;
+    rc = b200_geo_plan_execute(pl, p, orbit, dop, out->azt != nullptr, out->rgm != nullptr, out->azoff != nullptr,
+                               out->rgoff != nullptr, nullptr, err, errlen);
+    if (rc == B200_OK) rc = b200_geo_plan_fetch(pl, out, res, err, errlen);
+    b200_geo_plan_destroy(pl);
+    if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
+    return rc;
+}
+
+// =================================================================================================
+// utilities
+// =================================================================================================
+extern "C" int b200_abi_version(void) { return B200GEOM_ABI_VERSION; }
+
+extern "C" int b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int b200_device_name(int device, char *buf, size_t len)
+{
+    cudaDeviceProp prop;
+    if (!buf || !len) return B200_EINVAL;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        buf[0] = 0;
+        return B200_ENODEVICE;
+    }
+    snprintf(buf, len, "%s", prop.name);
+    return B200_OK;
+}
+
+extern "C" void *b200_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void b200_free_pinned(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// DFMA-saturating microbenchmark: 8 independent FMA chains per thread
+__global__ void k_fp64_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int b200_fp64_peak(int device, double *tflops, char *err, size_t errlen)
+{
+    int rc = select_device(device, err, errlen);
+    if (rc != B200_OK) return rc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (tflops) *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return B200_OK;
+}
+
+__global__ void k_primitive(int what, Ellipsoid e, OrbitView orb, const double *in, double *out)
+{
+    if (threadIdx.x != 0) return;
+    if (what == 0) {
+        Vec3 v = llh_to_xyz(e, in[0], in[1], in[2]);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    } else if (what == 1) {
+        xyz_to_llh(e, Vec3{in[0], in[1], in[2]}, out[0], out[1], out[2]);
+    } else {
+        Vec3 p = v3(0, 0, 0), v = v3(0, 0, 0);
+        int method = what == 2 ? 0 : (what == 3 ? 2 : 1);
+        int stat = orbit_interp(method, orb, in[0], p, v);
+        out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = v.x; out[4] = v.y; out[5] = v.z; out[6] = (double)stat;
+    }
+}
+
+extern "C" int b200_device_primitive(int device, int what, double a, double e2, const b200_orbit *orbit, const double *in,
+                                     double *out, char *err, size_t errlen)
+{
+    int rc = select_device(device, err, errlen);
+    if (rc != B200_OK) return rc;
+    if (what < 0 || what > 4 || !in || !out) return fail(err, errlen, B200_EINVAL, "bad primitive request");
+    DeviceOrbit dorb;
+    if (what >= 2) {
+        if (!orbit) return fail(err, errlen, B200_EINVAL, "orbit is NULL");
+        if ((rc = upload_orbit(orbit, dorb, 0, err, errlen)) != B200_OK) return rc;
+    }
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * 16));
+    CK(cudaMemcpy(d, in, sizeof(double) * 3, cudaMemcpyHostToDevice));
+    k_primitive<<<1, 32>>>(what, Ellipsoid{a, e2}, dorb.view, d, d + 8);
+    cudaError_t e = cudaMemcpy(out, d + 8, sizeof(double) * (what >= 2 ? 7 : 3), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(dorb.buf);
+    if (e != cudaSuccess) return fail(err, errlen, B200_ECUDA, "primitive kernel failed: %s", cudaGetErrorString(e));
+    return B200_OK;
+}

@@ -1,0 +1,205 @@
+// dem_interp.cuh -- DEM interpolators of the topozero path on a float32, lon-fastest DEM crop.
+//
+// Same window checks and BADVALUE (-1000) semantics as the reference wrappers
+// (components/zerodop/topozero/src/topozeroMethods.f:123-247).  ix/iy are the reference's
+// 1-based integer indices, fx/fy the float32-derived fractions widened to double.
+#pragma once
+
+#include "geom_device.cuh"
+
+namespace b2 {
+
+struct DemView {
+    const float *data; // [ny][nx], lon fastest == Fortran dem(nx, ny)
+    int nx, ny;
+};
+
+#ifdef __CUDA_ARCH__
+#define B2_LDG(p) __ldg(p)
+#else
+#define B2_LDG(p) (*(p))
+#endif
+
+B2_HD float dem_at(const DemView &d, int ix, int iy) // 1-based
+{
+    return B2_LDG(d.data + (size_t)(iy - 1) * (size_t)d.nx + (size_t)(ix - 1));
+}
+
+constexpr float kBadValue = -1000.0f; // topozeroMethods.f:33
+
+// uniform_interp.f90:13-44 called as bilinear(dy, dx, dem): evaluated in double on float32 taps
+B2_HD float interp_bilinear(const DemView &d, int i_x, int i_y, double f_x, double f_y)
+{
+    if ((i_x < 1) || (i_x >= d.nx)) return kBadValue;
+    if ((i_y < 1) || (i_y >= d.ny)) return kBadValue;
+    double x = i_y + f_y, y = i_x + f_x; // x: lat index, y: lon index (argument order of the reference call)
+    double x1 = floor(x), x2 = ceil(x), y1 = ceil(y), y2 = floor(y);
+    double q11 = dem_at(d, (int)y1, (int)x1);
+    double q12 = dem_at(d, (int)y2, (int)x1);
+    double q21 = dem_at(d, (int)y1, (int)x2);
+    double q22 = dem_at(d, (int)y2, (int)x2);
+    double r;
+    if (y1 == y2 && x1 == x2) r = q11;
+    else if (y1 == y2) r = (x2 - x) / (x2 - x1) * q11 + (x - x1) / (x2 - x1) * q21;
+    else if (x1 == x2) r = (y2 - y) / (y2 - y1) * q11 + (y - y1) / (y2 - y1) * q12;
+    else {
+        // (x2-x1)*(y2-y1) == 1 * -1: dividing by -1 is an exact sign flip
+        r = -(q11 * (x2 - x) * (y2 - y)) + -(q21 * (x - x1) * (y2 - y)) + -(q12 * (x2 - x) * (y - y1)) +
+            -(q22 * (x - x1) * (y - y1));
+    }
+    return (float)r;
+}
+
+// topozeroMethods.f:200-220
+B2_HD float interp_nearest(const DemView &d, int i_x, int i_y, double f_x, double f_y)
+{
+    int dx = (int)lround(i_x + f_x), dy = (int)lround(i_y + f_y);
+    if ((dx < 1) || (dx > d.nx)) return kBadValue;
+    if ((dy < 1) || (dy > d.ny)) return kBadValue;
+    return dem_at(d, dx, dy);
+}
+
+// uniform_interp.f90:123-130, DATA wt in column-major fill order: wt(i,k) = table[(k-1)*16 + (i-1)]
+#define B2_BICUBIC_WT { \
+    1, 0, -3, 2, 0, 0, 0, 0, -3, 0, 9, -6, 2, 0, -6, 4, \
+    0, 0, 0, 0, 0, 0, 0, 0, 3, 0, -9, 6, -2, 0, 6, -4, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 9, -6, 0, 0, -6, 4, \
+    0, 0, 3, -2, 0, 0, 0, 0, 0, 0, -9, 6, 0, 0, 6, -4, \
+    0, 0, 0, 0, 1, 0, -3, 2, -2, 0, 6, -4, 1, 0, -3, 2, \
+    0, 0, 0, 0, 0, 0, 0, 0, -1, 0, 3, -2, 1, 0, -3, 2, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -3, 2, 0, 0, 3, -2, \
+    0, 0, 0, 0, 0, 0, 3, -2, 0, 0, -6, 4, 0, 0, 3, -2, \
+    0, 1, -2, 1, 0, 0, 0, 0, 0, -3, 6, -3, 0, 2, -4, 2, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 3, -6, 3, 0, -2, 4, -2, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, 2, -2, \
+    0, 0, -1, 1, 0, 0, 0, 0, 0, 0, 3, -3, 0, 0, -2, 2, \
+    0, 0, 0, 0, 0, 1, -2, 1, 0, -2, 4, -2, 0, 1, -2, 1, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 2, -1, 0, 1, -2, 1, \
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 0, 0, -1, 1, \
+    0, 0, 0, 0, 0, 0, -1, 1, 0, 0, 2, -2, 0, 0, -1, 1}
+#ifdef __CUDACC__
+__device__ __constant__ static const signed char kBicubicWtDev[256] = B2_BICUBIC_WT;
+#endif
+static const signed char kBicubicWtHost[256] = B2_BICUBIC_WT;
+#ifdef __CUDA_ARCH__
+#define B2_BICUBIC_WT_AT(i) kBicubicWtDev[i]
+#else
+#define B2_BICUBIC_WT_AT(i) kBicubicWtHost[i]
+#endif
+
+// uniform_interp.f90:112-200 called as bicubic(dy, dx, dem).  z(a,b) == dem(lon=a, lat=b); sample
+// differences are float32 (the Fortran subtracts real*4 values); the dzdy(2..4) column typo is kept.
+B2_HD float interp_bicubic(const DemView &d, int i_x, int i_y, double f_x, double f_y)
+{
+    if ((i_x < 2) || (i_x >= (d.nx - 1))) return kBadValue;
+    if ((i_y < 2) || (i_y >= (d.ny - 1))) return kBadValue;
+    double x = i_y + f_y, y = i_x + f_x;
+    int x1 = (int)floor(x), x2 = (int)ceil(x), y1 = (int)floor(y), y2 = (int)ceil(y);
+#define Z(a, b) dem_at(d, (a), (b))
+    double q[16];
+    float f;
+    q[0] = Z(y1, x1);
+    q[3] = Z(y2, x1);
+    q[1] = Z(y1, x2);
+    q[2] = Z(y2, x2);
+    f = Z(y1, x1 + 1) - Z(y1, x1 - 1); q[4] = f / 2.0;
+    f = Z(y1, x2 + 1) - Z(y1, x2 - 1); q[5] = f / 2.0;
+    f = Z(y2, x2 + 1) - Z(y2, x2 - 1); q[6] = f / 2.0;
+    f = Z(y2, x1 + 1) - Z(y2, x1 - 1); q[7] = f / 2.0;
+    f = Z(y1 + 1, x1) - Z(y1 - 1, x1); q[8] = f / 2.0;
+    f = Z(y1 + 1, x2 + 1) - Z(y1 - 1, x2); q[9] = f / 2.0;
+    f = Z(y2 + 1, x2 + 1) - Z(y2 - 1, x2); q[10] = f / 2.0;
+    f = Z(y2 + 1, x1 + 1) - Z(y2 - 1, x1); q[11] = f / 2.0;
+    f = Z(y1 + 1, x1 + 1) - Z(y1 - 1, x1 + 1); f = f - Z(y1 + 1, x1 - 1); f = f + Z(y1 - 1, x1 - 1); q[12] = 0.25 * f;
+    f = Z(y2 + 1, x1 + 1) - Z(y2 - 1, x1 + 1); f = f - Z(y2 + 1, x1 - 1); f = f + Z(y2 - 1, x1 - 1); q[15] = 0.25 * f;
+    f = Z(y1 + 1, x2 + 1) - Z(y1 - 1, x2 + 1); f = f - Z(y1 + 1, x2 - 1); f = f + Z(y1 - 1, x2 - 1); q[13] = 0.25 * f;
+    f = Z(y2 + 1, x2 + 1) - Z(y2 - 1, x2 + 1); f = f - Z(y2 + 1, x2 - 1); f = f + Z(y2 - 1, x2 - 1); q[14] = 0.25 * f;
+#undef Z
+    double cl[16];
+    for (int i = 0; i < 16; i++) {
+        double qq = 0.0;
+        for (int k = 0; k < 16; k++) {
+            int w = B2_BICUBIC_WT_AT(k * 16 + i);
+            if (w != 0) qq = qq + (double)w * q[k]; // adding 0*q(k) never changes qq
+        }
+        cl[i] = qq;
+    }
+    double t = (x - x1), u = (y - y1), r = 0.0;
+    for (int i = 3; i >= 0; i--) r = t * r + ((cl[4 * i + 3] * u + cl[4 * i + 2]) * u + cl[4 * i + 1]) * u + cl[4 * i + 0];
+    return (float)r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "biquintic" == separable natural cubic spline over a 6x6 window (components/isceobj/Util/src/
+// spline.f:15-117 as called at topozeroMethods.f:196).  The spline of spline.f is linear in the six
+// samples and is always evaluated in the interval between the 2nd and 3rd node at X = 2 + frac, so it
+// reduces to six weights that are cubic polynomials of frac.  The second-derivative rows R(2), R(3)
+// come from the data-independent tridiagonal elimination of INITSPLINE (Q, P of spline.f:21-27):
+//   R(k) = sum_j Rk[j] * Y(j).
+// They are tabulated once on the host by running INITSPLINE on unit vectors (spline6_make_table).  The result
+// differs from the reference's own evaluation order only by double rounding (~1e-16 relative) and is
+// then rounded to float32 like the reference (sngl(temp), spline.f:115).
+// ---------------------------------------------------------------------------------------------
+// cubic-in-frac weight polynomials: w_j(xx) = tab[0][j] + xx*(tab[1][j] + xx*(tab[2][j] + xx*tab[3][j]))
+struct Spline6Table {
+    double c[4][6];
+};
+
+// Builds the table by running INITSPLINE's data-independent elimination on unit vectors (host, once):
+//   Q(1)=0; P=Q(k-1)/2+2; Q(k)=-0.5/P; R(k)=(3*(Y(k+1)-2Y(k)+Y(k-1))-R(k-1)/2)/P; back substitution;
+// then SPLINE at X = 2 + xx (J = 2, spline.f:50-52):
+//   S = Y2 + xx*((Y3 - Y2 - R2/3 - R3/6) + xx*(R2/2 + xx*(R3 - R2)/6))
+inline void spline6_make_table(Spline6Table &T)
+{
+    double Q[6], Rm[6][6];
+    for (int j = 0; j < 6; j++) Rm[0][j] = 0.0;
+    Q[0] = 0.0;
+    for (int K = 1; K <= 4; K++) { // Fortran K = 2..5
+        double P = Q[K - 1] / 2 + 2;
+        Q[K] = -0.5 / P;
+        for (int j = 0; j < 6; j++) {
+            double d2 = ((j == K + 1) ? 1.0 : 0.0) - 2.0 * ((j == K) ? 1.0 : 0.0) + ((j == K - 1) ? 1.0 : 0.0);
+            Rm[K][j] = (3 * d2 - Rm[K - 1][j] / 2) / P;
+        }
+    }
+    for (int j = 0; j < 6; j++) Rm[5][j] = 0.0;
+    for (int K = 4; K >= 1; K--)
+        for (int j = 0; j < 6; j++) Rm[K][j] = Q[K] * Rm[K + 1][j] + Rm[K][j];
+    for (int j = 0; j < 6; j++) {
+        double R2 = Rm[1][j], R3 = Rm[2][j];
+        T.c[0][j] = (j == 1) ? 1.0 : 0.0;
+        T.c[1][j] = ((j == 2) ? 1.0 : 0.0) - ((j == 1) ? 1.0 : 0.0) - R2 / 3 - R3 / 6;
+        T.c[2][j] = R2 / 2;
+        T.c[3][j] = (R3 - R2) / 6;
+    }
+}
+
+B2_HD float interp_biquintic(const DemView &d, const Spline6Table &T, int i_x, int i_y, double f_x, double f_y)
+{
+    if ((i_x < 3) || (i_x >= (d.nx - 2))) return kBadValue;
+    if ((i_y < 3) || (i_y >= (d.ny - 2))) return kBadValue;
+    double wx[6], wy[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        wx[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_x, T.c[2][j]), f_x, T.c[1][j]), f_x, T.c[0][j]);
+        wy[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_y, T.c[2][j]), f_y, T.c[1][j]), f_y, T.c[0][j]);
+    }
+    // window rows floor-1 .. floor+4 on both axes, indices clamped to [1, n] (spline.f:87-104)
+    double acc = 0.0;
+#pragma unroll
+    for (int I = 0; I < 6; I++) { // lon offset
+        int ix = i_x - 1 + I;
+        ix = ix < 1 ? 1 : (ix > d.nx ? d.nx : ix);
+        double hc = 0.0;
+#pragma unroll
+        for (int J = 0; J < 6; J++) { // lat offset
+            int iy = i_y - 1 + J;
+            iy = iy < 1 ? 1 : (iy > d.ny ? d.ny : iy);
+            hc = b2_fma(wy[J], (double)dem_at(d, ix, iy), hc);
+        }
+        acc = b2_fma(wx[I], hc, acc);
+    }
+    return (float)acc;
+}
+
+} // namespace b2

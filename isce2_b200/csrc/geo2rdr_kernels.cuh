@@ -1,0 +1,44 @@
+// geo2rdr_kernels.cuh -- device-side layout and launchers of the geo2rdr kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "geom_device.cuh"
+
+namespace b2 {
+
+constexpr int kGeoBlock = 128;
+constexpr int kGeoMaxSmemVectors = 512; // state vectors staged in shared memory (7 doubles each)
+
+// Scalars of geo2rdr.f90:118-208 (image limits, doppler-vs-range polynomials, mid-scene state).
+struct GeoConst {
+    Ellipsoid elp;
+    double wvl;
+    double tstart, tend, tmid, dtaz;
+    double rngstart, rngend, dmrg;
+    Poly1dDev fd, fdd; // fdvsrng, fddotvsrng (:161-189)
+    Vec3 xyz_mid, vel_mid, acc_mid;
+    int orbit_method, bistatic;
+    int demwidth;
+    double deg2rad, sol;
+};
+
+struct GeoLayers {
+    const double *lat, *lon, *hgt; // [nlines][demwidth] rows of the block, degrees / metres
+    void *azt, *rgm, *azoff, *rgoff; // [nlines][demwidth] float or double, may be null
+};
+
+struct GeoStats {
+    unsigned long long outside, valid, converged, iterations;
+};
+
+struct GeoMid { // result of k_geo_setup
+    double xyz[3], vel[3], acc[3];
+    int stat_mid, stat_acc;
+};
+
+void launch_geo_setup(int orbit_method, const OrbitView &orb, double tmid, GeoMid *d_out, cudaStream_t s);
+int launch_geo2rdr(const GeoConst &C, const OrbitView &orb, int line0, int nlines, const GeoLayers &L, int out_f32,
+                   GeoStats *stats, cudaStream_t s);
+
+} // namespace b2

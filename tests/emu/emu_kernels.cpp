@@ -1,0 +1,76 @@
+// emu_kernels.cpp -- DEVELOPMENT AID (tests only): compiles the per-pixel device functions of
+// isce2_b200/csrc/*.cuh for the host with g++ and loops over pixels on the CPU, so that the kernel
+// arithmetic can be compared bit-for-bit with the oracle in a container without a GPU.
+// It is never loaded by the product; the GPU parity tests (-m gpu) are the real check.
+#include <cstdint>
+#include <cstring>
+
+#include "../../isce2_b200/csrc/topo_pixel.cuh"
+
+using namespace b2;
+
+extern "C" {
+
+struct EmuTopoArgs {
+    double a, e2, wvl, thresh;
+    int ilrl, numiter, extraiter;
+    double ufirstlat, ufirstlon, deltalat, deltalon;
+    int nx, ny, method, width, length, nazlooks;
+    double t0, prf, peghdg;
+    int orbit_method;
+    int n_orbit;
+    int dop_range_order, dop_azimuth_order;
+    double r0, dr;
+    int line0, nlines, want_inc;
+};
+
+int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const double *opos, const double *ovel,
+             const double *dop_coeffs, double *lat, double *lon, double *hgt, float *los, float *inc, double *ctrack,
+             float *elev, long long *iters)
+{
+    TopoConst C;
+    memset(&C, 0, sizeof C);
+    C.elp = Ellipsoid{A->a, A->e2};
+    C.wvl = A->wvl; C.thresh = A->thresh; C.ilrl = A->ilrl; C.numiter = A->numiter; C.extraiter = A->extraiter;
+    C.ufirstlat = A->ufirstlat; C.ufirstlon = A->ufirstlon; C.deltalat = A->deltalat; C.deltalon = A->deltalon;
+    C.dem = DemView{dem, A->nx, A->ny};
+    C.method = A->method; C.width = A->width; C.length = A->length; C.nazlooks = A->nazlooks;
+    C.t0 = A->t0; C.prf = A->prf; C.peghdg = A->peghdg;
+    C.pi = 4.0 * atan(1.0); C.r2d = 180.0 / C.pi; C.orbit_method = A->orbit_method;
+    C.dop.range_order = A->dop_range_order; C.dop.azimuth_order = A->dop_azimuth_order;
+    C.dop.norm_range = C.dop.norm_azimuth = 1.0;
+    memcpy(C.dop.c, dop_coeffs, sizeof(double) * (A->dop_range_order + 1) * (A->dop_azimuth_order + 1));
+    C.slr.range_order = 1; C.slr.azimuth_order = 0; C.slr.norm_range = C.slr.norm_azimuth = 1.0;
+    C.slr.c[0] = A->r0; C.slr.c[1] = A->dr;
+    spline6_make_table(C.spl);
+    OrbitView orb{A->n_orbit, ot, opos, ovel};
+    long long it = 0;
+    for (int row = 0; row < A->nlines; row++) {
+        int line = A->line0 + row;
+        double tline = C.t0 + C.nazlooks * ((double)(line + 1) - 1.0) / C.prf;
+        Vec3 p = v3(0, 0, 0), v = v3(0, 0, 0);
+        orbit_interp(C.orbit_method, orb, tline, p, v);
+        LineState L;
+        make_line_state(C.elp, p, v, C.peghdg, L);
+        for (int pix = 0; pix < A->width; pix++) {
+            double rng = eval_poly2d(C.slr, (double)line, (double)pix);
+            double dop = eval_poly2d(C.dop, (double)line, (double)pix);
+            PixelResult R;
+            switch (A->method) {
+            case 1: topo_pixel<1>(C, L, rng, dop, A->want_inc != 0, R); break;
+            case 2: topo_pixel<2>(C, L, rng, dop, A->want_inc != 0, R); break;
+            case 3: topo_pixel<3>(C, L, rng, dop, A->want_inc != 0, R); break;
+            default: topo_pixel<5>(C, L, rng, dop, A->want_inc != 0, R); break;
+            }
+            size_t w = A->width, o = (size_t)row * w + pix;
+            lat[o] = R.lat; lon[o] = R.lon; hgt[o] = R.hgt;
+            los[(size_t)row * 2 * w + pix] = R.los0; los[(size_t)row * 2 * w + w + pix] = R.los1;
+            inc[(size_t)row * 2 * w + pix] = R.inc0; inc[(size_t)row * 2 * w + w + pix] = R.inc1;
+            ctrack[o] = R.ctrack; elev[o] = R.elev;
+            it += R.iters;
+        }
+    }
+    *iters = it;
+    return 0;
+}
+}
