@@ -126,6 +126,8 @@ typedef struct {
     float dem_max;
     float ms_setup;   /* device time: bbox + DEM upload/crop + per-line state */
     float ms_kernels; /* device time: per-pixel solve (+ mask), CUDA events on the launch stream */
+    float ms_pixels;  /* ... of which the per-pixel kernel */
+    float ms_mask;    /* ... of which the layover/shadow kernel (0 when no mask was requested) */
     float ms_total;   /* wall time of the call, host<->device copies included */
     int gpu_launches; /* kernels launched by this call */
 } b200_topo_result;

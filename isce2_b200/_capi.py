@@ -62,7 +62,8 @@ class TopoResult(C.Structure):
     _fields_ = [("min_lat", C.c_double), ("max_lat", C.c_double), ("min_lon", C.c_double), ("max_lon", C.c_double),
                 ("converged", C.c_longlong), ("iterations", C.c_longlong),
                 ("dem_x0", C.c_int), ("dem_y0", C.c_int), ("dem_nx", C.c_int), ("dem_ny", C.c_int),
-                ("dem_max", C.c_float), ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_total", C.c_float),
+                ("dem_max", C.c_float), ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_pixels", C.c_float),
+                ("ms_mask", C.c_float), ("ms_total", C.c_float),
                 ("gpu_launches", C.c_int)]
 
 

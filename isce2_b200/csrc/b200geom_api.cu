@@ -132,7 +132,8 @@ struct b200_topo_plan {
     MaskScratch scr{};
     int mask_grid = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+    float ms_pixels = 0.f, ms_mask = 0.f;
     int dem_x0 = 0, dem_y0 = 0;
     float dem_max = 0.f;
     float ms_setup = 0.f, ms_kernels = 0.f;
@@ -170,6 +171,7 @@ struct b200_topo_plan {
         cudaFree(scr.oflag);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (evm) cudaEventDestroy(evm);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -203,6 +205,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&pl->ev0));
     CK(cudaEventCreate(&pl->ev1));
+    CK(cudaEventCreate(&pl->evm));
     cudaStream_t s = pl->stream;
     CK(cudaEventRecord(pl->ev0, s));
 
@@ -402,6 +405,7 @@ extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, cha
     if (launch_topo_pixels(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the pixel kernel (method %d, %d lines)", pl->C.method, pl->nlines);
     int launches = 1;
+    CK(cudaEventRecord(pl->evm, s));
     if (pl->layers.mask) {
         if (launch_topo_mask(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->dem_max, pl->scr, pl->mask_grid, s) != 0)
             return fail(err, errlen, B200_EINVAL, "cannot launch the mask kernel");
@@ -411,6 +415,8 @@ extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, cha
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    CK(cudaEventElapsedTime(&pl->ms_pixels, pl->ev0, pl->evm));
+    CK(cudaEventElapsedTime(&pl->ms_mask, pl->evm, pl->ev1));
     if (!pl->executed) pl->launches += launches;
     pl->executed = true;
     if (ms_kernels) *ms_kernels = pl->ms_kernels;
@@ -450,6 +456,8 @@ extern "C" int b200_topo_plan_fetch(b200_topo_plan *pl, const b200_topo_outputs 
         res->dem_max = pl->dem_max;
         res->ms_setup = pl->ms_setup;
         res->ms_kernels = pl->ms_kernels;
+        res->ms_pixels = pl->ms_pixels;
+        res->ms_mask = pl->ms_mask;
         res->ms_total = 0.f;
         res->gpu_launches = pl->launches;
     }
@@ -687,7 +695,7 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
     pl->out_f32 = p.out_f32;
     GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
     CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
-    CK(cudaEventRecord(pl->ev0, s));
+    // ev0 was recorded before the mid-scene setup kernel: ms_kernels covers setup + solve
     if (launch_geo2rdr(C, dorb.view, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
     CK(cudaEventRecord(pl->ev1, s));

@@ -60,10 +60,12 @@ def compare_topo(g, c):
     return st
 
 
-def secondary_kwargs(sc, sec, misreg_az=0.013, misreg_rg=1.7):
-    """geo2rdr inputs of a secondary acquisition as topsStack builds them (contrib/stack/topsStack/geo2rdr.py:90-91)."""
+def secondary_kwargs(sc, sec, misreg_az=0.013, misreg_rg=1.7, recenter=0.0):
+    """geo2rdr inputs of a secondary acquisition as topsStack builds them (contrib/stack/topsStack/geo2rdr.py:90-91):
+    sensingStart - misreg_az, startingRange - misreg_rg.  The synthetic secondary flies 0.37 s ahead of the
+    reference; short test scenes pass recenter=0.37 so that its acquisition window still covers the scene."""
     return dict(orbit_t=sec.orbit_t, orbit_pos=sec.orbit_pos, orbit_vel=sec.orbit_vel, length=sc.length, width=sc.width,
-                r0=sc.r0 - misreg_rg, dr=sc.dr, prf=sc.prf, t0=sc.t0 - misreg_az, wvl=sc.wvl, side=sc.side)
+                r0=sc.r0 - misreg_rg, dr=sc.dr, prf=sc.prf, t0=sc.t0 - misreg_az - recenter, wvl=sc.wvl, side=sc.side)
 
 
 def gpu_geo2rdr(lat, lon, hgt, kw, *, out_f32=False, orbit_method="HERMITE", bistatic=False, doppler_coeffs=(0.0,),

@@ -34,7 +34,7 @@ def main():
             print(json.dumps(st), flush=True)
             if method == "BILINEAR":
                 sec = synth.config_c1_secondary(length=L, width=W)
-                kw = pu.secondary_kwargs(sc, sec)
+                kw = pu.secondary_kwargs(sc, sec, recenter=0.37)
                 for om in ("HERMITE", "LEGENDRE"):
                     if om == "LEGENDRE" and len(sec.orbit_t) < 9:
                         continue
