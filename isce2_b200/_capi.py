@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200geom.so")
+# B200GEOM_LIB lets a developer A/B an experimental build of the same ABI (never a different backend)
+LIB_PATH = os.environ.get("B200GEOM_LIB") or os.path.join(_HERE, "libb200geom.so")
 
 B200_OK = 0
 ERRORS = {-1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "EORBIT", -5: "EDEM", -6: "ENOMEM"}

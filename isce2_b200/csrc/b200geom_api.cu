@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -211,7 +212,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
 
     // ---- constants ----
     TopoConst &C = pl->C;
-    C.elp = Ellipsoid{p.major, p.e2};
+    C.elp = make_ellipsoid(p.major, p.e2);
     C.wvl = p.wvl;
     C.thresh = p.thresh;
     C.ilrl = p.look_side;
@@ -228,6 +229,9 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     C.peghdg = p.peg_heading;
     C.pi = 4.0 * atan(1.0); // fortranUtils.f90:38-41
     C.r2d = 180.0 / C.pi;
+    C.inv_r2d = 1.0 / C.r2d;
+    C.inv_dlat = 1.0 / p.delta_lat;
+    C.inv_dlon = 1.0 / p.delta_lon;
     C.orbit_method = p.orbit_method;
     if ((rc = fill_poly2d(dop, C.dop, "doppler", err, errlen)) != B200_OK) return rc;
     if (slrng) {
@@ -275,6 +279,20 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     }
     if (nok == 0 || !(min_lat <= max_lat) || !(min_lon <= max_lon))
         return fail(err, errlen, B200_EORBIT, "Error getting statevector for bounds computation");
+    // reference angles for the in-kernel trigonometry (geom_device.cuh: RefAngle): centre of the corner points;
+    // used only when every corner lies well inside the series' range, otherwise the kernels use libm
+    {
+        const double d2r = C.pi / 180.0;
+        const double clat = 0.5 * (min_lat + max_lat) * d2r, clon = 0.5 * (min_lon + max_lon) * d2r;
+        C.ref.lat = make_ref_angle(clat);
+        C.ref.lon = make_ref_angle(clon);
+        const double elat = fmax(fabs(max_lat * d2r - C.ref.lat.a0), fabs(min_lat * d2r - C.ref.lat.a0));
+        const double elon = fmax(fabs(max_lon * d2r - C.ref.lon.a0), fabs(min_lon * d2r - C.ref.lon.a0));
+        // 0.03 rad of slack: pixels inside the scene can bulge past the corner box, and the DEM-edge clamps
+        // never move a point by more than the 0.15 deg margin
+        C.ref.use_ref = (elat + 0.03 <= C.ref.lat.dmax && elon + 0.03 <= C.ref.lon.dmax) ? 1 : 0;
+        if (getenv("B200_FORCE_LIBM_TRIG")) C.ref.use_ref = 0; // developer switch for A/B measurements
+    }
     const double MARGIN = 0.15; // topozeroState.f:74-75
     min_lon -= MARGIN; max_lon += MARGIN; min_lat -= MARGIN; max_lat += MARGIN;
 
@@ -626,7 +644,7 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
 
     // ---- scalars of geo2rdr.f90:118-133 ----
     GeoConst C{};
-    C.elp = Ellipsoid{p.major, p.e2};
+    C.elp = make_ellipsoid(p.major, p.e2);
     C.wvl = p.wvl;
     C.tstart = p.t0;
     C.dtaz = p.nazlooks / p.prf;
@@ -870,7 +888,7 @@ extern "C" int b200_device_primitive(int device, int what, double a, double e2, 
     double *d = nullptr;
     CK(cudaMalloc(&d, sizeof(double) * 16));
     CK(cudaMemcpy(d, in, sizeof(double) * 3, cudaMemcpyHostToDevice));
-    k_primitive<<<1, 32>>>(what, Ellipsoid{a, e2}, dorb.view, d, d + 8);
+    k_primitive<<<1, 32>>>(what, make_ellipsoid(a, e2), dorb.view, d, d + 8);
     cudaError_t e = cudaMemcpy(out, d + 8, sizeof(double) * (what >= 2 ? 7 : 3), cudaMemcpyDeviceToHost);
     cudaFree(d);
     cudaFree(dorb.buf);

@@ -178,26 +178,26 @@ B2_HD float interp_biquintic(const DemView &d, const Spline6Table &T, int i_x, i
 {
     if ((i_x < 3) || (i_x >= (d.nx - 2))) return kBadValue;
     if ((i_y < 3) || (i_y >= (d.ny - 2))) return kBadValue;
-    double wx[6], wy[6];
+    // window floor-1 .. floor+4 on both axes, indices clamped to [1, n] (spline.f:87-104); only the last
+    // column / row of the window can leave the grid once the checks above passed
+    double wx[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-        wx[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_x, T.c[2][j]), f_x, T.c[1][j]), f_x, T.c[0][j]);
-        wy[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_y, T.c[2][j]), f_y, T.c[1][j]), f_y, T.c[0][j]);
-    }
-    // window rows floor-1 .. floor+4 on both axes, indices clamped to [1, n] (spline.f:87-104)
+    for (int j = 0; j < 6; j++) wx[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_x, T.c[2][j]), f_x, T.c[1][j]), f_x, T.c[0][j]);
+    const int x5 = (i_x + 4 > d.nx) ? d.nx : i_x + 4;
     double acc = 0.0;
 #pragma unroll
-    for (int I = 0; I < 6; I++) { // lon offset
-        int ix = i_x - 1 + I;
-        ix = ix < 1 ? 1 : (ix > d.nx ? d.nx : ix);
-        double hc = 0.0;
-#pragma unroll
-        for (int J = 0; J < 6; J++) { // lat offset
-            int iy = i_y - 1 + J;
-            iy = iy < 1 ? 1 : (iy > d.ny ? d.ny : iy);
-            hc = b2_fma(wy[J], (double)dem_at(d, ix, iy), hc);
-        }
-        acc = b2_fma(wx[I], hc, acc);
+    for (int J = 0; J < 6; J++) { // latitude rows: six consecutive longitudes per row (one or two 32-byte sectors)
+        int iy = i_y - 1 + J;
+        iy = iy > d.ny ? d.ny : iy;
+        const float *row = d.data + (size_t)(iy - 1) * (size_t)d.nx + (size_t)(i_x - 2);
+        double hc = wx[0] * (double)B2_LDG(row);
+        hc = b2_fma(wx[1], (double)B2_LDG(row + 1), hc);
+        hc = b2_fma(wx[2], (double)B2_LDG(row + 2), hc);
+        hc = b2_fma(wx[3], (double)B2_LDG(row + 3), hc);
+        hc = b2_fma(wx[4], (double)B2_LDG(row + 4), hc);
+        hc = b2_fma(wx[5], (double)B2_LDG(d.data + (size_t)(iy - 1) * (size_t)d.nx + (size_t)(x5 - 1)), hc);
+        double wy = b2_fma(b2_fma(b2_fma(T.c[3][J], f_y, T.c[2][J]), f_y, T.c[1][J]), f_y, T.c[0][J]);
+        acc = b2_fma(wy, hc, acc);
     }
     return (float)acc;
 }

@@ -30,7 +30,7 @@
 #else
 // host emulation follows the oracle literally: latlon.F:62 uses **(1/3) == pow
 #define B2_CBRT(x) pow((x), 1.0 / 3.0)
-#define b2_fma(a, b, c) ((a) * (b) + (c))
+#define b2_fma(a, b, c) fma((a), (b), (c))
 #endif
 
 namespace b2 {
@@ -56,11 +56,195 @@ B2_HD Vec3 unitvec(const Vec3 &v)
 B2_HD Vec3 sub(const Vec3 &a, const Vec3 &b) { return Vec3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 B2_HD Vec3 add(const Vec3 &a, const Vec3 &b) { return Vec3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 
-struct Ellipsoid {
-    double a, e2;
+// a / b for a divisor whose correctly rounded reciprocal rb = RN(1/b) is known (hoisted per scene, per line or per
+// pixel).  q0 = RN(a*rb) is within one ulp of the quotient, the residual a - q0*b is exact in an FMA, and the
+// corrected quotient rounds correctly (Markstein 1990): the result is the IEEE quotient at 3 FP64 instructions
+// instead of the ~30 of a full division, so the reference's divisions can be kept bit for bit.
+B2_HD double div_r(double a, double b, double rb)
+{
+    double q = a * rb;
+    double r = b2_fma(-q, b, a);
+    return b2_fma(r, rb, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IEEE-exact division and square root in ~8-11 FP64 instructions.
+//
+// CUDA's own double-precision `/` and sqrt() expand to ~30 / ~20 executed instructions (special-case handling
+// included) and drag a slow path into the instruction stream.  For normal, finite operands the sequences below
+// give the same correctly rounded result: a hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits), two Newton
+// steps to ~1 ulp, then one residual correction whose residual is exact in an FMA; the corrected value differs from
+// the infinitely precise one by O(2^-100) before the final rounding, so it can only miss the correctly rounded
+// result when the exact value lies within ~1e-30 (relative) of a rounding boundary.  The host emulation uses the
+// IEEE operators themselves.
+// ---------------------------------------------------------------------------------------------
+B2_HD double rcp_n(double b) // ~1 ulp reciprocal
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    y = __fma_rn(__fma_rn(-b, y, 1.0), y, y);
+    y = __fma_rn(__fma_rn(-b, y, 1.0), y, y);
+    return y;
+#else
+    return 1.0 / b;
+#endif
+}
+
+B2_HD double div_n(double a, double b) // a / b, correctly rounded (see above)
+{
+#ifdef __CUDA_ARCH__
+    return div_r(a, b, rcp_n(b));
+#else
+    return a / b;
+#endif
+}
+
+// sqrt(x) correctly rounded (see above) and, optionally, ~1 ulp 1/sqrt(x); x must be a positive normal number or 0
+B2_HD double sqrt_n(double x, double *rs = nullptr)
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    double d = __fma_rn(-g, g, x);
+    g = __fma_rn(d, h, g);
+    if (rs) *rs = h + h;
+    return x == 0.0 ? 0.0 : g;
+#else
+    double g = sqrt(x);
+    if (rs) *rs = 1.0 / g;
+    return g;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trigonometry about a reference angle.
+//
+// Inside one block of azimuth lines every latitude (longitude) handled by the kernels lies within a few hundredths
+// of a radian of a reference angle a0.  a0 is chosen on the host as an exact multiple of 2^-6 rad, and sin(a0),
+// cos(a0) are carried as double-double (hi + lo, evaluated in extended precision on the host).  Then
+//   atan2(y, x)  = a0 + atan(t),  t = (y*c0 - x*s0) / (x*c0 + y*s0)        (|t| small: short odd series)
+//   sin(a0 + d)  = s0 + (c0*sin d - s0*(1 - cos d)),  cos likewise          (|d| small: short series)
+// with the cancelling products formed exactly (FMA error terms).  The results carry ~0.5 ulp total error, i.e. they
+// are as close to correctly rounded as glibc's own atan2/sin/cos, at a third of the instructions of the generic
+// libm routines and without their slow paths.
+// ---------------------------------------------------------------------------------------------
+struct RefAngle {
+    double a0;             // exact multiple of 2^-6 rad
+    double sh, sl, ch, cl; // sin(a0) = sh + sl, cos(a0) = ch + cl
+    double dmax;           // largest |angle - a0| the series below are good for
 };
 
-// latlon.F:44-49 (LLH_2_XYZ), llh in radians
+// host only: extended-precision constants of a reference angle near `approx`
+inline RefAngle make_ref_angle(double approx)
+{
+    RefAngle R;
+    R.a0 = nearbyint(approx * 64.0) / 64.0;
+    long double s = sinl((long double)R.a0), c = cosl((long double)R.a0);
+    R.sh = (double)s;
+    R.sl = (double)(s - (long double)R.sh);
+    R.ch = (double)c;
+    R.cl = (double)(c - (long double)R.ch);
+    R.dmax = 0.12;
+    return R;
+}
+
+// atan2(y, x) for a direction within R.dmax of R.a0
+B2_HD double atan2_ref(const RefAngle &R, double y, double x)
+{
+    // N = y*c0 - x*s0 with both products exact (hi + fma error), D = x*c0 + y*s0
+    double p1 = y * R.ch, e1 = b2_fma(y, R.ch, -p1);
+    double p2 = x * R.sh, e2 = b2_fma(x, R.sh, -p2);
+    double N = (p1 - p2) + ((e1 - e2) + (y * R.cl - x * R.sl));
+    double D = b2_fma(x, R.ch, y * R.sh);
+    double t = N * rcp_n(D);
+    double t2 = t * t;
+    // odd Taylor series of atan through t^23 (|t| <= 0.12: remainder < 4e-25)
+    double pol = -1.0 / 23.0;
+    pol = b2_fma(pol, t2, 1.0 / 21.0);
+    pol = b2_fma(pol, t2, -1.0 / 19.0);
+    pol = b2_fma(pol, t2, 1.0 / 17.0);
+    pol = b2_fma(pol, t2, -1.0 / 15.0);
+    pol = b2_fma(pol, t2, 1.0 / 13.0);
+    pol = b2_fma(pol, t2, -1.0 / 11.0);
+    pol = b2_fma(pol, t2, 1.0 / 9.0);
+    pol = b2_fma(pol, t2, -1.0 / 7.0);
+    pol = b2_fma(pol, t2, 1.0 / 5.0);
+    pol = b2_fma(pol, t2, -1.0 / 3.0);
+    double at = b2_fma(t * t2, pol, t); // t + t^3 * pol
+    return R.a0 + at;
+}
+
+// sin and cos of theta = R.a0 + d, |d| <= R.dmax
+B2_HD void sincos_ref(const RefAngle &R, double theta, double &sn, double &cs)
+{
+    double d = theta - R.a0; // exact: both are within a factor two of each other or d is tiny
+    double d2 = d * d;
+    // S = sin d = d + d^3 * ps ; Cm = 1 - cos d = d^2 * pc   (|d| <= 0.12: remainders < 1e-24)
+    double ps = 1.0 / 6227020800.0;                 // 1/13!
+    ps = b2_fma(ps, d2, -1.0 / 39916800.0);         // -1/11!
+    ps = b2_fma(ps, d2, 1.0 / 362880.0);            // 1/9!
+    ps = b2_fma(ps, d2, -1.0 / 5040.0);             // -1/7!
+    ps = b2_fma(ps, d2, 1.0 / 120.0);               // 1/5!
+    ps = b2_fma(ps, d2, -1.0 / 6.0);                // -1/3!
+    double S = b2_fma(d * d2, ps, d);
+    double pc = -1.0 / 87178291200.0;               // -1/14!
+    pc = b2_fma(pc, d2, 1.0 / 479001600.0);         // 1/12!
+    pc = b2_fma(pc, d2, -1.0 / 3628800.0);          // -1/10!
+    pc = b2_fma(pc, d2, 1.0 / 40320.0);             // 1/8!
+    pc = b2_fma(pc, d2, -1.0 / 720.0);              // -1/6!
+    pc = b2_fma(pc, d2, 1.0 / 24.0);                // 1/4!
+    pc = b2_fma(pc, d2, -0.5);                      // -1/2!
+    double Cm = -(d2 * pc);                         // 1 - cos d  (>= 0)
+    // sin(a0 + d) = s0 + [c0*S - s0*Cm],  cos(a0 + d) = c0 - [s0*S + c0*Cm]; low words of s0, c0 folded in
+    sn = R.sh + (b2_fma(R.ch, S, -(R.sh * Cm)) + b2_fma(R.cl, S, R.sl));
+    cs = R.ch + (-(b2_fma(R.sh, S, R.ch * Cm)) + b2_fma(-R.sl, S, R.cl));
+}
+
+struct Ellipsoid {
+    double a, e2;
+    // derived once (host): a^2 and its reciprocal, 1 - e2, e2^2, RN(1/6)
+    double q3, inv_q3, ome2, e4, inv6;
+};
+
+// reference angles of one block of lines (see RefAngle); use_ref = 0 falls back to the generic libm routines
+struct GeoRef {
+    RefAngle lat, lon;
+    int use_ref;
+};
+
+B2_HD Ellipsoid make_ellipsoid(double a, double e2)
+{
+    Ellipsoid e;
+    e.a = a;
+    e.e2 = e2;
+    e.q3 = a * a;
+    e.inv_q3 = 1.0 / e.q3;
+    e.ome2 = 1.0 - e2;
+    e.e4 = e2 * e2;
+    e.inv6 = 1.0 / 6.0;
+    return e;
+}
+
+// latlon.F:44-49 (LLH_2_XYZ) from the sines / cosines of the angles
+B2_HD Vec3 llh_to_xyz_sc(const Ellipsoid &e, double sl, double cl, double so, double co, double h)
+{
+    double re = div_n(e.a, sqrt_n(1.0 - e.e2 * (sl * sl)));
+    Vec3 v;
+    v.x = (re + h) * cl * co;
+    v.y = (re + h) * cl * so;
+    v.z = (re * (1.0 - e.e2) + h) * sl;
+    return v;
+}
+
+// latlon.F:44-49 (LLH_2_XYZ), llh in radians, generic libm trigonometry (setup kernels, fallback path)
 B2_HD Vec3 llh_to_xyz(const Ellipsoid &e, double lat, double lon, double h)
 {
     double sl, cl, so, co;
@@ -70,46 +254,91 @@ B2_HD Vec3 llh_to_xyz(const Ellipsoid &e, double lat, double lon, double h)
 #else
     sl = sin(lat); cl = cos(lat); so = sin(lon); co = cos(lon);
 #endif
-    double re = e.a / sqrt(1.0 - e.e2 * (sl * sl));
-    Vec3 v;
-    v.x = (re + h) * cl * co;
-    v.y = (re + h) * cl * so;
-    v.z = (re * (1.0 - e.e2) + h) * sl;
-    return v;
+    return llh_to_xyz_sc(e, sl, cl, so, co, h);
 }
 
-// latlon.F:51-71 (XYZ_2_LLH): closed form; returns lat, lon (rad) and height
-B2_HD void xyz_to_llh(const Ellipsoid &e, const Vec3 &v, double &lat, double &lon, double &h)
+// same, trigonometry about the block's reference angles
+B2_HD Vec3 llh_to_xyz_ref(const Ellipsoid &e, const GeoRef &G, double lat, double lon, double h)
+{
+    double sl, cl, so, co;
+    sincos_ref(G.lat, lat, sl, cl);
+    sincos_ref(G.lon, lon, so, co);
+    return llh_to_xyz_sc(e, sl, cl, so, co, h);
+}
+
+// latlon.F:51-71 (XYZ_2_LLH): closed form; returns k and d (lat = atan2(z, d)).
+// Divisions by the scene constants a^2 and 6 use div_r, the others div_n, square roots sqrt_n: all IEEE-exact.
+// The reference's  t = (1 + s + sqrt(s(2+s)))**(1/3);  u = r*(1 + t + 1/t)  is evaluated through
+//   t + 1/t = 2 cosh(acosh(1+s)/3) = 2 (1 + e),   9e + 12e^2 + 4e^3 = s,
+// whose reverted series in s converges fast because s <= 13.5 e2^2 ~ 6e-4 on an Earth-like ellipsoid (the generic
+// cube-root form is kept for s >= 4e-3).  u feeds d only through k/(k+e2), which damps its rounding noise by
+// ~e2/2 = 1/300, so this re-association is far below one ulp of the latitude.
+B2_HD void xyz_to_llh_core(const Ellipsoid &e, const Vec3 &v, double &k, double &d)
 {
     double q2 = (v.x * v.x + v.y * v.y);
-    double q3 = e.a * e.a;
-    double e4 = e.e2 * e.e2;
-    double p = q2 / q3;
-    double q = (1.0 - e.e2) * (v.z * v.z) / q3;
-    double r = (p + q - e4) / 6.0;
-    double s = (e4 * p * q) / (4.0 * (r * r * r));
-    double t = B2_CBRT(1.0 + s + sqrt(s * (2.0 + s)));
-    double u = r * (1.0 + t + 1.0 / t);
-    double rv = sqrt(u * u + e4 * q);
-    double w = e.e2 * (u + rv - q) / (2.0 * rv);
-    double k = sqrt(u + rv + w * w) - w;
-    double d = k * sqrt(q2) / (k + e.e2);
+    double p = div_r(q2, e.q3, e.inv_q3);
+    double q = div_r(e.ome2 * (v.z * v.z), e.q3, e.inv_q3);
+    double r = div_r(p + q - e.e4, 6.0, e.inv6);
+    double s = div_n(e.e4 * p * q, 4.0 * (r * r * r));
+    double u;
+    if (s < 4.0e-3) {
+        double ee = 82688.0 / 1162261467.0;
+        ee = b2_fma(ee, s, -23296.0 / 129140163.0);
+        ee = b2_fma(ee, s, 2288.0 / 4782969.0);
+        ee = b2_fma(ee, s, -80.0 / 59049.0);
+        ee = b2_fma(ee, s, 28.0 / 6561.0);
+        ee = b2_fma(ee, s, -4.0 / 243.0);
+        ee = b2_fma(ee, s, 1.0 / 9.0);
+        ee = ee * s;
+        u = r * b2_fma(2.0, ee, 3.0);
+    } else {
+        double t = B2_CBRT(1.0 + s + sqrt(s * (2.0 + s)));
+        u = r * (1.0 + t + 1.0 / t);
+    }
+    double rv = sqrt_n(u * u + e.e4 * q);
+    double w = div_n(e.e2 * (u + rv - q), 2.0 * rv);
+    k = sqrt_n(u + rv + w * w) - w;
+    d = div_n(k * sqrt_n(q2), k + e.e2);
+}
+
+// lat, lon (rad) and height; generic libm arctangent
+B2_HD void xyz_to_llh(const Ellipsoid &e, const Vec3 &v, double &lat, double &lon, double &h)
+{
+    double k, d;
+    xyz_to_llh_core(e, v, k, d);
     lat = atan2(v.z, d);
     lon = atan2(v.y, v.x);
-    h = (k + e.e2 - 1.0) * sqrt(d * d + v.z * v.z) / k;
+    h = div_n((k + e.e2 - 1.0) * sqrt_n(d * d + v.z * v.z), k);
+}
+
+// same about the block's reference angles; want_h = false skips the height (the iteration never uses it)
+template <bool WANT_H>
+B2_HD void xyz_to_llh_ref(const Ellipsoid &e, const GeoRef &G, const Vec3 &v, double &lat, double &lon, double &h)
+{
+    double k, d;
+    xyz_to_llh_core(e, v, k, d);
+    lat = atan2_ref(G.lat, v.z, d);
+    lon = atan2_ref(G.lon, v.y, v.x);
+    if (WANT_H) h = div_n((k + e.e2 - 1.0) * sqrt_n(d * d + v.z * v.z), k);
+}
+
+// lat, lon only with libm (fallback path of the iteration)
+B2_HD void xyz_to_latlon(const Ellipsoid &e, const Vec3 &v, double &lat, double &lon)
+{
+    double k, d;
+    xyz_to_llh_core(e, v, k, d);
+    lat = atan2(v.z, d);
+    lon = atan2(v.y, v.x);
 }
 
 // curvature.F:26-64
-B2_HD double reast(const Ellipsoid &e, double lat)
+B2_HD double reast_s(const Ellipsoid &e, double s /* sin(lat) */) { return div_n(e.a, sqrt_n(1.0 - e.e2 * (s * s))); }
+B2_HD double reast(const Ellipsoid &e, double lat) { return reast_s(e, sin(lat)); }
+B2_HD double rnorth_s(const Ellipsoid &e, double s /* sin(lat) */)
 {
-    double s = sin(lat);
-    return e.a / sqrt(1.0 - e.e2 * (s * s));
-}
-B2_HD double rnorth(const Ellipsoid &e, double lat)
-{
-    double s = sin(lat);
     return (e.a * (1.0 - e.e2)) / pow(1.0 - e.e2 * (s * s), 1.5);
 }
+B2_HD double rnorth(const Ellipsoid &e, double lat) { return rnorth_s(e, sin(lat)); }
 B2_HD double rdir(const Ellipsoid &e, double hdg, double lat)
 {
     double re = reast(e, lat), rn = rnorth(e, lat);
@@ -126,6 +355,10 @@ struct LineState {
     Vec3 ov;
     double nv; // dot(nhat, vhat)
     double vt; // dot(vhat, that)
+    // hoisted reciprocals (IEEE, so that div_r reproduces the reference's divisions exactly)
+    double aa, inv_aa; // height + rcurv
+    double inv_vt, inv_vmag;
+    double rc2, inv_rc2; // rcurv^2
 };
 
 // tcnbasis.F:26-39 + radar_to_xyz.F:49-92 + topozero.f90:381-424
@@ -164,6 +397,12 @@ B2_HD void make_line_state(const Ellipsoid &e, const Vec3 &pos, const Vec3 &vel,
     L.ov = Vec3{p.x - L.rcurv * (clt * clo), p.y - L.rcurv * (clt * slo), p.z - L.rcurv * slt};
     L.nv = dot(L.nhat, L.vhat);
     L.vt = dot(L.vhat, L.that);
+    L.aa = L.height + L.rcurv;
+    L.inv_aa = 1.0 / L.aa;
+    L.inv_vt = 1.0 / L.vt;
+    L.inv_vmag = 1.0 / L.vmag;
+    L.rc2 = L.rcurv * L.rcurv;
+    L.inv_rc2 = 1.0 / L.rc2;
 }
 
 // convert_sch_to_xyz.F:63-72 (XYZ_2_SCH), height component only.  The spherical latlon call
@@ -171,21 +410,20 @@ B2_HD void make_line_state(const Ellipsoid &e, const Vec3 &pos, const Vec3 &vel,
 // order so that the SCH height matches the CPU path bit for bit.
 B2_HD double sch_height(const LineState &L, const Vec3 &xyz)
 {
-    double tx = 1.0 * xyz.x + (-1.0) * L.ov.x, ty = 1.0 * xyz.y + (-1.0) * L.ov.y, tz = 1.0 * xyz.z + (-1.0) * L.ov.z;
+    double tx = xyz.x - L.ov.x, ty = xyz.y - L.ov.y, tz = xyz.z - L.ov.z; // lincomb(1, xyz, -1, ov)
     double sx = L.minv[0] * tx + L.minv[1] * ty + L.minv[2] * tz;
     double sy = L.minv[3] * tx + L.minv[4] * ty + L.minv[5] * tz;
     double sz = L.minv[6] * tx + L.minv[7] * ty + L.minv[8] * tz;
     double q2 = (sx * sx + sy * sy);
-    double q3 = L.rcurv * L.rcurv;
-    double p = q2 / q3;
-    double q = (1.0 - 0.0) * (sz * sz) / q3;
-    double r = (p + q - 0.0) / 6.0;
-    // e2 = 0: s = 0, t = 1, u = 3 r, rv = sqrt(u*u) = u, w = 0, k = sqrt(2 u)
-    double u = r * (1.0 + 1.0 + 1.0 / 1.0);
-    double rv = sqrt(u * u);
-    double k = sqrt(u + rv);
-    double d = k * sqrt(q2) / k;
-    return (k - 1.0) * sqrt(d * d + sz * sz) / k;
+    double p = div_r(q2, L.rc2, L.inv_rc2);
+    double q = div_r(sz * sz, L.rc2, L.inv_rc2); // (1 - 0) * sz^2 / a^2
+    double r = div_r(p + q, 6.0, 1.0 / 6.0);     // (p + q - 0) / 6
+    // e2 = 0: s = 0, t = 1, u = r * (1 + 1 + 1/1), rv = sqrt(u*u) == u (exact for u > 0), w = 0, k = sqrt(u + rv)
+    double u = r * 3.0;
+    double rk;
+    double k = sqrt_n(u + u, &rk);
+    double d = div_r(k * sqrt_n(q2), k, rk);
+    return div_r((k - 1.0) * sqrt_n(d * d + sz * sz), k, rk);
 }
 
 // ---------------------------------------------------------------------------------------------

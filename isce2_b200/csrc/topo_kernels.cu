@@ -89,7 +89,6 @@ __global__ void k_topo_bbox(const __grid_constant__ TopoConst C, OrbitView orb, 
     int pixel = ind * (C.width - 1);
     double rng = pixel_range(C, 0, pixel); // the bbox stage reads row 1 of both accessors (:196-197)
     double dop = eval_poly2d(C.dop, 0.0, (double)pixel);
-    double dopfact = (0.5 * C.wvl * dop / L.vmag) * rng;
     double la, lo, h;
     if (rng <= (L.height - hgts[it] + 1.0)) { // near-nadir: pick the nadir point (:232-235)
         la = L.lat_sat;
@@ -97,7 +96,8 @@ __global__ void k_topo_bbox(const __grid_constant__ TopoConst C, OrbitView orb, 
     } else {
         double ct, st;
         Vec3 delta, xyz;
-        range_sphere(C, L, rng, dopfact, hgts[it], ct, st, delta, xyz);
+        PixelConst P = make_pixel_const(C, L, rng, dop);
+        range_sphere(C, L, P, hgts[it], ct, st, delta, xyz);
         xyz_to_llh(C.elp, xyz, la, lo, h);
     }
     out[3 * tid + 0] = la * C.r2d;
@@ -152,14 +152,17 @@ __global__ void k_line_setup(const __grid_constant__ TopoConst C, OrbitView orb,
 // -------------------------------------------------------------------------------------------------
 // per-pixel solve
 // -------------------------------------------------------------------------------------------------
-template <int METHOD>
-__global__ void __launch_bounds__(kTopoBlock)
+#ifndef B2_TOPO_MINBLOCKS
+#define B2_TOPO_MINBLOCKS 8
+#endif
+template <int METHOD, bool REF>
+__global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
 k_topo_pixels(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, TopoLayers out,
               TopoStats *stats)
 {
     __shared__ LineState sL;
-    __shared__ double s_red[4][kTopoBlock / 32];
-    __shared__ int s_cnt[2][kTopoBlock / 32];
+    __shared__ long long s_mm[4];          // order keys: min lat, max lat, min lon, max lon
+    __shared__ unsigned int s_cnt[3];      // converged, iterations, warps done
     const int bpl = (C.width + kTopoBlock - 1) / kTopoBlock; // CTAs per azimuth line
     const int row = blockIdx.x / bpl;                        // row within the block of lines
     const int seg = blockIdx.x - row * bpl;
@@ -167,6 +170,11 @@ k_topo_pixels(const __grid_constant__ TopoConst C, const LineState *__restrict__
         const double *src = reinterpret_cast<const double *>(states + row);
         double *dst = reinterpret_cast<double *>(&sL);
         for (int i = threadIdx.x; i < (int)(sizeof(LineState) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) {
+            s_mm[0] = s_mm[2] = 0x7fffffffffffffffLL;
+            s_mm[1] = s_mm[3] = (long long)0x8000000000000000ULL;
+            s_cnt[0] = s_cnt[1] = s_cnt[2] = 0u;
+        }
     }
     __syncthreads();
     const int pix = seg * blockDim.x + threadIdx.x;
@@ -177,7 +185,7 @@ k_topo_pixels(const __grid_constant__ TopoConst C, const LineState *__restrict__
         double rng = pixel_range(C, line, pix);
         double dop = eval_poly2d(C.dop, (double)line, (double)pix);
         PixelResult R;
-        topo_pixel<METHOD>(C, sL, rng, dop, out.inc != nullptr, R);
+        topo_pixel<METHOD, REF>(C, sL, rng, dop, out.inc != nullptr, R);
         const size_t w = (size_t)C.width;
         const size_t o = (size_t)row * w + (size_t)pix;
         out.lat[o] = R.lat;
@@ -200,32 +208,28 @@ k_topo_pixels(const __grid_constant__ TopoConst C, const LineState *__restrict__
         conv = R.converged;
         iters = R.iters;
     }
-    // block reduction of the scene statistics (topozero.f90:712-715, :570)
+    // Scene statistics (topozero.f90:712-715, :570) without a block-wide barrier: every warp folds its values into
+    // shared memory as it finishes and leaves; the last warp to arrive publishes the CTA's totals.  Early-converged
+    // warps therefore never wait for the slow ones.
     mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
     conv = warp_sum(conv); iters = warp_sum(iters);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        s_red[0][wid] = mnlat; s_red[1][wid] = mxlat; s_red[2][wid] = mnlon; s_red[3][wid] = mxlon;
-        s_cnt[0][wid] = conv; s_cnt[1][wid] = iters;
-    }
-    __syncthreads();
-    if (wid == 0) {
-        const int nw = blockDim.x >> 5;
-        mnlat = lane < nw ? s_red[0][lane] : 1e300;
-        mxlat = lane < nw ? s_red[1][lane] : -1e300;
-        mnlon = lane < nw ? s_red[2][lane] : 1e300;
-        mxlon = lane < nw ? s_red[3][lane] : -1e300;
-        conv = lane < nw ? s_cnt[0][lane] : 0;
-        iters = lane < nw ? s_cnt[1][lane] : 0;
-        mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
-        conv = warp_sum(conv); iters = warp_sum(iters);
-        if (lane == 0) {
-            atomicMin(&stats->min_lat, order_key(mnlat));
-            atomicMax(&stats->max_lat, order_key(mxlat));
-            atomicMin(&stats->min_lon, order_key(mnlon));
-            atomicMax(&stats->max_lon, order_key(mxlon));
-            atomicAdd(&stats->converged, (unsigned long long)conv);
-            atomicAdd(&stats->iterations, (unsigned long long)iters);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&s_mm[0], order_key(mnlat));
+        atomicMax(&s_mm[1], order_key(mxlat));
+        atomicMin(&s_mm[2], order_key(mnlon));
+        atomicMax(&s_mm[3], order_key(mxlon));
+        atomicAdd(&s_cnt[0], (unsigned int)conv);
+        atomicAdd(&s_cnt[1], (unsigned int)iters);
+        __threadfence_block();
+        const unsigned int done = atomicAdd(&s_cnt[2], 1u);
+        if (done == (blockDim.x >> 5) - 1) {
+            __threadfence_block();
+            atomicMin(&stats->min_lat, atomicMin(&s_mm[0], 0x7fffffffffffffffLL));
+            atomicMax(&stats->max_lat, atomicMax(&s_mm[1], (long long)0x8000000000000000ULL));
+            atomicMin(&stats->min_lon, atomicMin(&s_mm[2], 0x7fffffffffffffffLL));
+            atomicMax(&stats->max_lon, atomicMax(&s_mm[3], (long long)0x8000000000000000ULL));
+            atomicAdd(&stats->converged, (unsigned long long)atomicAdd(&s_cnt[0], 0u));
+            atomicAdd(&stats->iterations, (unsigned long long)atomicAdd(&s_cnt[1], 0u));
         }
     }
 }
@@ -365,7 +369,7 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
     __syncthreads();
 }
 
-template <int METHOD>
+template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kMaskBlock)
 k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines, TopoLayers out,
             float demmax, MaskScratch scr)
@@ -440,7 +444,7 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             int it = ref_binarysearch([&](int m) { return cs[m - 1]; }, w, aa);
             if (it == w) it = w - 1;
             if (it == 0) it = 1;
-            orng[p] = mask_resample<METHOD>(C, sL, cs, lats, lons, it, aa);
+            orng[p] = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
         }
         __syncthreads();
 
@@ -508,17 +512,24 @@ void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int 
     k_line_setup<<<(nlines + 63) / 64, 64, 0, s>>>(C, orb, line0, nlines, states);
 }
 
+template <int METHOD>
+static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, const TopoLayers &out, TopoStats *stats,
+                            unsigned grid, cudaStream_t s)
+{
+    if (C.ref.use_ref) k_topo_pixels<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
+    else k_topo_pixels<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
+}
+
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
                        TopoStats *stats, cudaStream_t s)
 {
     const long long nblk = (long long)((C.width + kTopoBlock - 1) / kTopoBlock) * nlines;
     if (nblk > 0x7fffffffLL) return -2;
-    dim3 grid((unsigned)nblk);
     switch (C.method) {
-    case 1: k_topo_pixels<1><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats); break;
-    case 2: k_topo_pixels<2><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats); break;
-    case 3: k_topo_pixels<3><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats); break;
-    case 5: k_topo_pixels<5><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats); break;
+    case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, s); break;
+    case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, s); break;
+    case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, s); break;
+    case 5: launch_pixels_m<5>(C, states, line0, out, stats, (unsigned)nblk, s); break;
     default: return -1;
     }
     return 0;
@@ -530,27 +541,28 @@ int mask_grid_size(int nlines)
     return nlines < g ? nlines : g;
 }
 
+template <int METHOD>
+static void launch_mask_m(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
+                          float demmax, const MaskScratch &scr, int grid, size_t smem, cudaStream_t s)
+{
+    if (C.ref.use_ref) {
+        cudaFuncSetAttribute(k_topo_mask<METHOD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_topo_mask<METHOD, true><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
+    } else {
+        cudaFuncSetAttribute(k_topo_mask<METHOD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_topo_mask<METHOD, false><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
+    }
+}
+
 int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out, float demmax,
                      const MaskScratch &scr, int grid, cudaStream_t s)
 {
     size_t smem = (size_t)((C.width + 3) / 4) * 4;
     switch (C.method) {
-    case 1:
-        cudaFuncSetAttribute(k_topo_mask<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<1><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
-        break;
-    case 2:
-        cudaFuncSetAttribute(k_topo_mask<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<2><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
-        break;
-    case 3:
-        cudaFuncSetAttribute(k_topo_mask<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<3><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
-        break;
-    case 5:
-        cudaFuncSetAttribute(k_topo_mask<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<5><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
-        break;
+    case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
+    case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
+    case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
+    case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     default: return -1;
     }
     return 0;

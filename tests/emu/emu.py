@@ -17,7 +17,7 @@ class EmuTopoArgs(C.Structure):
                 ("nazlooks", C.c_int), ("t0", C.c_double), ("prf", C.c_double), ("peghdg", C.c_double),
                 ("orbit_method", C.c_int), ("n_orbit", C.c_int), ("dop_range_order", C.c_int),
                 ("dop_azimuth_order", C.c_int), ("r0", C.c_double), ("dr", C.c_double),
-                ("line0", C.c_int), ("nlines", C.c_int), ("want_inc", C.c_int)]
+                ("line0", C.c_int), ("nlines", C.c_int), ("want_inc", C.c_int), ("use_ref", C.c_int)]
 
 
 def build():
@@ -26,11 +26,12 @@ def build():
     newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(hdr_dir, f)) for f in os.listdir(hdr_dir)
                                             if f.endswith(".cuh")])
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-std=c++17", "-o", LIB, src])
     return C.CDLL(LIB)
 
 
-def topo(sc, crop, *, dem_method=1, orbit_method=0, want_inc=True, numiter=25, extraiter=10, thresh=0.05, line0=0, nlines=-1):
+def topo(sc, crop, *, dem_method=1, orbit_method=0, want_inc=True, numiter=25, extraiter=10, thresh=0.05, line0=0, nlines=-1,
+         use_ref=True):
     """sc: synth.Scene; crop: dict with ustartx, ustarty, udemwidth, udemlength, ufirstlat, ufirstlon (from the oracle)."""
     L = build()
     x0, y0, nx, ny = crop["ustartx"], crop["ustarty"], crop["udemwidth"], crop["udemlength"]
@@ -40,7 +41,7 @@ def topo(sc, crop, *, dem_method=1, orbit_method=0, want_inc=True, numiter=25, e
     A = EmuTopoArgs(sc.a, sc.e2, sc.wvl, thresh, sc.side, numiter, extraiter, crop["ufirstlat"], crop["ufirstlon"],
                     sc.delta_lat, sc.delta_lon, nx, ny, dem_method, sc.width, sc.length, sc.nazlooks, sc.t0, sc.prf,
                     sc.peg_heading, orbit_method, len(sc.orbit_t), dop.shape[1] - 1, dop.shape[0] - 1, sc.r0,
-                    sc.dr * sc.nrnglooks, line0, n, int(want_inc))
+                    sc.dr * sc.nrnglooks, line0, n, int(want_inc), int(use_ref))
     w = sc.width
     out = dict(lat=np.empty((n, w)), lon=np.empty((n, w)), hgt=np.empty((n, w)), los=np.empty((n, 2, w), np.float32),
                inc=np.empty((n, 2, w), np.float32), ctrack=np.empty((n, w)), elev=np.empty((n, w), np.float32))

@@ -21,7 +21,7 @@ struct EmuTopoArgs {
     int n_orbit;
     int dop_range_order, dop_azimuth_order;
     double r0, dr;
-    int line0, nlines, want_inc;
+    int line0, nlines, want_inc, use_ref;
 };
 
 int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const double *opos, const double *ovel,
@@ -30,19 +30,26 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
 {
     TopoConst C;
     memset(&C, 0, sizeof C);
-    C.elp = Ellipsoid{A->a, A->e2};
+    C.elp = make_ellipsoid(A->a, A->e2);
     C.wvl = A->wvl; C.thresh = A->thresh; C.ilrl = A->ilrl; C.numiter = A->numiter; C.extraiter = A->extraiter;
     C.ufirstlat = A->ufirstlat; C.ufirstlon = A->ufirstlon; C.deltalat = A->deltalat; C.deltalon = A->deltalon;
     C.dem = DemView{dem, A->nx, A->ny};
     C.method = A->method; C.width = A->width; C.length = A->length; C.nazlooks = A->nazlooks;
     C.t0 = A->t0; C.prf = A->prf; C.peghdg = A->peghdg;
     C.pi = 4.0 * atan(1.0); C.r2d = 180.0 / C.pi; C.orbit_method = A->orbit_method;
+    C.inv_r2d = 1.0 / C.r2d; C.inv_dlat = 1.0 / C.deltalat; C.inv_dlon = 1.0 / C.deltalon;
     C.dop.range_order = A->dop_range_order; C.dop.azimuth_order = A->dop_azimuth_order;
     C.dop.norm_range = C.dop.norm_azimuth = 1.0;
     memcpy(C.dop.c, dop_coeffs, sizeof(double) * (A->dop_range_order + 1) * (A->dop_azimuth_order + 1));
     C.slr.range_order = 1; C.slr.azimuth_order = 0; C.slr.norm_range = C.slr.norm_azimuth = 1.0;
     C.slr.c[0] = A->r0; C.slr.c[1] = A->dr;
     spline6_make_table(C.spl);
+    {
+        const double d2r = C.pi / 180.0;
+        C.ref.lat = make_ref_angle((C.ufirstlat + 0.5 * C.deltalat * A->ny) * d2r);
+        C.ref.lon = make_ref_angle((C.ufirstlon + 0.5 * C.deltalon * A->nx) * d2r);
+        C.ref.use_ref = A->use_ref;
+    }
     OrbitView orb{A->n_orbit, ot, opos, ovel};
     long long it = 0;
     for (int row = 0; row < A->nlines; row++) {
@@ -56,11 +63,21 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
             double rng = eval_poly2d(C.slr, (double)line, (double)pix);
             double dop = eval_poly2d(C.dop, (double)line, (double)pix);
             PixelResult R;
-            switch (A->method) {
-            case 1: topo_pixel<1>(C, L, rng, dop, A->want_inc != 0, R); break;
-            case 2: topo_pixel<2>(C, L, rng, dop, A->want_inc != 0, R); break;
-            case 3: topo_pixel<3>(C, L, rng, dop, A->want_inc != 0, R); break;
-            default: topo_pixel<5>(C, L, rng, dop, A->want_inc != 0, R); break;
+            const bool winc = A->want_inc != 0;
+            if (A->use_ref) {
+                switch (A->method) {
+                case 1: topo_pixel<1, true>(C, L, rng, dop, winc, R); break;
+                case 2: topo_pixel<2, true>(C, L, rng, dop, winc, R); break;
+                case 3: topo_pixel<3, true>(C, L, rng, dop, winc, R); break;
+                default: topo_pixel<5, true>(C, L, rng, dop, winc, R); break;
+                }
+            } else {
+                switch (A->method) {
+                case 1: topo_pixel<1, false>(C, L, rng, dop, winc, R); break;
+                case 2: topo_pixel<2, false>(C, L, rng, dop, winc, R); break;
+                case 3: topo_pixel<3, false>(C, L, rng, dop, winc, R); break;
+                default: topo_pixel<5, false>(C, L, rng, dop, winc, R); break;
+                }
             }
             size_t w = A->width, o = (size_t)row * w + pix;
             lat[o] = R.lat; lon[o] = R.lon; hgt[o] = R.hgt;

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Kernel timings + parity spot check of the current build (run on the GPU box).  Prints one JSON line per case."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from isce2_b200 import _capi, synth  # noqa: E402
+from tests import parity_util as pu  # noqa: E402
+
+
+def perf(lines=1500, width=25000, reps=3):
+    sc = synth.make_scene(lines, width)
+    sec = synth.make_scene(lines, width, dem=False, perturb=dict(da=120.0, d_cross=80.0, d_along_s=0.37))
+    out = {}
+    for method, inc, mask in (("BILINEAR", False, False), ("BIQUINTIC", True, True)):
+        p = _capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                              delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
+                              side=sc.side, peg_heading=sc.peg_heading, dem_method=method)
+        tp = _capi.TopoPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]],
+                            want_los=True, want_inc=inc, want_mask=mask)
+        best = None
+        for _ in range(reps):
+            tp.execute()
+            import ctypes as C
+            res = _capi.TopoResult()
+            e = C.create_string_buffer(512)
+            _capi._check(_capi.lib().b200_topo_plan_fetch(tp.handle, None, C.byref(res), e, 512), e)
+            if best is None or res.ms_pixels < best[0]:
+                best = (res.ms_pixels, res.ms_mask, res.iterations / float(lines * width))
+        out[method] = dict(ms_pixels=round(best[0], 3), ms_mask=round(best[1], 3), K=round(best[2], 3),
+                           gpix_s=round(lines * width / best[0] / 1e6, 3))
+        if method == "BILINEAR":
+            gp = _capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0 - 1.7, dr=sc.dr,
+                                  prf=sc.prf, t0=sc.t0 - 0.013, wvl=sc.wvl, side=sc.side, out_f32=True)
+            g = _capi.GeoPlan(gp, topo_plan=tp)
+            ms = min(g.execute(gp, sec.orbit_t, sec.orbit_pos, sec.orbit_vel, want=("azoff", "rgoff")) for _ in range(reps))
+            out["GEO2RDR_HERMITE"] = dict(ms=round(ms, 3), gpix_s=round(lines * width / ms / 1e6, 3))
+            g.close()
+        tp.close()
+    return out
+
+
+def parity(L=96, W=8192):
+    sc = pu.rough_scene(L, W)
+    rep = {}
+    for method in ("BILINEAR", "BIQUINTIC"):
+        g = pu.gpu_topo(sc, dem_method=method)
+        c = pu.cpu_topo(sc, dem_method=method)
+        st = pu.compare_topo(g, c)
+        rep[method] = {k: (st[k]["n_over"], float("%.3g" % st[k]["max"]), round(st[k]["n_exact"] / st[k]["n"], 4))
+                       for k in ("lat", "lon", "hgt", "los", "inc")}
+        rep[method]["mask_diff"] = st["mask"]["n_diff"]
+        rep[method]["iters_equal"] = st["iters"]["gpu"] == st["iters"]["cpu"]
+    return rep
+
+
+if __name__ == "__main__":
+    tag = os.environ.get("B200GEOM_LIB", "default")
+    print(json.dumps({"lib": tag, "perf": perf()}), flush=True)
+    if "--no-parity" not in sys.argv:
+        print(json.dumps({"lib": tag, "parity(n_over,max,exact_frac)": parity()}), flush=True)
