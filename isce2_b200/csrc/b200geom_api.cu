@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "geo2rdr_kernels.cuh"
+#include "orbit_poly.h"
 #include "topo_kernels.cuh"
 
 using namespace b2;
@@ -714,8 +715,33 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
     GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
     CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
     // ev0 was recorded before the mid-scene setup kernel: ms_kernels covers setup + solve
-    if (launch_geo2rdr(C, dorb.view, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
+    double *d_poly = nullptr;
+    struct PolyGuard {
+        double **p;
+        ~PolyGuard() { cudaFree(*p); }
+    } pguard{&d_poly};
+    if (p.orbit_method == B200_ORBIT_HERMITE || p.orbit_method == B200_ORBIT_LEGENDRE) {
+        // Hermite / Legendre: Newton solve on per-window orbit polynomials (orbit_poly.h)
+        HostOrbitPoly hp;
+        if (!build_orbit_poly(p.orbit_method, orbit->nvec, orbit->t, orbit->pos, orbit->vel, hp))
+            return fail(err, errlen, B200_EORBIT, "cannot build the orbit polynomials");
+        const size_t nt = (size_t)hp.n, nw = (size_t)hp.nwin, nc = hp.cp.size(), nv = hp.cv.size();
+        std::vector<double> blob(nt + 2 * nw + nc + nv);
+        memcpy(blob.data(), orbit->t, sizeof(double) * nt);
+        memcpy(blob.data() + nt, hp.tc.data(), sizeof(double) * nw);
+        memcpy(blob.data() + nt + nw, hp.inv_h.data(), sizeof(double) * nw);
+        memcpy(blob.data() + nt + 2 * nw, hp.cp.data(), sizeof(double) * nc);
+        if (nv) memcpy(blob.data() + nt + 2 * nw + nc, hp.cv.data(), sizeof(double) * nv);
+        CK(cudaMalloc(&d_poly, sizeof(double) * blob.size()));
+        CK(cudaMemcpyAsync(d_poly, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s)); // blob goes out of scope
+        OrbitPolyView op{hp.method, hp.n, hp.nwin, hp.ncoef, d_poly, d_poly + nt, d_poly + nt + nw, d_poly + nt + 2 * nw,
+                         nv ? d_poly + nt + 2 * nw + nc : nullptr};
+        if (launch_geo2rdr_poly(C, op, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
+            return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
+    } else if (launch_geo2rdr(C, dorb.view, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0) {
         return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
+    }
     CK(cudaEventRecord(pl->ev1, s));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));

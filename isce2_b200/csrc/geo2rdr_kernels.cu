@@ -148,6 +148,183 @@ k_geo2rdr(const __grid_constant__ GeoConst C, OrbitView orb_g, int line0, int nl
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Newton solve on per-window orbit polynomials
+// -------------------------------------------------------------------------------------------------
+// The reference iterates  t <- t - fn/fnprime  with fnprime = -v.v + (fdop/r + fdop')(dr.v): the acceleration term
+// is multiplied by zero (geo2rdr.f90:271), so it converges linearly (ratio ~0.1) and stops at |dt| < 5e-9 s, i.e. up
+// to ~6e-10 s (3e-7 azimuth pixels) short of the root of fn(t) = dr.v - fdop(r) r.  This kernel solves the same
+// equation for the same root with the true derivative (acceleration from the orbit polynomial) until |dt| < 1e-10 s;
+// its first step is the reference's own first step so that the reference's out-of-span test on the first iterate
+// (geo2rdr.f90:287-291, the only iterate that can overshoot by seconds) is reproduced.  Final range / validity tests
+// are the reference's (:308-329), evaluated at the converged state.
+struct OrbState {
+    Vec3 x, v, a;
+};
+
+template <int METHOD>
+__device__ __forceinline__ int poly_window(const OrbitPolyView &op, double time)
+{
+    // first i with t[i] >= time (orbit.c:203-206); epochs are ascending
+    int i = 0;
+    while (i < op.n && __ldg(op.t + i) < time) i++;
+    const int back = (METHOD == 0) ? 2 : 5, span = (METHOD == 0) ? 4 : 9;
+    int w = i - back;
+    w = w < 0 ? 0 : w;
+    w = w > op.n - span ? op.n - span : w;
+    return w;
+}
+
+template <int METHOD>
+__device__ __forceinline__ void poly_state(const OrbitPolyView &op, double time, OrbState &S)
+{
+    const int w = poly_window<METHOD>(op, time);
+    const double ih = __ldg(op.inv_h + w);
+    const double s = (time - __ldg(op.tc + w)) * ih;
+    constexpr int NC = (METHOD == 0) ? 8 : 9;
+    double xo[3], vo[3], ao[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double *cp = op.cp + ((size_t)w * 3 + c) * NC;
+        if (METHOD == 0) { // position, first and second derivative from one coefficient set
+            double p = __ldg(cp), dp = 0.0, ddp = 0.0;
+#pragma unroll
+            for (int k = 1; k < NC; k++) {
+                ddp = __fma_rn(ddp, s, dp);
+                dp = __fma_rn(dp, s, p);
+                p = __fma_rn(p, s, __ldg(cp + k));
+            }
+            xo[c] = p;
+            vo[c] = dp * ih;
+            ao[c] = 2.0 * ddp * ih * ih;
+        } else { // Legendre: velocity is its own polynomial; acceleration = d/dt of it
+            const double *cv = op.cv + ((size_t)w * 3 + c) * NC;
+            double p = __ldg(cp), q = __ldg(cv), dq = 0.0;
+#pragma unroll
+            for (int k = 1; k < NC; k++) {
+                dq = __fma_rn(dq, s, q);
+                q = __fma_rn(q, s, __ldg(cv + k));
+                p = __fma_rn(p, s, __ldg(cp + k));
+            }
+            xo[c] = p;
+            vo[c] = q;
+            ao[c] = dq * ih;
+        }
+    }
+    S.x = Vec3{xo[0], xo[1], xo[2]};
+    S.v = Vec3{vo[0], vo[1], vo[2]};
+    S.a = Vec3{ao[0], ao[1], ao[2]};
+}
+
+__device__ __forceinline__ double poly1d_fast(const Poly1dDev &p, double inv_norm, double x)
+{
+    if (p.order == 0) return p.c[0];
+    const double xv = (x - p.mean) * inv_norm;
+    double v = p.c[p.order];
+    for (int i = p.order - 1; i >= 0; i--) v = __fma_rn(v, xv, p.c[i]);
+    return v;
+}
+
+template <int METHOD, typename T>
+__global__ void __launch_bounds__(kGeoBlock)
+k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, int nlines, GeoLayers L, GeoStats *stats)
+{
+    const int bpl = (C.demwidth + kGeoBlock - 1) / kGeoBlock;
+    const int row = blockIdx.x / bpl;
+    const int pix = (blockIdx.x - row * bpl) * blockDim.x + threadIdx.x;
+    unsigned int n_out = 0, n_valid = 0, n_conv = 0, n_it = 0;
+    if (pix < C.demwidth) {
+        const double BAD_VALUE = (double)(-999999.0f);
+        const int line = line0 + row;
+        const size_t o = (size_t)row * (size_t)C.demwidth + (size_t)pix;
+        double azt = BAD_VALUE, rgm = BAD_VALUE, rgoff = BAD_VALUE, azoff = BAD_VALUE;
+        const Vec3 xyz = llh_to_xyz(C.elp, L.lat[o] * C.deg2rad, L.lon[o] * C.deg2rad, L.hgt[o]);
+        const double t_lo = __ldg(op.t), t_hi = __ldg(op.t + op.n - 1);
+        const double inv_fd = C.fd.order ? rcp_n(C.fd.norm) : 0.0, inv_fdd = C.fdd.order ? rcp_n(C.fdd.norm) : 0.0;
+        double tline = C.tmid, rngpix = 0.0;
+        OrbState S;
+        S.x = C.xyz_mid;
+        S.v = C.vel_mid;
+        S.a = C.acc_mid;
+        bool bad = false;
+#pragma unroll 1
+        for (int k = 1; k <= 51; k++) {
+            n_it++;
+            const Vec3 dr = sub(xyz, S.x);
+            rngpix = sqrt_n(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+            const double dopfact = dot(dr, S.v);
+            const double fdop = 0.5 * C.wvl * poly1d_fast(C.fd, inv_fd, rngpix);
+            const double fdopder = 0.5 * C.wvl * poly1d_fast(C.fdd, inv_fdd, rngpix);
+            const double fn = dopfact - fdop * rngpix;
+            // k == 1: the reference's derivative (no acceleration term); afterwards the true one
+            const double c1 = (k == 1 ? 0.0 : dot(S.a, dr)) - dot(S.v, S.v);
+            const double c2 = div_n(fdop, rngpix) + fdopder;
+            const double tnew = tline - div_n(fn, c1 + c2 * dopfact);
+            const double step = tnew - tline;
+            tline = tnew;
+            if ((tline < t_lo) || (tline > t_hi) || !(tline == tline)) { // interpolator stat != 0 (orbit.c:224-233)
+                bad = true;
+                break;
+            }
+            poly_state<METHOD>(op, tline, S);
+            if (fabs(step) < 1.0e-10) {
+                n_conv = 1;
+                break;
+            }
+        }
+        bool outside = bad;
+        if (!outside) {
+            if (tline < C.tstart) outside = true;
+            else if (tline > C.tend) outside = true;
+            else {
+                const Vec3 dr = sub(xyz, S.x);
+                rngpix = sqrt_n(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+                if (rngpix < C.rngstart) outside = true;
+                else if (rngpix > C.rngend) outside = true;
+                else if (C.bistatic) { // :331-368
+                    tline = tline + 2.0 * rngpix / C.sol;
+                    if (tline < C.tstart) outside = true;
+                    else if (tline > C.tend) outside = true;
+                    else if ((tline < t_lo) || (tline > t_hi)) outside = true;
+                    else {
+                        poly_state<METHOD>(op, tline, S);
+                        const Vec3 d2 = sub(xyz, S.x);
+                        rngpix = sqrt_n(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z);
+                        if (rngpix < C.rngstart) outside = true;
+                        else if (rngpix > C.rngend) outside = true;
+                    }
+                }
+            }
+        }
+        if (outside) n_out = 1;
+        else {
+            n_valid = 1;
+            rgm = rngpix;
+            azt = tline;
+            rgoff = div_n(rngpix - C.rngstart, C.dmrg) - 1.0 * ((pix + 1) - 1);
+            azoff = div_n(tline - C.tstart, C.dtaz) - 1.0 * ((line + 1) - 1);
+        }
+        store_out<T>(L.azt, o, azt);
+        store_out<T>(L.rgm, o, rgm);
+        store_out<T>(L.azoff, o, azoff);
+        store_out<T>(L.rgoff, o, rgoff);
+    }
+    // counters without a block-wide barrier (warps leave as they finish)
+    unsigned int v[4] = {n_out, n_valid, n_conv, n_it};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        unsigned int x = v[q];
+        for (int sft = 16; sft > 0; sft >>= 1) x += __shfl_xor_sync(0xffffffffu, x, sft);
+        v[q] = x;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long *dst[4] = {&stats->outside, &stats->valid, &stats->converged, &stats->iterations};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (v[q]) atomicAdd(dst[q], (unsigned long long)v[q]);
+    }
+}
+
 void launch_geo_setup(int orbit_method, const OrbitView &orb, double tmid, GeoMid *d_out, cudaStream_t s)
 {
     k_geo_setup<<<1, 32, 0, s>>>(orbit_method, orb, tmid, d_out);
@@ -161,6 +338,24 @@ int launch_geo2rdr(const GeoConst &C, const OrbitView &orb, int line0, int nline
     size_t smem = orb.n <= kGeoMaxSmemVectors ? (size_t)orb.n * 7 * sizeof(double) : 0;
     if (out_f32) k_geo2rdr<float><<<(unsigned)nblk, kGeoBlock, smem, s>>>(C, orb, line0, nlines, L, stats);
     else k_geo2rdr<double><<<(unsigned)nblk, kGeoBlock, smem, s>>>(C, orb, line0, nlines, L, stats);
+    return 0;
+}
+
+int launch_geo2rdr_poly(const GeoConst &C, const OrbitPolyView &op, int line0, int nlines, const GeoLayers &L, int out_f32,
+                        GeoStats *stats, cudaStream_t s)
+{
+    const long long nblk = (long long)((C.demwidth + kGeoBlock - 1) / kGeoBlock) * nlines;
+    if (nblk > 0x7fffffffLL) return -2;
+    const unsigned g = (unsigned)nblk;
+    if (op.method == 0) {
+        if (out_f32) k_geo2rdr_poly<0, float><<<g, kGeoBlock, 0, s>>>(C, op, line0, nlines, L, stats);
+        else k_geo2rdr_poly<0, double><<<g, kGeoBlock, 0, s>>>(C, op, line0, nlines, L, stats);
+    } else if (op.method == 2) {
+        if (out_f32) k_geo2rdr_poly<2, float><<<g, kGeoBlock, 0, s>>>(C, op, line0, nlines, L, stats);
+        else k_geo2rdr_poly<2, double><<<g, kGeoBlock, 0, s>>>(C, op, line0, nlines, L, stats);
+    } else {
+        return -1;
+    }
     return 0;
 }
 

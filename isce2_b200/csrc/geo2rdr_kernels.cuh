@@ -32,6 +32,17 @@ struct GeoStats {
     unsigned long long outside, valid, converged, iterations;
 };
 
+// Per-window orbit polynomials (host: orbit_poly.h).  s = (t - tc[w]) * inv_h[w]; coefficients highest power first.
+struct OrbitPolyView {
+    int method; // 0 Hermite (velocity = d/dt of the position polynomial), 2 Legendre (separate velocity polynomial)
+    int n, nwin, ncoef;
+    const double *t;     // [n] state-vector epochs (window selection + span test, orbit.c:203-233)
+    const double *tc;    // [nwin]
+    const double *inv_h; // [nwin]
+    const double *cp;    // [nwin][3][ncoef]
+    const double *cv;    // [nwin][3][ncoef] (Legendre only)
+};
+
 struct GeoMid { // result of k_geo_setup
     double xyz[3], vel[3], acc[3];
     int stat_mid, stat_acc;
@@ -40,5 +51,8 @@ struct GeoMid { // result of k_geo_setup
 void launch_geo_setup(int orbit_method, const OrbitView &orb, double tmid, GeoMid *d_out, cudaStream_t s);
 int launch_geo2rdr(const GeoConst &C, const OrbitView &orb, int line0, int nlines, const GeoLayers &L, int out_f32,
                    GeoStats *stats, cudaStream_t s);
+// Newton solve on the per-window orbit polynomials (Hermite / Legendre); same outputs as launch_geo2rdr
+int launch_geo2rdr_poly(const GeoConst &C, const OrbitPolyView &op, int line0, int nlines, const GeoLayers &L, int out_f32,
+                        GeoStats *stats, cudaStream_t s);
 
 } // namespace b2

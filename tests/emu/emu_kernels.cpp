@@ -91,3 +91,35 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
     return 0;
 }
 }
+
+// ---- orbit polynomials (host construction in orbit_poly.h, Horner evaluation as in k_geo2rdr_poly) ----
+#include "../../isce2_b200/csrc/orbit_poly.h"
+extern "C" int emu_orbit_poly(int method, int n, const double *t, const double *pos, const double *vel, int nq, const double *tq,
+                              double *out /*[nq][9]: pos, vel, acc*/)
+{
+    HostOrbitPoly hp;
+    if (!build_orbit_poly(method, n, t, pos, vel, hp)) return -1;
+    const int back = method == 0 ? 2 : 5, span = method == 0 ? 4 : 9, NC = hp.ncoef;
+    for (int q = 0; q < nq; q++) {
+        int i = 0;
+        while (i < n && t[i] < tq[q]) i++;
+        int w = i - back;
+        if (w < 0) w = 0;
+        if (w > n - span) w = n - span;
+        const double ih = hp.inv_h[w], s = (tq[q] - hp.tc[w]) * ih;
+        for (int c = 0; c < 3; c++) {
+            const double *cp = &hp.cp[((size_t)w * 3 + c) * NC];
+            if (method == 0) {
+                double p = cp[0], dp = 0.0, ddp = 0.0;
+                for (int k = 1; k < NC; k++) { ddp = fma(ddp, s, dp); dp = fma(dp, s, p); p = fma(p, s, cp[k]); }
+                out[9 * q + c] = p; out[9 * q + 3 + c] = dp * ih; out[9 * q + 6 + c] = 2.0 * ddp * ih * ih;
+            } else {
+                const double *cv = &hp.cv[((size_t)w * 3 + c) * NC];
+                double p = cp[0], v = cv[0], dv = 0.0;
+                for (int k = 1; k < NC; k++) { dv = fma(dv, s, v); v = fma(v, s, cv[k]); p = fma(p, s, cp[k]); }
+                out[9 * q + c] = p; out[9 * q + 3 + c] = v; out[9 * q + 6 + c] = dv * ih;
+            }
+        }
+    }
+    return 0;
+}

@@ -39,3 +39,37 @@ def test_native_doppler_and_left_looking_bit_exact():
     o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method="BIQUINTIC", orbit_method="LEGENDRE", want_mask=False))
     for use_ref in (False, True):
         _check(o, emu.topo(sc, o, dem_method=5, orbit_method=2, use_ref=use_ref))
+
+
+@pytest.mark.parametrize("method,name", [(0, "HERMITE"), (2, "LEGENDRE")])
+def test_orbit_window_polynomials_match_reference_interpolators(method, name, golden):
+    """geo2rdr evaluates the orbit through per-window polynomials (isce2_b200/csrc/orbit_poly.h) expanded from the
+    reference's own Hermite / Lagrange formulas: they must reproduce orbit.c to rounding (~1e-8 m, 1e-9 m/s), on the
+    real state vectors of the reference's orbit test fixture and on a synthetic Keplerian orbit, at nodes, between
+    nodes and in the clamped end windows."""
+    import ctypes as C
+    L = emu.build()
+    dp = C.POINTER(C.c_double)
+    rows = np.array(golden["orbit_rsc"])
+    sc = synth.make_scene(1500, 64, dem=False)
+    for t, pos, vel in ((rows[:, 0].copy(), rows[:, 1:4].copy(), rows[:, 4:7].copy()), (sc.orbit_t, sc.orbit_pos, sc.orbit_vel)):
+        t, pos, vel = (np.ascontiguousarray(a, np.float64) for a in (t, pos, vel))
+        rng = np.random.default_rng(3)
+        tq = np.concatenate([rng.uniform(t[0], t[-1], 500), t, [t[0] + 1e-7, t[-1] - 1e-7]])
+        out = np.zeros((len(tq), 9))
+        assert L.emu_orbit_poly(method, len(t), t.ctypes.data_as(dp), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp), len(tq),
+                                tq.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        o = orc.Orbit(t, pos, vel)
+        for q, tt in enumerate(tq):
+            stat, p, v = o.interp(tt, name)
+            assert stat == 0
+            assert np.abs(out[q, :3] - p).max() < 2e-8, (tt, out[q, :3] - p)
+            assert np.abs(out[q, 3:6] - v).max() < 1e-9, (tt, out[q, 3:6] - v)
+        # acceleration = derivative of the velocity: compare with a central difference of the reference velocity
+        tt = 0.5 * (t[0] + t[-1]) + 0.37
+        out1 = np.zeros((1, 9))
+        tq1 = np.array([tt])
+        L.emu_orbit_poly(method, len(t), t.ctypes.data_as(dp), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp), 1,
+                         tq1.ctypes.data_as(dp), out1.ctypes.data_as(dp))
+        fd = (o.interp(tt + 0.01, name)[2] - o.interp(tt - 0.01, name)[2]) / 0.02
+        assert np.abs(out1[0, 6:9] - fd).max() < 1e-5
