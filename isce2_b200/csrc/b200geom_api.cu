@@ -108,6 +108,8 @@ int fill_poly2d(const b200_poly2d *src, Poly2dDev &dst, const char *what, char *
     dst.mean_azimuth = src->mean_azimuth;
     dst.norm_range = src->norm_range;
     dst.norm_azimuth = src->norm_azimuth;
+    dst.inv_norm_range = 1.0 / src->norm_range;
+    dst.inv_norm_azimuth = 1.0 / src->norm_azimuth;
     memset(dst.c, 0, sizeof dst.c);
     memcpy(dst.c, src->coeffs, sizeof(double) * n);
     return B200_OK;
@@ -161,8 +163,10 @@ struct b200_topo_plan {
         cudaFree(layers.ctrack);
         cudaFree(layers.elev);
         cudaFree(d_stats);
-        cudaFree(scr.key);
-        cudaFree(scr.idx);
+        cudaFree(scr.orng_sorted);
+        cudaFree(scr.pm);
+        cudaFree(scr.sm);
+        cudaFree(scr.rank);
         cudaFree(scr.cs);
         cudaFree(scr.lats);
         cudaFree(scr.lons);
@@ -239,6 +243,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         if ((rc = fill_poly2d(slrng, C.slr, "slant range", err, errlen)) != B200_OK) return rc;
     } else {
         memset(&C.slr, 0, sizeof C.slr);
+        C.slr.norm_range = C.slr.norm_azimuth = C.slr.inv_norm_range = C.slr.inv_norm_azimuth = 1.0;
     }
     spline6_make_table(C.spl);
 
@@ -363,18 +368,13 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     CK(cudaMalloc(&pl->layers.hgt, sizeof(double) * npix));
     if (want_los) CK(cudaMalloc(&pl->layers.los, sizeof(float) * 2 * npix));
     if (want_inc) CK(cudaMalloc(&pl->layers.inc, sizeof(float) * 2 * npix));
+    CK(cudaMalloc(&pl->layers.ctrack, sizeof(double) * npix)); // SCH height between solve and final pass, then ctrack
     if (want_mask) {
         CK(cudaMalloc(&pl->layers.mask, npix));
-        CK(cudaMalloc(&pl->layers.ctrack, sizeof(double) * npix));
         CK(cudaMalloc(&pl->layers.elev, sizeof(float) * npix));
         const int ow = 2 * p.width + 1;
-        int P = 1;
-        while (P < ow) P <<= 1;
         const int g = mask_grid_size(pl->nlines);
         pl->mask_grid = g;
-        pl->scr.padded = P;
-        CK(cudaMalloc(&pl->scr.key, sizeof(double) * (size_t)g * P));
-        CK(cudaMalloc(&pl->scr.idx, sizeof(int) * (size_t)g * P));
         CK(cudaMalloc(&pl->scr.cs, sizeof(double) * (size_t)g * p.width));
         CK(cudaMalloc(&pl->scr.lats, sizeof(double) * (size_t)g * p.width));
         CK(cudaMalloc(&pl->scr.lons, sizeof(double) * (size_t)g * p.width));
@@ -382,6 +382,10 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         CK(cudaMalloc(&pl->scr.orng, sizeof(double) * (size_t)g * ow));
         CK(cudaMalloc(&pl->scr.ctr, sizeof(double) * (size_t)g * ow));
         CK(cudaMalloc(&pl->scr.ctr_sorted, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.orng_sorted, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.pm, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.sm, sizeof(double) * (size_t)g * ow));
+        CK(cudaMalloc(&pl->scr.rank, sizeof(int) * (size_t)g * ow));
         CK(cudaMalloc(&pl->scr.oflag, (size_t)g * ow));
     }
     CK(cudaMalloc(&pl->d_stats, sizeof(TopoStats)));
@@ -423,7 +427,7 @@ extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, cha
     CK(cudaEventRecord(pl->ev0, s));
     if (launch_topo_pixels(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the pixel kernel (method %d, %d lines)", pl->C.method, pl->nlines);
-    int launches = 1;
+    int launches = topo_pixel_launches(pl->C.method);
     CK(cudaEventRecord(pl->evm, s));
     if (pl->layers.mask) {
         if (launch_topo_mask(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->dem_max, pl->scr, pl->mask_grid, s) != 0)

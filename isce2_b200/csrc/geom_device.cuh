@@ -564,6 +564,7 @@ constexpr int kMaxPoly1dCoeffs = 32;
 struct Poly2dDev {
     int range_order, azimuth_order;
     double mean_range, mean_azimuth, norm_range, norm_azimuth;
+    double inv_norm_range, inv_norm_azimuth; // IEEE reciprocals (host) for div_r
     double c[kMaxPoly2dCoeffs];
 };
 
@@ -577,8 +578,8 @@ struct Poly1dDev {
 B2_HD double eval_poly2d(const Poly2dDev &p, double azi, double rng)
 {
     double value = 0.0;
-    double xval = (rng - p.mean_range) / p.norm_range;
-    double yval = (azi - p.mean_azimuth) / p.norm_azimuth;
+    double xval = div_r(rng - p.mean_range, p.norm_range, p.inv_norm_range);
+    double yval = div_r(azi - p.mean_azimuth, p.norm_azimuth, p.inv_norm_azimuth);
     double scaley = 1.0;
     for (int i = 0; i <= p.azimuth_order; i++, scaley *= yval) {
         double scalex = 1.0;

@@ -25,12 +25,11 @@ struct TopoStats {
 };
 
 struct MaskScratch { // per persistent CTA
-    int padded;      // power of two >= 2*width+1
-    double *key;     // [grid][padded]
-    int *idx;        // [grid][padded]
-    double *cs, *lats, *lons, *rho; // [grid][width]
-    double *orng, *ctr, *ctr_sorted; // [grid][2*width+1]
-    unsigned char *oflag;            // [grid][2*width+1]
+    double *cs, *lats, *lons, *rho;                 // [grid][width]
+    double *orng, *ctr, *ctr_sorted, *orng_sorted;  // [grid][2*width+1]
+    double *pm, *sm;                                // [grid][2*width+1] prefix max / suffix min
+    int *rank;                                      // [grid][2*width+1]
+    unsigned char *oflag;                           // [grid][2*width+1]
 };
 
 double stats_decode(long long k);
@@ -41,6 +40,7 @@ void launch_dem_prepare(const void *raw, int dtype, float *dem, size_t n, int *m
 void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int nlines, LineState *states, cudaStream_t s);
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
                        TopoStats *stats, cudaStream_t s);
+int topo_pixel_launches(int method);
 int mask_grid_size(int nlines);
 int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out, float demmax,
                      const MaskScratch &scr, int grid, cudaStream_t s);

@@ -179,16 +179,17 @@ void topo_secondary(const TopoConst &C, const LineState &L, const PixelConst &P,
     }
 }
 
+// The iterative height solve of one pixel (:425-599): returns the SCH height the final pass starts from.
 template <int METHOD, bool REF>
-B2_HD void topo_pixel(const TopoConst &C, const LineState &L, double rng, double dopline, bool want_inc, PixelResult &R)
+B2_HD double topo_solve(const TopoConst &C, const LineState &L, double rng, double dopline, int &converged, int &iters)
 {
-    const double r2d = C.r2d;
     const PixelConst P = make_pixel_const(C, L, rng, dopline);
     // :425-436 (the initial lat/lon only feed llh_prev of iteration 1, which nothing reads before the secondary phase)
     double lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny;
     double lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
     double z = 0.0, zsch = 0.0;
-    int converged = 0, iters = 0;
+    converged = 0;
+    iters = 0;
     const int nprimary = C.numiter + 1 < C.numiter + C.extraiter + 1 ? C.numiter + 1 : C.numiter + C.extraiter + 1;
 #pragma unroll 1
     for (int iter = 1; iter <= nprimary; iter++) { // :458-570
@@ -200,9 +201,17 @@ B2_HD void topo_pixel(const TopoConst &C, const LineState &L, double rng, double
         }
     }
     if (!converged && C.extraiter > 0) topo_secondary<METHOD, REF>(C, L, P, lat, lon, z, zsch, converged, iters);
-    R.converged = converged;
-    R.iters = iters;
+    return zsch;
+}
 
+// The final computation of one pixel (:618-707) from the converged SCH height.
+template <int METHOD, bool REF>
+B2_HD void topo_final(const TopoConst &C, const LineState &L, double rng, double dopline, double zsch, bool want_inc,
+                      PixelResult &R)
+{
+    const double r2d = C.r2d;
+    const PixelConst P = make_pixel_const(C, L, rng, dopline);
+    double lat, lon;
     // ---- final computation :618-707 ----
     double costheta, sintheta, la, lo, h;
     Vec3 delta, xyz;
@@ -277,6 +286,17 @@ B2_HD void topo_pixel(const TopoConst &C, const LineState &L, double rng, double
         double cospsi = div_n(dot(n_trg, n_img_enu), n1 * n2);
         R.inc0 = (float)(acos(cospsi) * r2d);
     }
+}
+
+// solve + final in one call (host emulation harness)
+template <int METHOD, bool REF>
+B2_HD void topo_pixel(const TopoConst &C, const LineState &L, double rng, double dopline, bool want_inc, PixelResult &R)
+{
+    int conv, iters;
+    const double zsch = topo_solve<METHOD, REF>(C, L, rng, dopline, conv, iters);
+    topo_final<METHOD, REF>(C, L, rng, dopline, zsch, want_inc, R);
+    R.converged = conv;
+    R.iters = iters;
 }
 
 // One sample of the regular cross-track grid used by the layover test (:745-782): returns the slant

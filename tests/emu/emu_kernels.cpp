@@ -39,9 +39,9 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
     C.pi = 4.0 * atan(1.0); C.r2d = 180.0 / C.pi; C.orbit_method = A->orbit_method;
     C.inv_r2d = 1.0 / C.r2d; C.inv_dlat = 1.0 / C.deltalat; C.inv_dlon = 1.0 / C.deltalon;
     C.dop.range_order = A->dop_range_order; C.dop.azimuth_order = A->dop_azimuth_order;
-    C.dop.norm_range = C.dop.norm_azimuth = 1.0;
+    C.dop.norm_range = C.dop.norm_azimuth = C.dop.inv_norm_range = C.dop.inv_norm_azimuth = 1.0;
     memcpy(C.dop.c, dop_coeffs, sizeof(double) * (A->dop_range_order + 1) * (A->dop_azimuth_order + 1));
-    C.slr.range_order = 1; C.slr.azimuth_order = 0; C.slr.norm_range = C.slr.norm_azimuth = 1.0;
+    C.slr.range_order = 1; C.slr.azimuth_order = 0; C.slr.norm_range = C.slr.norm_azimuth = C.slr.inv_norm_range = C.slr.inv_norm_azimuth = 1.0;
     C.slr.c[0] = A->r0; C.slr.c[1] = A->dr;
     spline6_make_table(C.spl);
     {

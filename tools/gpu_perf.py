@@ -13,11 +13,11 @@ from isce2_b200 import _capi, synth  # noqa: E402
 from tests import parity_util as pu  # noqa: E402
 
 
-def perf(lines=1500, width=25000, reps=3):
-    sc = synth.make_scene(lines, width)
+def perf(lines=1500, width=25000, reps=3, rough=False):
+    sc = pu.rough_scene(lines, width) if rough else synth.make_scene(lines, width)
     sec = synth.make_scene(lines, width, dem=False, perturb=dict(da=120.0, d_cross=80.0, d_along_s=0.37))
     out = {}
-    for method, inc, mask in (("BILINEAR", False, False), ("BIQUINTIC", True, True)):
+    for method, inc, mask in ((("BIQUINTIC", True, True),) if rough else (("BILINEAR", False, False), ("BIQUINTIC", True, True))):
         p = _capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
                               delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
                               side=sc.side, peg_heading=sc.peg_heading, dem_method=method)
@@ -62,5 +62,7 @@ def parity(L=96, W=8192):
 if __name__ == "__main__":
     tag = os.environ.get("B200GEOM_LIB", "default")
     print(json.dumps({"lib": tag, "perf": perf()}), flush=True)
+    if "--rough" in sys.argv:
+        print(json.dumps({"lib": tag, "perf_rough_terrain": perf(rough=True)}), flush=True)
     if "--no-parity" not in sys.argv:
         print(json.dumps({"lib": tag, "parity(n_over,max,exact_frac)": parity()}), flush=True)
