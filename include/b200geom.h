@@ -126,7 +126,8 @@ typedef struct {
     float dem_max;
     float ms_setup;   /* device time: bbox + DEM upload/crop + per-line state */
     float ms_kernels; /* device time: per-pixel solve (+ mask), CUDA events on the launch stream */
-    float ms_pixels;  /* ... of which the per-pixel kernel */
+    float ms_pixels;  /* ... of which the per-pixel kernels (iterative solve + final pass) */
+    float ms_solve;   /* ... of which the iterative-solve kernel alone (== ms_pixels when the two are fused) */
     float ms_mask;    /* ... of which the layover/shadow kernel (0 when no mask was requested) */
     float ms_total;   /* wall time of the call, host<->device copies included */
     int gpu_launches; /* kernels launched by this call */
@@ -218,6 +219,8 @@ void b200_geo_plan_destroy(b200_geo_plan *plan);
 int b200_abi_version(void);
 int b200_device_count(void);                             /* 0 when no CUDA device is visible */
 int b200_device_name(int device, char *buf, size_t len); /* e.g. "NVIDIA B200" */
+/* device buffers of finished calls are cached per device for the next call; this returns them to the driver */
+void b200_release_cached_memory(void);
 void *b200_alloc_pinned(size_t bytes);                   /* page-locked host memory (fast H2D/D2H); NULL on failure */
 void b200_free_pinned(void *p);
 /* DFMA-saturating microbenchmark: measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per FMA) */

@@ -64,7 +64,7 @@ class TopoResult(C.Structure):
                 ("converged", C.c_longlong), ("iterations", C.c_longlong),
                 ("dem_x0", C.c_int), ("dem_y0", C.c_int), ("dem_nx", C.c_int), ("dem_ny", C.c_int),
                 ("dem_max", C.c_float), ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_pixels", C.c_float),
-                ("ms_mask", C.c_float), ("ms_total", C.c_float),
+                ("ms_solve", C.c_float), ("ms_mask", C.c_float), ("ms_total", C.c_float),
                 ("gpu_launches", C.c_int)]
 
 
@@ -90,7 +90,7 @@ class GeoResult(C.Structure):
 EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "b200_topo_plan_fetch",
            "b200_topo_plan_device_layers", "b200_topo_plan_destroy", "b200_geo2rdr_run", "b200_geo_plan_create",
            "b200_geo_plan_create_from_topo", "b200_geo_plan_execute", "b200_geo_plan_fetch", "b200_geo_plan_destroy",
-           "b200_abi_version", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
+           "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
            "b200_fp64_peak", "b200_device_primitive"]
 
 _lib = None
@@ -124,6 +124,7 @@ def lib():
     L.b200_geo_plan_fetch.argtypes = [C.c_void_p, C.POINTER(GeoOutputs), C.POINTER(GeoResult)] + err
     L.b200_geo_plan_destroy.argtypes = [C.c_void_p]
     L.b200_geo_plan_destroy.restype = None
+    L.b200_release_cached_memory.restype = None
     L.b200_device_name.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
     L.b200_alloc_pinned.argtypes = [C.c_size_t]
     L.b200_alloc_pinned.restype = C.c_void_p

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -62,6 +63,95 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Device workspace cache.  A topo + geo2rdr pass over a swath needs ~20 GB of layers; cudaMalloc / cudaFree of that
+// costs more than the kernels once a stack of bursts or dates is processed call after call.  Freed buffers are kept
+// per device and handed out again to requests of similar size; b200_release_cached_memory() (or a failed cudaMalloc)
+// returns them to the driver.  B200_NO_CACHE=1 disables the cache.
+// -------------------------------------------------------------------------------------------------
+struct CacheBlock {
+    void *ptr;
+    size_t size;
+    int device;
+    bool free;
+};
+std::mutex g_cache_mu;
+std::vector<CacheBlock> g_cache;
+
+void cache_release_locked(int device /* -1: all */)
+{
+    for (size_t i = 0; i < g_cache.size();) {
+        if (g_cache[i].free && (device < 0 || g_cache[i].device == device)) {
+            cudaSetDevice(g_cache[i].device);
+            cudaFree(g_cache[i].ptr);
+            g_cache[i] = g_cache.back();
+            g_cache.pop_back();
+        } else {
+            i++;
+        }
+    }
+}
+
+cudaError_t dmalloc(void **p, size_t bytes)
+{
+    static const bool no_cache = getenv("B200_NO_CACHE") != nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes == 0) bytes = 1;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (!no_cache) {
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); i++) {
+            const CacheBlock &b = g_cache[i];
+            if (b.free && b.device == dev && b.size >= bytes && b.size <= bytes + bytes / 4 + 4096 &&
+                (best < 0 || b.size < g_cache[best].size))
+                best = (int)i;
+        }
+        if (best >= 0) {
+            g_cache[best].free = false;
+            *p = g_cache[best].ptr;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { // give cached memory back and retry once
+        cudaGetLastError();
+        cache_release_locked(dev);
+        cudaSetDevice(dev);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess && !no_cache) g_cache.push_back(CacheBlock{*p, bytes, dev, false});
+    return e;
+}
+
+void dfree(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (CacheBlock &b : g_cache)
+        if (b.ptr == p) {
+            b.free = true;
+            return;
+        }
+    cudaFree(p); // not ours (cache disabled)
+}
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t bytes)
+{
+    return dmalloc(reinterpret_cast<void **>(p), bytes);
+}
+
+// lines per pipeline chunk: ~8 Mpixel, so that copies of one chunk overlap the kernels of the next
+int chunk_lines(int width, int nlines)
+{
+    long long c = 8000000LL / (width > 0 ? width : 1);
+    if (c < 32) c = 32;
+    if (c > nlines) c = nlines;
+    return (int)c;
+}
+
 struct DeviceOrbit {
     double *buf = nullptr;
     OrbitView view{0, nullptr, nullptr, nullptr};
@@ -74,7 +164,7 @@ int upload_orbit(const b200_orbit *o, DeviceOrbit &d, cudaStream_t s, char *err,
     memcpy(h.data(), o->t, sizeof(double) * n);
     memcpy(h.data() + n, o->pos, sizeof(double) * 3 * n);
     memcpy(h.data() + 4 * (size_t)n, o->vel, sizeof(double) * 3 * n);
-    CK(cudaMalloc(&d.buf, sizeof(double) * 7 * (size_t)n));
+    CK(dmalloc(&d.buf, sizeof(double) * 7 * (size_t)n));
     CK(cudaMemcpyAsync(d.buf, h.data(), sizeof(double) * 7 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s)); // h goes out of scope
     d.view = OrbitView{n, d.buf, d.buf + n, d.buf + 4 * (size_t)n};
@@ -136,8 +226,8 @@ struct b200_topo_plan {
     MaskScratch scr{};
     int mask_grid = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
-    float ms_pixels = 0.f, ms_mask = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, evs = nullptr;
+    float ms_pixels = 0.f, ms_mask = 0.f, ms_solve = 0.f;
     int dem_x0 = 0, dem_y0 = 0;
     float dem_max = 0.f;
     float ms_setup = 0.f, ms_kernels = 0.f;
@@ -147,37 +237,38 @@ struct b200_topo_plan {
     ~b200_topo_plan()
     {
         cudaSetDevice(p.device);
-        cudaFree(orb.buf);
-        cudaFree(d_dem);
-        cudaFree(d_raw);
-        cudaFree(d_maxkey);
-        cudaFree(d_rho);
-        cudaFree(d_rho0);
-        cudaFree(d_states);
-        cudaFree(layers.lat);
-        cudaFree(layers.lon);
-        cudaFree(layers.hgt);
-        cudaFree(layers.los);
-        cudaFree(layers.inc);
-        cudaFree(layers.mask);
-        cudaFree(layers.ctrack);
-        cudaFree(layers.elev);
-        cudaFree(d_stats);
-        cudaFree(scr.orng_sorted);
-        cudaFree(scr.pm);
-        cudaFree(scr.sm);
-        cudaFree(scr.rank);
-        cudaFree(scr.cs);
-        cudaFree(scr.lats);
-        cudaFree(scr.lons);
-        cudaFree(scr.rho);
-        cudaFree(scr.orng);
-        cudaFree(scr.ctr);
-        cudaFree(scr.ctr_sorted);
-        cudaFree(scr.oflag);
+        dfree(orb.buf);
+        dfree(d_dem);
+        dfree(d_raw);
+        dfree(d_maxkey);
+        dfree(d_rho);
+        dfree(d_rho0);
+        dfree(d_states);
+        dfree(layers.lat);
+        dfree(layers.lon);
+        dfree(layers.hgt);
+        dfree(layers.los);
+        dfree(layers.inc);
+        dfree(layers.mask);
+        dfree(layers.ctrack);
+        dfree(layers.elev);
+        dfree(d_stats);
+        dfree(scr.orng_sorted);
+        dfree(scr.pm);
+        dfree(scr.sm);
+        dfree(scr.rank);
+        dfree(scr.cs);
+        dfree(scr.lats);
+        dfree(scr.lons);
+        dfree(scr.rho);
+        dfree(scr.orng);
+        dfree(scr.ctr);
+        dfree(scr.ctr_sorted);
+        dfree(scr.oflag);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evm) cudaEventDestroy(evm);
+        if (evs) cudaEventDestroy(evs);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -212,6 +303,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     CK(cudaEventCreate(&pl->ev0));
     CK(cudaEventCreate(&pl->ev1));
     CK(cudaEventCreate(&pl->evm));
+    CK(cudaEventCreate(&pl->evs));
     cudaStream_t s = pl->stream;
     CK(cudaEventRecord(pl->ev0, s));
 
@@ -251,9 +343,9 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
 
     if (rho_image) {
         const size_t w = (size_t)p.width;
-        CK(cudaMalloc(&pl->d_rho0, sizeof(double) * w));
+        CK(dmalloc(&pl->d_rho0, sizeof(double) * w));
         CK(cudaMemcpyAsync(pl->d_rho0, rho_image, sizeof(double) * w, cudaMemcpyHostToDevice, s));
-        CK(cudaMalloc(&pl->d_rho, sizeof(double) * w * pl->nlines));
+        CK(dmalloc(&pl->d_rho, sizeof(double) * w * pl->nlines));
         CK(cudaMemcpyAsync(pl->d_rho, rho_image + (size_t)pl->line0 * w, sizeof(double) * w * pl->nlines,
                            cudaMemcpyHostToDevice, s));
     }
@@ -261,7 +353,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     // ---- bbox of interest (topozero.f90:192-263) ----
     double *d_bbox = nullptr;
     double h_bbox[24];
-    CK(cudaMalloc(&d_bbox, sizeof h_bbox));
+    CK(dmalloc(&d_bbox, sizeof h_bbox));
     {
         TopoConst Cb = C;
         Cb.dem = DemView{nullptr, 0, 0};
@@ -271,7 +363,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     }
     cudaError_t ce = cudaMemcpyAsync(h_bbox, d_bbox, sizeof h_bbox, cudaMemcpyDeviceToHost, s);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    cudaFree(d_bbox);
+    dfree(d_bbox);
     if (ce != cudaSuccess) return fail(err, errlen, B200_ECUDA, "bbox kernel failed: %s", cudaGetErrorString(ce));
     double min_lat = 10000., max_lat = -10000., min_lon = 10000., max_lon = -10000.;
     int nok = 0;
@@ -329,12 +421,12 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     // ---- crop + float32 conversion + demmax (topozero.f90:333-345) ----
     const size_t ncell = (size_t)udemwidth * (size_t)udemlength;
     const size_t esz = dem_dtype == B200_DEM_I16 ? 2 : 4;
-    CK(cudaMalloc(&pl->d_dem, sizeof(float) * ncell));
-    CK(cudaMalloc(&pl->d_maxkey, sizeof(int)));
+    CK(dmalloc(&pl->d_dem, sizeof(float) * ncell));
+    CK(dmalloc(&pl->d_maxkey, sizeof(int)));
     const char *src = (const char *)dem + ((size_t)(ustarty - 1) * (size_t)idemwidth + (size_t)(ustartx - 1)) * esz;
     void *dst = pl->d_dem;
     if (dem_dtype == B200_DEM_I16) {
-        CK(cudaMalloc(&pl->d_raw, esz * ncell));
+        CK(dmalloc(&pl->d_raw, esz * ncell));
         dst = pl->d_raw;
     }
     CK(cudaMemcpy2DAsync(dst, (size_t)udemwidth * esz, src, (size_t)idemwidth * esz, (size_t)udemwidth * esz,
@@ -350,45 +442,45 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         pl->dem_max = dem_max_decode(key);
     }
     if (pl->d_raw) {
-        cudaFree(pl->d_raw);
+        dfree(pl->d_raw);
         pl->d_raw = nullptr;
     }
     C.dem = DemView{pl->d_dem, udemwidth, udemlength};
     C.rho_image = pl->d_rho ? pl->d_rho - (size_t)pl->line0 * (size_t)p.width : nullptr;
 
     // ---- per-line state ----
-    CK(cudaMalloc(&pl->d_states, sizeof(LineState) * (size_t)pl->nlines));
+    CK(dmalloc(&pl->d_states, sizeof(LineState) * (size_t)pl->nlines));
     launch_line_setup(C, pl->orb.view, pl->line0, pl->nlines, pl->d_states, s);
     pl->launches++;
 
     // ---- resident output layers ----
     const size_t npix = (size_t)pl->nlines * (size_t)p.width;
-    CK(cudaMalloc(&pl->layers.lat, sizeof(double) * npix));
-    CK(cudaMalloc(&pl->layers.lon, sizeof(double) * npix));
-    CK(cudaMalloc(&pl->layers.hgt, sizeof(double) * npix));
-    if (want_los) CK(cudaMalloc(&pl->layers.los, sizeof(float) * 2 * npix));
-    if (want_inc) CK(cudaMalloc(&pl->layers.inc, sizeof(float) * 2 * npix));
-    CK(cudaMalloc(&pl->layers.ctrack, sizeof(double) * npix)); // SCH height between solve and final pass, then ctrack
+    CK(dmalloc(&pl->layers.lat, sizeof(double) * npix));
+    CK(dmalloc(&pl->layers.lon, sizeof(double) * npix));
+    CK(dmalloc(&pl->layers.hgt, sizeof(double) * npix));
+    if (want_los) CK(dmalloc(&pl->layers.los, sizeof(float) * 2 * npix));
+    if (want_inc) CK(dmalloc(&pl->layers.inc, sizeof(float) * 2 * npix));
+    CK(dmalloc(&pl->layers.ctrack, sizeof(double) * npix)); // SCH height between solve and final pass, then ctrack
     if (want_mask) {
-        CK(cudaMalloc(&pl->layers.mask, npix));
-        CK(cudaMalloc(&pl->layers.elev, sizeof(float) * npix));
+        CK(dmalloc(&pl->layers.mask, npix));
+        CK(dmalloc(&pl->layers.elev, sizeof(float) * npix));
         const int ow = 2 * p.width + 1;
         const int g = mask_grid_size(pl->nlines);
         pl->mask_grid = g;
-        CK(cudaMalloc(&pl->scr.cs, sizeof(double) * (size_t)g * p.width));
-        CK(cudaMalloc(&pl->scr.lats, sizeof(double) * (size_t)g * p.width));
-        CK(cudaMalloc(&pl->scr.lons, sizeof(double) * (size_t)g * p.width));
-        CK(cudaMalloc(&pl->scr.rho, sizeof(double) * (size_t)g * p.width));
-        CK(cudaMalloc(&pl->scr.orng, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.ctr, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.ctr_sorted, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.orng_sorted, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.pm, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.sm, sizeof(double) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.rank, sizeof(int) * (size_t)g * ow));
-        CK(cudaMalloc(&pl->scr.oflag, (size_t)g * ow));
+        CK(dmalloc(&pl->scr.cs, sizeof(double) * (size_t)g * p.width));
+        CK(dmalloc(&pl->scr.lats, sizeof(double) * (size_t)g * p.width));
+        CK(dmalloc(&pl->scr.lons, sizeof(double) * (size_t)g * p.width));
+        CK(dmalloc(&pl->scr.rho, sizeof(double) * (size_t)g * p.width));
+        CK(dmalloc(&pl->scr.orng, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.ctr, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.ctr_sorted, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.orng_sorted, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.pm, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.sm, sizeof(double) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.rank, sizeof(int) * (size_t)g * ow));
+        CK(dmalloc(&pl->scr.oflag, (size_t)g * ow));
     }
-    CK(cudaMalloc(&pl->d_stats, sizeof(TopoStats)));
+    CK(dmalloc(&pl->d_stats, sizeof(TopoStats)));
     CK(cudaEventRecord(pl->ev1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->ms_setup, pl->ev0, pl->ev1));
@@ -425,7 +517,7 @@ extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, cha
     init.converged = init.iterations = 0;
     CK(cudaMemcpyAsync(pl->d_stats, &init, sizeof init, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(pl->ev0, s));
-    if (launch_topo_pixels(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->d_stats, s) != 0)
+    if (launch_topo_pixels(pl->C, pl->d_states, pl->line0, pl->nlines, pl->layers, pl->d_stats, s, pl->evs) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the pixel kernel (method %d, %d lines)", pl->C.method, pl->nlines);
     int launches = topo_pixel_launches(pl->C.method);
     CK(cudaEventRecord(pl->evm, s));
@@ -439,6 +531,7 @@ extern "C" int b200_topo_plan_execute(b200_topo_plan *pl, float *ms_kernels, cha
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
     CK(cudaEventElapsedTime(&pl->ms_pixels, pl->ev0, pl->evm));
+    CK(cudaEventElapsedTime(&pl->ms_solve, pl->ev0, pl->evs));
     CK(cudaEventElapsedTime(&pl->ms_mask, pl->evm, pl->ev1));
     if (!pl->executed) pl->launches += launches;
     pl->executed = true;
@@ -480,6 +573,7 @@ extern "C" int b200_topo_plan_fetch(b200_topo_plan *pl, const b200_topo_outputs 
         res->ms_setup = pl->ms_setup;
         res->ms_kernels = pl->ms_kernels;
         res->ms_pixels = pl->ms_pixels;
+        res->ms_solve = pl->ms_solve;
         res->ms_mask = pl->ms_mask;
         res->ms_total = 0.f;
         res->gpu_launches = pl->launches;
@@ -509,9 +603,85 @@ extern "C" int b200_topo_run(const b200_topo_params *p, const void *dem, int dem
     int rc = b200_topo_plan_create(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out->los != nullptr, out->inc != nullptr,
                                    out->mask != nullptr, &pl, err, errlen);
     if (rc != B200_OK) return rc;
-    rc = b200_topo_plan_execute(pl, nullptr, err, errlen);
-    if (rc == B200_OK) rc = b200_topo_plan_fetch(pl, out, res, err, errlen);
-    b200_topo_plan_destroy(pl);
+    struct PlanGuard {
+        b200_topo_plan *p;
+        ~PlanGuard() { delete p; }
+    } pg{pl};
+    // ---- two-stage pipeline over blocks of lines: kernels(c+1) | D2H(c) ----
+    struct Streams {
+        cudaStream_t d = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Streams()
+        {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            if (d) cudaStreamDestroy(d);
+        }
+    } st;
+    CK(cudaStreamCreateWithFlags(&st.d, cudaStreamNonBlocking));
+    cudaStream_t s = pl->stream;
+    TopoStats init;
+    init.min_lat = init.min_lon = 0x7fffffffffffffffLL;
+    init.max_lat = init.max_lon = (long long)0x8000000000000000ULL;
+    init.converged = init.iterations = 0;
+    CK(cudaMemcpyAsync(pl->d_stats, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->ev0, s));
+    const size_t w = (size_t)pl->p.width;
+    const int cl = chunk_lines(pl->p.width, pl->nlines);
+    int launches = 0;
+    auto launch_chunk = [&](int c0, int n, cudaEvent_t done) -> int {
+        const size_t o = (size_t)c0 * w;
+        TopoLayers L = pl->layers;
+        L.lat += o; L.lon += o; L.hgt += o; L.ctrack += o;
+        if (L.los) L.los += 2 * o;
+        if (L.inc) L.inc += 2 * o;
+        if (L.mask) L.mask += o;
+        if (L.elev) L.elev += o;
+        if (launch_topo_pixels(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->d_stats, s) != 0) return -1;
+        launches += topo_pixel_launches(pl->C.method);
+        if (L.mask) {
+            const int g = pl->mask_grid < n ? pl->mask_grid : n;
+            if (launch_topo_mask(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->dem_max, pl->scr, g, s) != 0) return -1;
+            launches++;
+        }
+        return cudaEventRecord(done, s) == cudaSuccess ? 0 : -1;
+    };
+    auto copy_chunk = [&](int c0, int n, cudaEvent_t done) -> cudaError_t {
+        const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
+        cudaError_t e = cudaStreamWaitEvent(st.d, done, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lat + o, pl->layers.lat + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lon + o, pl->layers.lon + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->hgt + o, pl->layers.hgt + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->los && pl->layers.los)
+            e = cudaMemcpyAsync(out->los + 2 * o, pl->layers.los + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->inc && pl->layers.inc)
+            e = cudaMemcpyAsync(out->inc + 2 * o, pl->layers.inc + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->mask && pl->layers.mask)
+            e = cudaMemcpyAsync(out->mask + o, pl->layers.mask + o, cnt, cudaMemcpyDeviceToHost, st.d);
+        return e;
+    };
+    const int nchunks = (pl->nlines + cl - 1) / cl;
+    st.ev.resize(nchunks, nullptr);
+    for (int c = 0; c < nchunks; c++) CK(cudaEventCreateWithFlags(&st.ev[c], cudaEventDisableTiming));
+    // kernels of chunk c+1 are queued before the (possibly host-blocking, pageable) copies of chunk c
+    if (launch_chunk(0, cl < pl->nlines ? cl : pl->nlines, st.ev[0]) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
+    for (int c = 0; c < nchunks; c++) {
+        const int c0 = c * cl, n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
+        if (c + 1 < nchunks) {
+            const int d0 = (c + 1) * cl, dn = (d0 + cl <= pl->nlines) ? cl : pl->nlines - d0;
+            if (launch_chunk(d0, dn, st.ev[c + 1]) != 0) return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
+        }
+        CK(copy_chunk(c0, n, st.ev[c]));
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(st.d));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    pl->ms_pixels = pl->ms_solve = pl->ms_mask = 0.f; // not separable in the pipelined form
+    pl->launches += launches;
+    pl->executed = true;
+    rc = b200_topo_plan_fetch(pl, nullptr, res, err, errlen);
     if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
     return rc;
 }
@@ -539,13 +709,13 @@ struct b200_geo_plan {
     {
         cudaSetDevice(p.device);
         if (owns_inputs) {
-            cudaFree(d_lat);
-            cudaFree(d_lon);
-            cudaFree(d_hgt);
+            dfree(d_lat);
+            dfree(d_lon);
+            dfree(d_hgt);
         }
-        for (void *q : d_out) cudaFree(q);
-        cudaFree(d_stats);
-        cudaFree(d_mid);
+        for (void *q : d_out) dfree(q);
+        dfree(d_stats);
+        dfree(d_mid);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -564,8 +734,8 @@ static int geo_plan_common(b200_geo_plan *pl, char *err, size_t errlen)
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&pl->ev0));
     CK(cudaEventCreate(&pl->ev1));
-    CK(cudaMalloc(&pl->d_stats, sizeof(GeoStats)));
-    CK(cudaMalloc(&pl->d_mid, sizeof(GeoMid)));
+    CK(dmalloc(&pl->d_stats, sizeof(GeoStats)));
+    CK(dmalloc(&pl->d_mid, sizeof(GeoMid)));
     return B200_OK;
 }
 
@@ -582,7 +752,7 @@ extern "C" int b200_geo_plan_create(const b200_geo_params *p, const double *lat,
     if (rc == B200_OK) {
         const size_t npix = (size_t)pl->nlines * (size_t)p->dem_width, off = (size_t)pl->line0 * (size_t)p->dem_width;
         auto up = [&](double **d, const double *h) -> int {
-            CK(cudaMalloc(d, sizeof(double) * npix));
+            CK(dmalloc(d, sizeof(double) * npix));
             CK(cudaMemcpyAsync(*d, h + off, sizeof(double) * npix, cudaMemcpyHostToDevice, pl->stream));
             return B200_OK;
         };
@@ -632,23 +802,35 @@ extern "C" int b200_geo_plan_create_from_topo(const b200_geo_params *p, b200_top
     return B200_OK;
 }
 
-extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *pp, const b200_orbit *orbit,
-                                     const b200_poly1d *dop, int want_azt, int want_rgm, int want_azoff, int want_rgoff,
-                                     float *ms_kernels, char *err, size_t errlen)
+namespace {
+
+// Everything one orbit / Doppler / radar-grid combination needs on the device (geo2rdr.f90:118-208)
+struct GeoRun {
+    GeoConst C{};
+    DeviceOrbit dorb;
+    double *d_poly = nullptr;
+    OrbitPolyView op{};
+    bool use_poly = false;
+    ~GeoRun()
+    {
+        dfree(dorb.buf);
+        dfree(d_poly);
+    }
+};
+
+int geo_prepare(b200_geo_plan *pl, const b200_geo_params &p, const b200_orbit *orbit, const b200_poly1d *dop, GeoRun &R,
+                char *err, size_t errlen)
 {
-    if (!pl || !pp) return fail(err, errlen, B200_EINVAL, "plan/params is NULL");
-    const b200_geo_params &p = *pp;
     int rc;
     if ((rc = check_orbit(orbit, p.orbit_method, err, errlen)) != B200_OK) return rc;
     if (!dop || !dop->coeffs || dop->order < 0 || dop->order + 1 > kMaxPoly1dCoeffs)
         return fail(err, errlen, B200_EINVAL, "bad doppler polynomial");
     if (p.dem_width != pl->p.dem_width) return fail(err, errlen, B200_EINVAL, "dem_width differs from the plan");
     if (p.prf <= 0 || p.nazlooks < 1 || p.nrnglooks < 1) return fail(err, errlen, B200_EINVAL, "bad prf / looks");
-    CK(cudaSetDevice(pl->p.device));
     cudaStream_t s = pl->stream;
 
     // ---- scalars of geo2rdr.f90:118-133 ----
-    GeoConst C{};
+    GeoConst &C = R.C;
     C.elp = make_ellipsoid(p.major, p.e2);
     C.wvl = p.wvl;
     C.tstart = p.t0;
@@ -680,20 +862,10 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
         C.fdd.norm = C.fd.norm;
         for (int k = 1; k <= dop->order; k++) C.fdd.c[k - 1] = k * C.fd.c[k] / C.fd.norm;
     }
-
-    DeviceOrbit dorb;
-    if ((rc = upload_orbit(orbit, dorb, s, err, errlen)) != B200_OK) {
-        cudaFree(dorb.buf);
-        return rc;
-    }
-    struct Guard {
-        double *b;
-        ~Guard() { cudaFree(b); }
-    } guard{dorb.buf};
+    if ((rc = upload_orbit(orbit, R.dorb, s, err, errlen)) != B200_OK) return rc;
 
     // ---- mid-scene state (:194-208) ----
-    CK(cudaEventRecord(pl->ev0, s));
-    launch_geo_setup(p.orbit_method, dorb.view, C.tmid, pl->d_mid, s);
+    launch_geo_setup(p.orbit_method, R.dorb.view, C.tmid, pl->d_mid, s);
     GeoMid mid;
     CK(cudaMemcpyAsync(&mid, pl->d_mid, sizeof mid, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -703,29 +875,8 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
     C.vel_mid = Vec3{mid.vel[0], mid.vel[1], mid.vel[2]};
     C.acc_mid = Vec3{mid.acc[0], mid.acc[1], mid.acc[2]};
 
-    // ---- outputs ----
-    const int want[4] = {want_azt, want_rgm, want_azoff, want_rgoff};
-    const size_t npix = (size_t)pl->nlines * (size_t)p.dem_width;
-    const size_t esz = p.out_f32 ? 4 : 8;
-    for (int i = 0; i < 4; i++) {
-        if (pl->d_out[i] && (pl->out_f32 != p.out_f32 || !want[i])) {
-            cudaFree(pl->d_out[i]);
-            pl->d_out[i] = nullptr;
-        }
-        if (want[i] && !pl->d_out[i]) CK(cudaMalloc(&pl->d_out[i], esz * npix));
-        pl->want[i] = want[i];
-    }
-    pl->out_f32 = p.out_f32;
-    GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
-    CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
-    // ev0 was recorded before the mid-scene setup kernel: ms_kernels covers setup + solve
-    double *d_poly = nullptr;
-    struct PolyGuard {
-        double **p;
-        ~PolyGuard() { cudaFree(*p); }
-    } pguard{&d_poly};
-    if (p.orbit_method == B200_ORBIT_HERMITE || p.orbit_method == B200_ORBIT_LEGENDRE) {
-        // Hermite / Legendre: Newton solve on per-window orbit polynomials (orbit_poly.h)
+    R.use_poly = (p.orbit_method == B200_ORBIT_HERMITE || p.orbit_method == B200_ORBIT_LEGENDRE);
+    if (R.use_poly) { // Newton solve on per-window orbit polynomials (orbit_poly.h)
         HostOrbitPoly hp;
         if (!build_orbit_poly(p.orbit_method, orbit->nvec, orbit->t, orbit->pos, orbit->vel, hp))
             return fail(err, errlen, B200_EORBIT, "cannot build the orbit polynomials");
@@ -736,16 +887,57 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
         memcpy(blob.data() + nt + nw, hp.inv_h.data(), sizeof(double) * nw);
         memcpy(blob.data() + nt + 2 * nw, hp.cp.data(), sizeof(double) * nc);
         if (nv) memcpy(blob.data() + nt + 2 * nw + nc, hp.cv.data(), sizeof(double) * nv);
-        CK(cudaMalloc(&d_poly, sizeof(double) * blob.size()));
-        CK(cudaMemcpyAsync(d_poly, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, s));
+        CK(dmalloc(&R.d_poly, sizeof(double) * blob.size()));
+        CK(cudaMemcpyAsync(R.d_poly, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s)); // blob goes out of scope
-        OrbitPolyView op{hp.method, hp.n, hp.nwin, hp.ncoef, d_poly, d_poly + nt, d_poly + nt + nw, d_poly + nt + 2 * nw,
-                         nv ? d_poly + nt + 2 * nw + nc : nullptr};
-        if (launch_geo2rdr_poly(C, op, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
-            return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
-    } else if (launch_geo2rdr(C, dorb.view, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0) {
-        return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
+        R.op = OrbitPolyView{hp.method, hp.n, hp.nwin, hp.ncoef, R.d_poly, R.d_poly + nt, R.d_poly + nt + nw,
+                             R.d_poly + nt + 2 * nw, nv ? R.d_poly + nt + 2 * nw + nc : nullptr};
     }
+    return B200_OK;
+}
+
+int geo_launch(const GeoRun &R, int line0_abs, int nlines, const GeoLayers &L, int out_f32, GeoStats *stats, cudaStream_t s)
+{
+    if (R.use_poly) return launch_geo2rdr_poly(R.C, R.op, line0_abs, nlines, L, out_f32, stats, s);
+    return launch_geo2rdr(R.C, R.dorb.view, line0_abs, nlines, L, out_f32, stats, s);
+}
+
+int geo_alloc_outputs(b200_geo_plan *pl, const b200_geo_params &p, const int want[4], char *err, size_t errlen)
+{
+    const size_t npix = (size_t)pl->nlines * (size_t)p.dem_width;
+    const size_t esz = p.out_f32 ? 4 : 8;
+    for (int i = 0; i < 4; i++) {
+        if (pl->d_out[i] && (pl->out_f32 != p.out_f32 || !want[i])) {
+            dfree(pl->d_out[i]);
+            pl->d_out[i] = nullptr;
+        }
+        if (want[i] && !pl->d_out[i]) CK(dmalloc(&pl->d_out[i], esz * npix));
+        pl->want[i] = want[i];
+    }
+    pl->out_f32 = p.out_f32;
+    return B200_OK;
+}
+
+} // namespace
+
+extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *pp, const b200_orbit *orbit,
+                                     const b200_poly1d *dop, int want_azt, int want_rgm, int want_azoff, int want_rgoff,
+                                     float *ms_kernels, char *err, size_t errlen)
+{
+    if (!pl || !pp) return fail(err, errlen, B200_EINVAL, "plan/params is NULL");
+    const b200_geo_params &p = *pp;
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    CK(cudaEventRecord(pl->ev0, s)); // ms_kernels covers the mid-scene setup kernel and the solve
+    GeoRun R;
+    int rc = geo_prepare(pl, p, orbit, dop, R, err, errlen);
+    if (rc != B200_OK) return rc;
+    const int want[4] = {want_azt, want_rgm, want_azoff, want_rgoff};
+    if ((rc = geo_alloc_outputs(pl, p, want, err, errlen)) != B200_OK) return rc;
+    GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
+    CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
+    if (geo_launch(R, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
     CK(cudaEventRecord(pl->ev1, s));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
@@ -793,14 +985,77 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
 {
     if (!out || (!out->azt && !out->rgm && !out->azoff && !out->rgoff))
         return fail(err, errlen, B200_EINVAL, "No outputs requested from geo2rdr. Check again."); // Geo2rdr.py:271-274
+    if (!p) return fail(err, errlen, B200_EINVAL, "params is NULL");
+    if (!lat || !lon || !hgt) return fail(err, errlen, B200_EINVAL, "lat/lon/hgt is NULL");
     const double t0 = now_ms();
-    b200_geo_plan *pl = nullptr;
-    int rc = b200_geo_plan_create(p, lat, lon, hgt, &pl, err, errlen);
+    b200_geo_plan plan;
+    b200_geo_plan *pl = &plan;
+    pl->p = *p;
+    int rc = geo_plan_common(pl, err, errlen);
     if (rc != B200_OK) return rc;
-    rc = b200_geo_plan_execute(pl, p, orbit, dop, out->azt != nullptr, out->rgm != nullptr, out->azoff != nullptr,
-                               out->rgoff != nullptr, nullptr, err, errlen);
-    if (rc == B200_OK) rc = b200_geo_plan_fetch(pl, out, res, err, errlen);
-    b200_geo_plan_destroy(pl);
+    const size_t w = (size_t)p->dem_width, npix = (size_t)pl->nlines * w, off = (size_t)pl->line0 * w;
+    CK(dmalloc(&pl->d_lat, sizeof(double) * npix));
+    CK(dmalloc(&pl->d_lon, sizeof(double) * npix));
+    CK(dmalloc(&pl->d_hgt, sizeof(double) * npix));
+    cudaStream_t s = pl->stream;
+    CK(cudaEventRecord(pl->ev0, s));
+    GeoRun R;
+    if ((rc = geo_prepare(pl, *p, orbit, dop, R, err, errlen)) != B200_OK) return rc;
+    const int want[4] = {out->azt != nullptr, out->rgm != nullptr, out->azoff != nullptr, out->rgoff != nullptr};
+    if ((rc = geo_alloc_outputs(pl, *p, want, err, errlen)) != B200_OK) return rc;
+    CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
+
+    // ---- three-stage pipeline over blocks of lines: H2D(c+1) | kernel(c) | D2H(c-1) ----
+    struct Streams {
+        cudaStream_t h = nullptr, d = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Streams()
+        {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            if (h) cudaStreamDestroy(h);
+            if (d) cudaStreamDestroy(d);
+        }
+    } st;
+    CK(cudaStreamCreateWithFlags(&st.h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st.d, cudaStreamNonBlocking));
+    const int cl = chunk_lines(p->dem_width, pl->nlines);
+    const size_t esz = p->out_f32 ? 4 : 8;
+    void *hout[4] = {out->azt, out->rgm, out->azoff, out->rgoff};
+    int launches = 1;
+    for (int c0 = 0; c0 < pl->nlines; c0 += cl) {
+        const int n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
+        const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
+        cudaEvent_t eh, ek;
+        CK(cudaEventCreateWithFlags(&eh, cudaEventDisableTiming));
+        st.ev.push_back(eh);
+        CK(cudaEventCreateWithFlags(&ek, cudaEventDisableTiming));
+        st.ev.push_back(ek);
+        CK(cudaMemcpyAsync(pl->d_lat + o, lat + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
+        CK(cudaMemcpyAsync(pl->d_lon + o, lon + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
+        CK(cudaMemcpyAsync(pl->d_hgt + o, hgt + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
+        CK(cudaEventRecord(eh, st.h));
+        CK(cudaStreamWaitEvent(s, eh, 0));
+        GeoLayers L{pl->d_lat + o, pl->d_lon + o, pl->d_hgt + o, nullptr, nullptr, nullptr, nullptr};
+        void **lo[4] = {&L.azt, &L.rgm, &L.azoff, &L.rgoff};
+        for (int i = 0; i < 4; i++)
+            if (pl->d_out[i]) *lo[i] = (char *)pl->d_out[i] + o * esz;
+        if (geo_launch(R, pl->line0 + c0, n, L, p->out_f32, pl->d_stats, s) != 0)
+            return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
+        launches++;
+        CK(cudaEventRecord(ek, s));
+        CK(cudaStreamWaitEvent(st.d, ek, 0));
+        for (int i = 0; i < 4; i++)
+            if (hout[i] && pl->d_out[i])
+                CK(cudaMemcpyAsync((char *)hout[i] + o * esz, (char *)pl->d_out[i] + o * esz, cnt * esz, cudaMemcpyDeviceToHost, st.d));
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(st.d));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    pl->launches = launches;
+    pl->executed = true;
+    rc = b200_geo_plan_fetch(pl, nullptr, res, err, errlen);
     if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
     return rc;
 }
@@ -809,6 +1064,12 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
 // utilities
 // =================================================================================================
 extern "C" int b200_abi_version(void) { return B200GEOM_ABI_VERSION; }
+
+extern "C" void b200_release_cached_memory(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_release_locked(-1);
+}
 
 extern "C" int b200_device_count(void)
 {
@@ -867,7 +1128,7 @@ extern "C" int b200_fp64_peak(int device, double *tflops, char *err, size_t errl
     CK(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
     double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    CK(dmalloc(&d, sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -883,7 +1144,7 @@ extern "C" int b200_fp64_peak(int device, double *tflops, char *err, size_t errl
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d);
+    dfree(d);
     if (tflops) *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return B200_OK;
 }
@@ -916,12 +1177,12 @@ extern "C" int b200_device_primitive(int device, int what, double a, double e2, 
         if ((rc = upload_orbit(orbit, dorb, 0, err, errlen)) != B200_OK) return rc;
     }
     double *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double) * 16));
+    CK(dmalloc(&d, sizeof(double) * 16));
     CK(cudaMemcpy(d, in, sizeof(double) * 3, cudaMemcpyHostToDevice));
     k_primitive<<<1, 32>>>(what, make_ellipsoid(a, e2), dorb.view, d, d + 8);
     cudaError_t e = cudaMemcpy(out, d + 8, sizeof(double) * (what >= 2 ? 7 : 3), cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    cudaFree(dorb.buf);
+    dfree(d);
+    dfree(dorb.buf);
     if (e != cudaSuccess) return fail(err, errlen, B200_ECUDA, "primitive kernel failed: %s", cudaGetErrorString(e));
     return B200_OK;
 }

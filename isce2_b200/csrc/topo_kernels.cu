@@ -662,20 +662,23 @@ void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int 
 
 template <int METHOD>
 static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, const TopoLayers &out, TopoStats *stats,
-                            unsigned grid, cudaStream_t s)
+                            unsigned grid, cudaStream_t s, cudaEvent_t ev_mid)
 {
     constexpr bool kSplit = (METHOD == 5 || METHOD == 2);
     if (kSplit) {
         if (C.ref.use_ref) {
             k_topo_solve<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
+            if (ev_mid) cudaEventRecord(ev_mid, s);
             k_topo_final<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         } else {
             k_topo_solve<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
+            if (ev_mid) cudaEventRecord(ev_mid, s);
             k_topo_final<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         }
     } else {
         if (C.ref.use_ref) k_topo_fused<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         else k_topo_fused<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
+        if (ev_mid) cudaEventRecord(ev_mid, s);
     }
 }
 
@@ -683,15 +686,15 @@ int topo_pixel_launches(int method) { return (method == 5 || method == 2) ? 2 : 
 
 // launches k_topo_solve + k_topo_final (2 kernels); out.ctrack must be allocated (it carries the SCH height between them)
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
-                       TopoStats *stats, cudaStream_t s)
+                       TopoStats *stats, cudaStream_t s, cudaEvent_t ev_mid)
 {
     const long long nblk = (long long)((C.width + kTopoBlock - 1) / kTopoBlock) * nlines;
     if (nblk > 0x7fffffffLL || !out.ctrack) return -2;
     switch (C.method) {
-    case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, s); break;
-    case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, s); break;
-    case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, s); break;
-    case 5: launch_pixels_m<5>(C, states, line0, out, stats, (unsigned)nblk, s); break;
+    case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, s, ev_mid); break;
+    case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, s, ev_mid); break;
+    case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, s, ev_mid); break;
+    case 5: launch_pixels_m<5>(C, states, line0, out, stats, (unsigned)nblk, s, ev_mid); break;
     default: return -1;
     }
     return 0;
