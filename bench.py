@@ -357,6 +357,8 @@ def run_b200(args, ranks):
     e2e_value = npix_total / wall_e2e / 1e6
     h2d = sc.dem.nbytes * 0 + res.dem_nx * res.dem_ny * 4 + 3 * 8 * npix_local + 2 * 7 * 8 * len(sc.orbit_t)
     d2h = sum(v.nbytes for v in outs.values() if v is not None) + sum(v.nbytes for v in gouts.values() if v is not None)
+    h2d = ranks.reduce_sum(h2d)
+    d2h = ranks.reduce_sum(d2h)
     valid_frac = r["num_valid"] / float(npix_local)
 
     # ---------------- roofline of the dominant kernel ----------------

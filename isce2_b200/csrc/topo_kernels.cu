@@ -461,6 +461,22 @@ __device__ bool block_stable_ranks(const double *v, int n, const double *pm, con
     return sorted;
 }
 
+// block-wide "is non-decreasing" test of a[0..n) (adjacent compares; NaNs count as ordered, like the reference's
+// insertion sort, which never moves across a false comparison)
+__device__ bool block_is_sorted(const double *a, int n, int *s_flag)
+{
+    if (threadIdx.x == 0) *s_flag = 1;
+    __syncthreads();
+    int bad = 0;
+    for (int i = threadIdx.x + 1; i < n; i += blockDim.x)
+        if (a[i - 1] > a[i]) bad = 1;
+    if (bad) *s_flag = 0; // benign race: everybody writes the same value
+    __syncthreads();
+    const int r = *s_flag;
+    __syncthreads();
+    return r != 0;
+}
+
 // Forward scan of the reference (:791-799, :834-842):  aa = v(1); for i = 2..nflag: if v(i) <= aa flag else aa = v(i).
 // Flagged samples never exceed aa, so aa is the plain prefix maximum: flag[i] |= bit if v[i] <= max(v[0..i-1]).
 template <typename T, typename S, typename Op>
@@ -569,10 +585,11 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double ctrackmin = s_mm[0] - demmax, ctrackmax = s_mm[1] + demmax;
         const double dctrack = (ctrackmax - ctrackmin) / (ow - 1.0);
 
-        // ---- stable co-sort (ctrack; lat, lon) :735 ----
-        block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
+        // ---- stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
         const double *cs = ctrack_in, *lats = lat_in, *lons = lon_in;
-        if (!block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag)) {
+        if (!block_is_sorted(ctrack_in, w, &s_flag)) {
+            block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
+            block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < w; i += blockDim.x) {
                 const int r = rank[i];
                 cs_s[r] = ctrack_in[i];
@@ -595,36 +612,38 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         }
         __syncthreads();
 
-        // ---- stable co-sort (orng; ctrack) :787 ----
-        block_prefix_max_suffix_min(orng, ow, pm, sm, s_warp_d);
-        const double *orng_s = orng, *ctr_s = ctr;
-        if (!block_stable_ranks(orng, ow, pm, sm, rank, &s_flag)) {
+        // ---- shadow (:791-809) on float32 elevang in pixel order ----
+        for (int i = threadIdx.x; i < (w + 3) / 4; i += blockDim.x) smask[i] = 0u;
+        __syncthreads();
+        block_prefix_max_flags<float>(elev, w, w, sbytes, (unsigned char)1, s_warp_f, OpMaxF());
+        block_suffix_min_flags<float>(elev, w, nullptr, 0, sbytes, (unsigned char)1, s_warp);
+
+        // ---- stable co-sort (orng; ctrack) :787 and layover (:834-852) on the range-sorted ctrack ----
+        // ctrack increases with the sample index by construction, so when the slant ranges are already ascending the
+        // sorted ctrack is ascending too and neither layover scan can flag anything: the line is done.
+        const bool orng_sorted_already = block_is_sorted(orng, ow, &s_flag);
+        if (!orng_sorted_already) {
+            block_prefix_max_suffix_min(orng, ow, pm, sm, s_warp_d);
+            block_stable_ranks(orng, ow, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < ow; i += blockDim.x) {
                 const int r = rank[i];
                 orng_sorted[r] = orng[i];
                 ctr_sorted[r] = ctr[i];
+                oflag[i] = 0;
             }
-            orng_s = orng_sorted; ctr_s = ctr_sorted;
             __syncthreads();
+            // forward layover scan is bounded by `width`, not `owidth`, exactly as in the reference (:835); the
+            // backward scan treats forward-flagged samples as resets (:847)
+            block_prefix_max_flags<double>(ctr_sorted, ow, w, oflag, (unsigned char)2, s_warp_d, OpMaxD());
+            block_suffix_min_flags<double>(ctr_sorted, ow, oflag, (unsigned char)2, oflag, (unsigned char)4, s_warp);
         }
-
-        // ---- shadow (:791-809) on float32 elevang in pixel order; layover (:834-852) on range-sorted ctrack ----
-        for (int i = threadIdx.x; i < (w + 3) / 4; i += blockDim.x) smask[i] = 0u;
-        for (int i = threadIdx.x; i < ow; i += blockDim.x) oflag[i] = 0;
-        __syncthreads();
-        block_prefix_max_flags<float>(elev, w, w, sbytes, (unsigned char)1, s_warp_f, OpMaxF());
-        block_suffix_min_flags<float>(elev, w, nullptr, 0, sbytes, (unsigned char)1, s_warp);
-        // forward layover scan is bounded by `width`, not `owidth`, exactly as in the reference (:835); the
-        // backward scan treats forward-flagged samples as resets (:847)
-        block_prefix_max_flags<double>(ctr_s, ow, w, oflag, (unsigned char)2, s_warp_d, OpMaxD());
-        block_suffix_min_flags<double>(ctr_s, ow, oflag, (unsigned char)2, oflag, (unsigned char)4, s_warp);
 
         // ---- scatter to radar pixels through the slant-range line (:855-865) ----
         const double rho0 = rho[0], rhon = rho[w - 1];
         const double rscale = (rhon > rho0) ? (double)(w - 1) / (rhon - rho0) : 0.0;
-        for (int i = threadIdx.x; i < ow; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (orng_sorted_already ? 0 : ow); i += blockDim.x) {
             if (oflag[i]) {
-                const double val = orng_s[i];
+                const double val = orng_sorted[i];
                 const int guess = (int)((val - rho0) * rscale);
                 const int j = ref_search_result(search_count_le([&](int m) { return rho[m]; }, w, val, guess), w);
                 // mask(j) < omask(i) => mask(j) += 2  <=>  set bit 1 (mask is 0/1 before any layover hit)
@@ -702,7 +721,7 @@ int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, i
 
 int mask_grid_size(int nlines)
 {
-    int g = 2 * 148; // persistent CTAs, two per SM
+    int g = 148 * (2048 / kMaskBlock); // persistent CTAs: as many as can be resident at 64 registers/thread, x2
     return nlines < g ? nlines : g;
 }
 

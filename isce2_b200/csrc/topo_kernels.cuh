@@ -8,7 +8,10 @@
 namespace b2 {
 
 constexpr int kTopoBlock = 128; // threads per CTA of the per-pixel kernel (one pixel per thread)
-constexpr int kMaskBlock = 1024;
+#ifndef B2_MASK_BLOCK
+#define B2_MASK_BLOCK 1024
+#endif
+constexpr int kMaskBlock = B2_MASK_BLOCK;
 
 // Resident output layers of one block of azimuth lines (device pointers; optional ones may be null).
 struct TopoLayers {
