@@ -216,6 +216,7 @@ struct b200_topo_plan {
     TopoConst C{};
     DeviceOrbit orb;
     float *d_dem = nullptr;
+    float *d_sinc = nullptr;
     void *d_raw = nullptr;
     int *d_maxkey = nullptr;
     double *d_rho = nullptr;  // block rows of the slant-range image
@@ -239,6 +240,7 @@ struct b200_topo_plan {
         cudaSetDevice(p.device);
         dfree(orb.buf);
         dfree(d_dem);
+        dfree(d_sinc);
         dfree(d_raw);
         dfree(d_maxkey);
         dfree(d_rho);
@@ -283,10 +285,9 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     if (!dem) return fail(err, errlen, B200_EINVAL, "dem is NULL");
     if (dem_dtype != B200_DEM_F32 && dem_dtype != B200_DEM_I16) return fail(err, errlen, B200_EINVAL, "bad dem_dtype %d", dem_dtype);
     if (p.dem_method != B200_DEM_BILINEAR && p.dem_method != B200_DEM_BICUBIC && p.dem_method != B200_DEM_NEAREST &&
-        p.dem_method != B200_DEM_BIQUINTIC) {
-        if (p.dem_method == B200_DEM_SINC || p.dem_method == B200_DEM_AKIMA)
-            return fail(err, errlen, B200_EINVAL, "DEM interpolation method %d (SINC/AKIMA) is not implemented on the GPU yet",
-                        p.dem_method);
+        p.dem_method != B200_DEM_BIQUINTIC && p.dem_method != B200_DEM_SINC) {
+        if (p.dem_method == B200_DEM_AKIMA)
+            return fail(err, errlen, B200_EINVAL, "DEM interpolation method AKIMA is not implemented on the GPU yet");
         return fail(err, errlen, B200_EINVAL, "Undefined interpolation method.");
     }
     if ((rc = check_orbit(orbit, p.orbit_method, err, errlen)) != B200_OK) return rc;
@@ -356,7 +357,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     CK(dmalloc(&d_bbox, sizeof h_bbox));
     {
         TopoConst Cb = C;
-        Cb.dem = DemView{nullptr, 0, 0};
+        Cb.dem = DemView{nullptr, 0, 0, nullptr};
         Cb.rho_image = pl->d_rho0; // row 1 of the image, or NULL -> polynomial
         launch_topo_bbox(Cb, pl->orb.view, d_bbox, s);
         pl->launches++;
@@ -445,7 +446,14 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         dfree(pl->d_raw);
         pl->d_raw = nullptr;
     }
-    C.dem = DemView{pl->d_dem, udemwidth, udemlength};
+    if (p.dem_method == B200_DEM_SINC) { // prepareMethods (topozeroMethods.f:46-63)
+        std::vector<float> tab((size_t)kSincSub * kSincLen);
+        sinc_make_table(tab.data());
+        CK(dmalloc(&pl->d_sinc, sizeof(float) * tab.size()));
+        CK(cudaMemcpyAsync(pl->d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    C.dem = DemView{pl->d_dem, udemwidth, udemlength, pl->d_sinc};
     C.rho_image = pl->d_rho ? pl->d_rho - (size_t)pl->line0 * (size_t)p.width : nullptr;
 
     // ---- per-line state ----

@@ -12,6 +12,7 @@ namespace b2 {
 struct DemView {
     const float *data; // [ny][nx], lon fastest == Fortran dem(nx, ny)
     int nx, ny;
+    const float *sinc; // fintp table [8192][8] of the SINC interpolator (topozeroMethods.f:57-61), else NULL
 };
 
 #ifdef __CUDA_ARCH__
@@ -48,6 +49,59 @@ B2_HD float interp_bilinear(const DemView &d, int i_x, int i_y, double f_x, doub
             -(q22 * (x - x1) * (y - y1));
     }
     return (float)r;
+}
+
+// SINC: 8x8 taps, 8192 sub-sample shifts, everything in float32 (topozeroMethods.f:100-121 -> uniform_interp.f90:
+// 407-430 sinc_eval_2d_f): products and the running sum round to float32 in the reference's order (k outer, m inner),
+// so the result is bit-identical.  The coefficient table is built on the host by sinc_make_table().
+constexpr int kSincSub = 8192, kSincLen = 8;
+B2_HD float interp_sinc(const DemView &d, int i_x, int i_y, double f_x, double f_y)
+{
+    if ((i_x < 4) || (i_x > (d.nx - 3))) return kBadValue;
+    if ((i_y < 4) || (i_y > (d.ny - 3))) return kBadValue;
+    const int intpx = i_x + kSincLen / 2, intpy = i_y + kSincLen / 2; // 0-based into the DEM
+    float acc = 0.f;
+    if ((intpx >= kSincLen - 1 && intpx < d.nx) && (intpy >= kSincLen - 1 && intpy < d.ny)) {
+        int ifx = (int)(f_x * kSincSub), ify = (int)(f_y * kSincSub);
+        ifx = ifx < 0 ? 0 : (ifx > kSincSub - 1 ? kSincSub - 1 : ifx);
+        ify = ify < 0 ? 0 : (ify > kSincSub - 1 ? kSincSub - 1 : ify);
+        const float *cx = d.sinc + (size_t)ifx * kSincLen, *cy = d.sinc + (size_t)ify * kSincLen;
+        float wy[kSincLen];
+#pragma unroll
+        for (int m = 0; m < kSincLen; m++) wy[m] = B2_LDG(cy + m);
+#pragma unroll 1
+        for (int k = 0; k < kSincLen; k++) {
+            const float wxk = B2_LDG(cx + k);
+#pragma unroll
+            for (int m = 0; m < kSincLen; m++) {
+                float a = B2_LDG(d.data + (size_t)(intpy - m) * (size_t)d.nx + (size_t)(intpx - k));
+                float t = a * wxk;
+                t = t * wy[m];
+                acc = acc + t;
+            }
+        }
+    }
+    return acc;
+}
+
+// host: sinc_coef(beta=1, relfiltlen=8, decfactor=8192, pedestal=0, weight=1) (uniform_interp.f90:296-384) rearranged
+// as prepareMethods does (topozeroMethods.f:57-61)
+inline void sinc_make_table(float *fintp /* [kSincSub * kSincLen] */)
+{
+    const double pi = 4.0 * atan(1.0);
+    const int nco = kSincLen * kSincSub;
+    const double wgthgt = 0.5, soff = nco / 2.0;
+    double *r = new double[nco];
+    for (int i = 0; i < nco; i++) {
+        double wa = i - soff;
+        double sx = wa * 1.0 / (1.0 * kSincSub);
+        double fct = (sx != 0.0) ? sin(pi * sx) / (pi * sx) : 1.0;
+        double wgt = (1.0 - wgthgt) + wgthgt * cos((pi * wa) / soff);
+        r[i] = fct * wgt;
+    }
+    for (int i = 0; i < kSincLen; i++)
+        for (int j = 0; j < kSincSub; j++) fintp[i + j * kSincLen] = (float)r[j + i * kSincSub];
+    delete[] r;
 }
 
 // topozeroMethods.f:200-220

@@ -182,36 +182,23 @@ __device__ __forceinline__ void load_line_state(LineState &sL, const LineState *
 // and Doppler values are evaluated up front into shared memory so that a refill costs a few instructions.
 constexpr int kStrip = 128;                                  // pixels per warp
 constexpr int kSolvePixelsPerCta = (kTopoBlock / 32) * kStrip; // 512
+
+// Solve the strip_n pixels of one warp's strip (slant ranges / Doppler values in rng_s / dop_s): lanes pull the next
+// unsolved pixel as soon as their current one converges.  zrow[j] receives the SCH height of strip pixel j.
 template <int METHOD, bool REF>
-__global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
-k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, double *__restrict__ zsch_out,
-             TopoStats *stats)
+__device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState &sL, const double *rng_s, const double *dop_s,
+                                            int strip_n, double *zrow, int &conv, int &iters)
 {
-    __shared__ LineState sL;
-    __shared__ double s_rng[kTopoBlock / 32][kStrip];
-    __shared__ double s_dop[kTopoBlock / 32][kStrip];
-    const int bpl = (C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta; // CTAs per azimuth line
-    const int row = blockIdx.x / bpl;                                         // row within the block of lines
-    const int seg = blockIdx.x - row * bpl;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int line = line0 + row;
-    const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
-    const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip; // may be <= 0
-    load_line_state(sL, states, row);
-    for (int j = lane; j < strip_n; j += 32) {
-        s_rng[warp][j] = pixel_range(C, line, strip0 + j);
-        s_dop[warp][j] = eval_poly2d(C.dop, (double)line, (double)(strip0 + j));
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int nprimary = C.numiter + 1 < C.numiter + C.extraiter + 1 ? C.numiter + 1 : C.numiter + C.extraiter + 1;
-    double *zrow = zsch_out + (size_t)row * (size_t)C.width + (size_t)strip0;
     PixelConst P;
     double lat = 0.0, lon = 0.0, z = 0.0, zsch = 0.0;
     int it = 0, slot = lane, next = 32;
-    int conv = 0, iters = 0;
+    conv = 0;
+    iters = 0;
     bool active = slot < strip_n;
     if (active) {
-        P = make_pixel_const(C, sL, s_rng[warp][slot], s_dop[warp][slot]);
+        P = make_pixel_const(C, sL, rng_s[slot], dop_s[slot]);
         lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny; // :435-436
         lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
     }
@@ -255,7 +242,7 @@ k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
             active = j < strip_n;
             if (active) {
                 slot = j;
-                P = make_pixel_const(C, sL, s_rng[warp][j], s_dop[warp][j]);
+                P = make_pixel_const(C, sL, rng_s[j], dop_s[j]);
                 lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny;
                 lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
                 z = 0.0;
@@ -265,6 +252,32 @@ k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
         }
         next += __popc(m);
     }
+}
+
+template <int METHOD, bool REF>
+__global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
+k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, double *__restrict__ zsch_out,
+             TopoStats *stats)
+{
+    __shared__ LineState sL;
+    __shared__ double s_rng[kTopoBlock / 32][kStrip];
+    __shared__ double s_dop[kTopoBlock / 32][kStrip];
+    const int bpl = (C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta; // CTAs per azimuth line
+    const int row = blockIdx.x / bpl;                                         // row within the block of lines
+    const int seg = blockIdx.x - row * bpl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int line = line0 + row;
+    const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
+    const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip; // may be <= 0
+    load_line_state(sL, states, row);
+    for (int j = lane; j < strip_n; j += 32) {
+        s_rng[warp][j] = pixel_range(C, line, strip0 + j);
+        s_dop[warp][j] = eval_poly2d(C.dop, (double)line, (double)(strip0 + j));
+    }
+    __syncthreads();
+    double *zrow = zsch_out + (size_t)row * (size_t)C.width + (size_t)strip0;
+    int conv = 0, iters = 0;
+    solve_strip<METHOD, REF>(C, sL, s_rng[warp], s_dop[warp], strip_n, zrow, conv, iters);
     // convergence statistics (:570): warps leave as they finish, no block-wide barrier
     conv = warp_sum(conv);
     iters = warp_sum(iters);
@@ -330,23 +343,33 @@ __global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
 k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, TopoLayers out, TopoStats *stats)
 {
     __shared__ LineState sL;
-    const int bpl = (C.width + kTopoBlock - 1) / kTopoBlock;
+    __shared__ double s_rng[kTopoBlock / 32][kStrip];
+    __shared__ double s_dop[kTopoBlock / 32][kStrip];
+    __shared__ double s_z[kTopoBlock / 32][kStrip];
+    const int bpl = (C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta;
     const int row = blockIdx.x / bpl;
     const int seg = blockIdx.x - row * bpl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int line = line0 + row;
+    const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
+    const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip;
     load_line_state(sL, states, row);
+    for (int j = lane; j < strip_n; j += 32) {
+        s_rng[warp][j] = pixel_range(C, line, strip0 + j);
+        s_dop[warp][j] = eval_poly2d(C.dop, (double)line, (double)(strip0 + j));
+    }
     __syncthreads();
-    const int pix = seg * blockDim.x + threadIdx.x;
-    double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
     int conv = 0, iters = 0;
-    if (pix < C.width) {
-        const int line = line0 + row;
-        const double rng = pixel_range(C, line, pix);
-        const double dop = eval_poly2d(C.dop, (double)line, (double)pix);
-        const size_t w = (size_t)C.width;
+    solve_strip<METHOD, REF>(C, sL, s_rng[warp], s_dop[warp], strip_n, s_z[warp], conv, iters);
+    __syncwarp();
+    // final pass over the strip, consecutive lanes on consecutive pixels (coalesced layer stores)
+    double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
+    const size_t w = (size_t)C.width;
+    for (int j = lane; j < strip_n; j += 32) {
+        const int pix = strip0 + j;
         const size_t o = (size_t)row * w + (size_t)pix;
         PixelResult R;
-        const double zsch = topo_solve<METHOD, REF>(C, sL, rng, dop, conv, iters);
-        topo_final<METHOD, REF>(C, sL, rng, dop, zsch, out.inc != nullptr, R);
+        topo_final<METHOD, REF>(C, sL, s_rng[warp][j], s_dop[warp][j], s_z[warp][j], out.inc != nullptr, R);
         out.lat[o] = R.lat;
         out.lon[o] = R.lon;
         out.hgt[o] = R.hgt;
@@ -362,13 +385,13 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
             out.ctrack[o] = R.ctrack;
             out.elev[o] = R.elev;
         }
-        mnlat = mxlat = R.lat;
-        mnlon = mxlon = R.lon;
+        mnlat = fmin(mnlat, R.lat); mxlat = fmax(mxlat, R.lat);
+        mnlon = fmin(mnlon, R.lon); mxlon = fmax(mxlon, R.lon);
     }
     mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
     conv = warp_sum(conv);
     iters = warp_sum(iters);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0 && strip_n > 0) {
         atomicMin(&stats->min_lat, order_key(mnlat));
         atomicMax(&stats->max_lat, order_key(mxlat));
         atomicMin(&stats->min_lon, order_key(mnlon));
@@ -755,7 +778,7 @@ template <int METHOD>
 static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, const TopoLayers &out, TopoStats *stats,
                             unsigned grid, unsigned grid_solve, cudaStream_t s, cudaEvent_t ev_mid)
 {
-    constexpr bool kSplit = (METHOD == 5 || METHOD == 2);
+    constexpr bool kSplit = (METHOD == 5 || METHOD == 2 || METHOD == 0);
     if (kSplit) {
         if (C.ref.use_ref) {
             k_topo_solve<METHOD, true><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
@@ -767,13 +790,13 @@ static void launch_pixels_m(const TopoConst &C, const LineState *states, int lin
             k_topo_final<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         }
     } else {
-        if (C.ref.use_ref) k_topo_fused<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
-        else k_topo_fused<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
+        if (C.ref.use_ref) k_topo_fused<METHOD, true><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
+        else k_topo_fused<METHOD, false><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         if (ev_mid) cudaEventRecord(ev_mid, s);
     }
 }
 
-int topo_pixel_launches(int method) { return (method == 5 || method == 2) ? 2 : 1; }
+int topo_pixel_launches(int method) { return (method == 5 || method == 2 || method == 0) ? 2 : 1; }
 
 // launches k_topo_solve + k_topo_final (2 kernels); out.ctrack must be allocated (it carries the SCH height between them)
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
@@ -783,6 +806,7 @@ int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, i
     if (nblk > 0x7fffffffLL || !out.ctrack) return -2;
     const unsigned gs = (unsigned)(((C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta) * (long long)nlines);
     switch (C.method) {
+    case 0: launch_pixels_m<0>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
@@ -816,6 +840,7 @@ int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int
 {
     size_t smem = (size_t)((C.width + 3) / 4) * 4;
     switch (C.method) {
+    case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;

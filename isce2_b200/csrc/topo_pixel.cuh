@@ -51,6 +51,7 @@ struct PixelResult {
 template <int METHOD>
 B2_HD float interp_dem(const TopoConst &C, int ix, int iy, double fx, double fy)
 {
+    if (METHOD == 0) return interp_sinc(C.dem, ix, iy, fx, fy);
     if (METHOD == 1) return interp_bilinear(C.dem, ix, iy, fx, fy);
     if (METHOD == 2) return interp_bicubic(C.dem, ix, iy, fx, fy);
     if (METHOD == 3) return interp_nearest(C.dem, ix, iy, fx, fy);

@@ -503,11 +503,69 @@ static float interp2dspline(int order, const float *dem, int nx /*lon count*/, i
     return (float)temp;
 }
 
+/* ---- sinc: uniform_interp.f90:296-384 (sinc_coef) + topozeroMethods.f:46-63 (prepareMethods) ---- */
+#define SINC_SUB 8192
+#define SINC_LEN 8
+static float *g_fintp = NULL;
+static const float *sinc_table(void)
+{
+#pragma omp critical(orc_sinc_table)
+    if (!g_fintp) {
+        const double pi = 4.0 * atan(1.0);
+        const double r_beta = 1.0, r_relfiltlen = 1.0 * SINC_LEN, r_pedestal = 0.0;
+        const int i_decfactor = SINC_SUB;
+        const int i_intplength = (int)lround(r_relfiltlen / r_beta);
+        const int i_filtercoef = i_intplength * i_decfactor;
+        const double r_wgthgt = (1.0 - r_pedestal) / 2.0;
+        const double r_soff = i_filtercoef / 2.0;
+        double *r_filter = malloc(sizeof(double) * (i_filtercoef + 1));
+        for (int i = 0; i < i_filtercoef; i++) {
+            double r_wa = i - r_soff;
+            double r_s = r_wa * r_beta / (1.0 * i_decfactor);
+            double r_fct = (r_s != 0.0) ? sin(pi * r_s) / (pi * r_s) : 1.0;
+            double r_wgt = (1.0 - r_wgthgt) + r_wgthgt * cos((pi * r_wa) / r_soff);
+            r_filter[i] = r_fct * r_wgt;
+        }
+        float *f = malloc(sizeof(float) * SINC_SUB * SINC_LEN);
+        for (int i = 0; i < SINC_LEN; i++)
+            for (int j = 0; j < SINC_SUB; j++) f[i + j * SINC_LEN] = (float)r_filter[j + i * SINC_SUB];
+        free(r_filter);
+        g_fintp = f;
+    }
+    return g_fintp;
+}
+void orc_sinc_table(float *out) { memcpy(out, sinc_table(), sizeof(float) * SINC_SUB * SINC_LEN); }
+
+/* uniform_interp.f90:407-430 sinc_eval_2d_f: everything in real*4, k outer / m inner */
+static float sinc_eval_2d_f(const float *dem, const float *intarr, int idec, int ilen, int intpx, int intpy, double frpx,
+                            double frpy, int nx, int ny)
+{
+    float acc = 0.f;
+    if ((intpx >= ilen - 1 && intpx < nx) && (intpy >= ilen - 1 && intpy < ny)) {
+        int ifracx = (int)(frpx * idec), ifracy = (int)(frpy * idec);
+        ifracx = ifracx < 0 ? 0 : (ifracx > idec - 1 ? idec - 1 : ifracx);
+        ifracy = ifracy < 0 ? 0 : (ifracy > idec - 1 ? idec - 1 : ifracy);
+        for (int k = 0; k < ilen; k++)
+            for (int m = 0; m < ilen; m++) {
+                /* arrin(intpx-k, intpy-m) is 0-based: dem element (intpx-k+1, intpy-m+1) in 1-based terms */
+                float a = DEM(intpx - k + 1, intpy - m + 1);
+                float t = a * intarr[k + ifracx * ilen];
+                t = t * intarr[m + ifracy * ilen];
+                acc = acc + t;
+            }
+    }
+    return acc;
+}
+
 /* topozeroMethods.f:123-247 wrappers (window checks -> BADVALUE) */
 float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x, double f_y, int nx, int ny)
 {
     double dx = i_x + f_x, dy = i_y + f_y;
     switch (method) {
+    case ORC_SINC: /* :100-121 */
+        if ((i_x < 4) || (i_x > (nx - 3))) return ORC_BADVALUE;
+        if ((i_y < 4) || (i_y > (ny - 3))) return ORC_BADVALUE;
+        return sinc_eval_2d_f(dem, sinc_table(), SINC_SUB, SINC_LEN, i_x + SINC_LEN / 2, i_y + SINC_LEN / 2, f_x, f_y, nx, ny);
     case ORC_BILINEAR: /* :123-147 */
         if ((i_x < 1) || (i_x >= nx)) return ORC_BADVALUE;
         if ((i_y < 1) || (i_y >= ny)) return ORC_BADVALUE;
@@ -527,7 +585,7 @@ float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x,
         return DEM(ix, iy);
     }
     default:
-        return NAN; /* SINC / AKIMA not restated yet */
+        return NAN; /* AKIMA not restated yet */
     }
 }
 
@@ -627,7 +685,10 @@ int orc_topo(const orc_topo_params *p, const float *dem_full, const orc_orbit *o
     int rc = 0;
 
     if (p->orbitmethod == ORC_LEGENDRE ? orb->nvec < 9 : orb->nvec < 4) return -2; /* :104-131 'stop' */
-    if (method != ORC_BILINEAR && method != ORC_BICUBIC && method != ORC_BIQUINTIC && method != ORC_NEAREST) return -3;
+    if (method != ORC_BILINEAR && method != ORC_BICUBIC && method != ORC_BIQUINTIC && method != ORC_NEAREST &&
+        method != ORC_SINC)
+        return -3;
+    if (method == ORC_SINC) sinc_table();
     if (!slrng && !rho_image) return -4;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);

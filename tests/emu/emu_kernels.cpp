@@ -33,7 +33,9 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
     C.elp = make_ellipsoid(A->a, A->e2);
     C.wvl = A->wvl; C.thresh = A->thresh; C.ilrl = A->ilrl; C.numiter = A->numiter; C.extraiter = A->extraiter;
     C.ufirstlat = A->ufirstlat; C.ufirstlon = A->ufirstlon; C.deltalat = A->deltalat; C.deltalon = A->deltalon;
-    C.dem = DemView{dem, A->nx, A->ny};
+    static float *sinc_tab = nullptr;
+    if (A->method == 0 && !sinc_tab) { sinc_tab = new float[(size_t)kSincSub * kSincLen]; sinc_make_table(sinc_tab); }
+    C.dem = DemView{dem, A->nx, A->ny, sinc_tab};
     C.method = A->method; C.width = A->width; C.length = A->length; C.nazlooks = A->nazlooks;
     C.t0 = A->t0; C.prf = A->prf; C.peghdg = A->peghdg;
     C.pi = 4.0 * atan(1.0); C.r2d = 180.0 / C.pi; C.orbit_method = A->orbit_method;
@@ -66,6 +68,7 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
             const bool winc = A->want_inc != 0;
             if (A->use_ref) {
                 switch (A->method) {
+                case 0: topo_pixel<0, true>(C, L, rng, dop, winc, R); break;
                 case 1: topo_pixel<1, true>(C, L, rng, dop, winc, R); break;
                 case 2: topo_pixel<2, true>(C, L, rng, dop, winc, R); break;
                 case 3: topo_pixel<3, true>(C, L, rng, dop, winc, R); break;
@@ -73,6 +76,7 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
                 }
             } else {
                 switch (A->method) {
+                case 0: topo_pixel<0, false>(C, L, rng, dop, winc, R); break;
                 case 1: topo_pixel<1, false>(C, L, rng, dop, winc, R); break;
                 case 2: topo_pixel<2, false>(C, L, rng, dop, winc, R); break;
                 case 3: topo_pixel<3, false>(C, L, rng, dop, winc, R); break;

@@ -209,7 +209,7 @@ def test_golden_rdr2geo_and_geo2rdr(golden):
     for e in golden["rdr2geo"]:
         h = e["height"]
         dem, flat, flon, dlat, dlon = _flat_dem(e["llh"][0], e["llh"][1], h)
-        for method in ("BILINEAR", "BICUBIC", "BIQUINTIC", "NEAREST"):
+        for method in ("BILINEAR", "BICUBIC", "BIQUINTIC", "NEAREST", "SINC"):
             out = orc.topo(dem=dem, first_lat=flat, first_lon=flon, delta_lat=dlat, delta_lon=dlon,
                            orbit_t=rows[:, 0], orbit_pos=rows[:, 1:4], orbit_vel=rows[:, 4:7], length=2, width=2,
                            r0=e["rng"], dr=1.0, prf=1000.0, t0=e["t"], wvl=0.056, side=e["side"],
@@ -227,3 +227,22 @@ def test_golden_rdr2geo_and_geo2rdr(golden):
         # and the oracle's own round trip closes far tighter
         assert abs(g["azt"][0, 0] - e["t"]) < 2e-9
         assert abs(g["rgm"][0, 0] - e["rng"]) < 1e-6
+
+
+def test_sinc_table_and_unit_response():
+    """SINC interpolator (topozeroMethods.f:100-121, uniform_interp.f90:296-430): 8 taps x 8192 shifts, raised-cosine
+    weighted, unit DC gain to float32 accuracy, peak tap 4 at zero shift.  Because the Fortran passes the 1-based DEM to
+    a 0-based dummy argument, the interpolant is the DEM shifted by one cell: on a ramp z = x + 10 y the value at
+    (ix, iy, 0, 0) is that of cell (ix+1, iy+1)."""
+    tab = np.zeros(8192 * 8, np.float32)
+    orc.lib().orc_sinc_table.argtypes = [orc._fp]
+    orc.lib().orc_sinc_table(orc._f(tab))
+    tab = tab.reshape(8192, 8)
+    assert tab[0, 4] == 1.0 and abs(tab[0].sum() - 1.0) < 1e-6
+    assert np.abs(tab.sum(axis=1) - 1.0).max() < 2e-2  # 8-tap truncation ripple
+    ny, nx = 40, 50
+    yy, xx = np.mgrid[1:ny + 1, 1:nx + 1]
+    dem = (xx + 10.0 * yy).astype(np.float32)
+    v = orc.interp_dem("SINC", dem, 20, 15, 0.0, 0.0)
+    assert abs(v - (21 + 10.0 * 16)) < 1e-3
+    assert orc.interp_dem("SINC", dem, 3, 15, 0.0, 0.0) == -1000.0 and orc.interp_dem("SINC", dem, 20, ny - 2, 0.0, 0.0) == -1000.0
