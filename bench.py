@@ -443,13 +443,63 @@ def run_b200(args, ranks):
     return line
 
 
+def run_c4(args, ranks):
+    """BASELINE configs[4]: topsStack geo2rdr batch -- one reference geometry (the C2 swath's lat/lon/hgt, computed once
+    per GPU and kept resident) against 29 perturbed secondary orbits; the 29 jobs are dealt round-robin to the ranks
+    (contrib/stack/topsStack/Stack.py:805-827 launches one process per secondary date).  One step = all 29 jobs."""
+    from isce2_b200 import _capi as capi
+    dev = ranks.local_rank % capi.device_count()
+    w = dict(WORKLOADS["c2"])
+    if args.lines:
+        w["length"] = int(args.lines)
+    sc = synth.make_scene(w["length"], w["width"], sensor="s1", name="c4")
+    tparams = capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                               delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
+                               side=sc.side, peg_heading=sc.peg_heading, dem_method="BIQUINTIC", device=dev)
+    tplan = capi.TopoPlan(tparams, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]],
+                          want_los=False, want_inc=False, want_mask=False)
+    tplan.execute()
+    jobs = [j for j in range(29) if j % ranks.world == ranks.rank]
+    secs = {j: synth.config_c1_secondary(length=sc.length, width=sc.width, seed=j + 1) for j in jobs}
+    gp = capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0 - 1.7, dr=sc.dr, prf=sc.prf,
+                         t0=sc.t0 - 0.013, wvl=sc.wvl, side=sc.side, device=dev, out_f32=True)
+    gplan = capi.GeoPlan(gp, topo_plan=tplan)
+
+    def step():
+        ms = 0.0
+        for j in jobs:
+            o = secs[j]
+            ms += gplan.execute(gp, o.orbit_t, o.orbit_pos, o.orbit_vel, want=("azoff", "rgoff"))
+        return ms
+
+    for _ in range(args.warmup):
+        step()
+    ranks.barrier()
+    sampler = ClockSampler(dev)
+    t_lo = time.time()
+    ms = sum(step() for _ in range(args.steps)) / args.steps
+    clocks = sampler.stop(t_lo, time.time())
+    ms = ranks.reduce_max(ms)
+    npx = 29 * sc.pixels
+    if ranks.rank == 0:
+        print(json.dumps({"metric": "geo2rdr Mpixels/s (29-orbit stack batch)", "value": npx / (ms * 1e-3) / 1e6, "unit": "Mpixels/s",
+                          "n_gpus": ranks.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "topsStack batch: 29 secondary orbits x (13500 x 25000) geo2rdr on one resident "
+                                                 "reference geometry, jobs dealt round-robin to the GPUs",
+                                     "pixels_per_step": npx, "jobs_on_rank0": len(jobs)},
+                          "gpu_launches": int(args.steps * 2 * len(jobs)), "clocks": clocks}), flush=True)
+    gplan.close()
+    tplan.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
     ap.add_argument("--lines", type=int, default=None, help="override the number of azimuth lines (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-step-seconds", type=float, default=6.0)
@@ -459,7 +509,11 @@ def main():
         log("[bench] note: W < 3 warm-up steps requested; the timing rules ask for >= 3")
     ranks = Ranks()
     try:
-        if args.impl == "reference":
+        if args.workload == "c4" and args.impl == "b200":
+            run_c4(args, ranks)
+        elif args.impl == "reference":
+            if args.workload == "c4":
+                args.workload = "c2"
             run_reference(args, ranks)
         else:
             run_b200(args, ranks)

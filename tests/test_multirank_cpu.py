@@ -1,0 +1,70 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): the azimuth line-block sharding of bench.py covers the swath exactly
+once, the timing reduction is a max over ranks, byte counters are summed, and the `--impl reference` arm runs on rank
+0 only.  No data-path collective exists on this path (lines are independent), so this is all the multi-rank code."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import json, os, sys
+sys.path.insert(0, {root!r})
+import bench
+r = bench.Ranks()
+a, n = bench.shard(13501, r.rank, r.world)
+tot = r.reduce_sum(n)
+mx = r.reduce_max(10.0 * (r.rank + 1))
+r.barrier()
+print(json.dumps(dict(rank=r.rank, world=r.world, line0=a, nlines=n, total=tot, max=mx)), flush=True)
+r.close()
+'''
+
+
+def _torchrun(args, timeout=240):
+    env = dict(os.environ)
+    env["MASTER_ADDR"] = "127.0.0.1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533"] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_line_block_sharding_and_reductions_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    p = _torchrun([str(script)])
+    assert p.returncode == 0, p.stderr[-2000:]
+    rows = sorted((json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")), key=lambda d: d["rank"])
+    assert [r["rank"] for r in rows] == [0, 1] and all(r["world"] == 2 for r in rows)
+    assert rows[0]["line0"] == 0 and rows[0]["line0"] + rows[0]["nlines"] == rows[1]["line0"]
+    assert rows[1]["line0"] + rows[1]["nlines"] == 13501
+    assert all(r["total"] == 13501 and r["max"] == 20.0 for r in rows)
+
+
+def test_shard_partitions_any_world():
+    sys.path.insert(0, ROOT)
+    import bench
+    for length in (1, 7, 1500, 13500, 60001):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [bench.shard(length, r, world) for r in range(world)]
+            pos = 0
+            for a, n in blocks:
+                assert a == pos and n >= 0
+                pos += n
+            assert pos == length
+            assert max(n for _, n in blocks) - min(n for _, n in blocks) <= 1
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_runs_on_rank0_only_world2():
+    p = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--workload", "c0c1",
+                   "--lines", "48", "--ref-step-seconds", "1"], timeout=500)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = lines[0]
+    assert d["impl"] == "reference" and d["metric"] == "topo+geo2rdr Mpixels/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
