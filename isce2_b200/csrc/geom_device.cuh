@@ -336,7 +336,9 @@ B2_HD double reast_s(const Ellipsoid &e, double s /* sin(lat) */) { return div_n
 B2_HD double reast(const Ellipsoid &e, double lat) { return reast_s(e, sin(lat)); }
 B2_HD double rnorth_s(const Ellipsoid &e, double s /* sin(lat) */)
 {
-    return (e.a * (1.0 - e.e2)) / pow(1.0 - e.e2 * (s * s), 1.5);
+    // (...)**1.5 of curvature.F:45 as x*sqrt(x): within an ulp of pow(), and only the float32 incidence layer sees it
+    const double x = 1.0 - e.e2 * (s * s);
+    return div_n(e.a * (1.0 - e.e2), x * sqrt_n(x));
 }
 B2_HD double rnorth(const Ellipsoid &e, double lat) { return rnorth_s(e, sin(lat)); }
 B2_HD double rdir(const Ellipsoid &e, double hdg, double lat)

@@ -19,7 +19,8 @@ a, n = bench.shard(13501, r.rank, r.world)
 tot = r.reduce_sum(n)
 mx = r.reduce_max(10.0 * (r.rank + 1))
 r.barrier()
-print(json.dumps(dict(rank=r.rank, world=r.world, line0=a, nlines=n, total=tot, max=mx)), flush=True)
+open(os.path.join({out!r}, "rank%d.json" % r.rank), "w").write(
+    json.dumps(dict(rank=r.rank, world=r.world, line0=a, nlines=n, total=tot, max=mx)))
 r.close()
 '''
 
@@ -34,10 +35,10 @@ def _torchrun(args, timeout=240):
 
 def test_line_block_sharding_and_reductions_world2(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT))
+    script.write_text(WORKER.format(root=ROOT, out=str(tmp_path)))
     p = _torchrun([str(script)])
     assert p.returncode == 0, p.stderr[-2000:]
-    rows = sorted((json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")), key=lambda d: d["rank"])
+    rows = [json.loads((tmp_path / f"rank{r}.json").read_text()) for r in (0, 1)]
     assert [r["rank"] for r in rows] == [0, 1] and all(r["world"] == 2 for r in rows)
     assert rows[0]["line0"] == 0 and rows[0]["line0"] + rows[0]["nlines"] == rows[1]["line0"]
     assert rows[1]["line0"] + rows[1]["nlines"] == 13501
