@@ -348,10 +348,13 @@ def run_b200(args, ranks):
     for _ in range(min(args.warmup, 1)):
         e2e_step()
     ranks.barrier()
-    w0 = time.perf_counter()
+    e2e_times = []
     for _ in range(e2e_steps):
+        w0 = time.perf_counter()
         r = e2e_step()
-    wall_e2e = (time.perf_counter() - w0) / e2e_steps
+        e2e_times.append(time.perf_counter() - w0)
+    log(f"[bench] rank {ranks.rank} e2e step times (ms): {[round(1e3 * t, 1) for t in e2e_times]}")
+    wall_e2e = sum(e2e_times) / e2e_steps
     wall_e2e = ranks.reduce_max(wall_e2e)
     ranks.barrier()
     e2e_value = npix_total / wall_e2e / 1e6
