@@ -284,12 +284,8 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     if (p.width < 2 || p.length < 1) return fail(err, errlen, B200_EINVAL, "bad radar grid %d x %d", p.length, p.width);
     if (!dem) return fail(err, errlen, B200_EINVAL, "dem is NULL");
     if (dem_dtype != B200_DEM_F32 && dem_dtype != B200_DEM_I16) return fail(err, errlen, B200_EINVAL, "bad dem_dtype %d", dem_dtype);
-    if (p.dem_method != B200_DEM_BILINEAR && p.dem_method != B200_DEM_BICUBIC && p.dem_method != B200_DEM_NEAREST &&
-        p.dem_method != B200_DEM_BIQUINTIC && p.dem_method != B200_DEM_SINC) {
-        if (p.dem_method == B200_DEM_AKIMA)
-            return fail(err, errlen, B200_EINVAL, "DEM interpolation method AKIMA is not implemented on the GPU yet");
-        return fail(err, errlen, B200_EINVAL, "Undefined interpolation method.");
-    }
+    if (p.dem_method < B200_DEM_SINC || p.dem_method > B200_DEM_BIQUINTIC)
+        return fail(err, errlen, B200_EINVAL, "Undefined interpolation method."); // topozero.f90:96-99
     if ((rc = check_orbit(orbit, p.orbit_method, err, errlen)) != B200_OK) return rc;
     if (!slrng && !rho_image)
         return fail(err, errlen, B200_EINVAL, "Both the slant range accessor and starting range are zero"); // topozero.f90:156-159

@@ -104,6 +104,85 @@ inline void sinc_make_table(float *fintp /* [kSincSub * kSincLen] */)
     delete[] r;
 }
 
+
+// AKIMA (components/isceobj/Util/src/akima_reg.F:54-317 through intp_akima, topozeroMethods.f:222-247), as written:
+// the partial derivatives are taken at (ix+1..ix+2, iy+1..iy+2) while the corner values are those of
+// (ix..ix+1, iy..iy+1) (getParDer :70-73 vs polyfitAkima :166-169), and the weights wx2/wx3/wy2/wy3 keep the value of
+// the previous grid point when the "equal slopes" branch is taken (:81-86, :95-100; initialised to 0 here, which the
+// guard at :113-120 turns into 1).  Sample differences are float32, everything else double, divisions IEEE.
+B2_HD bool aki_almost_equal(double x, double y) { return fabs(x - y) <= 2.220446049250313e-16; }
+B2_HD float interp_akima(const DemView &d, int i_x, int i_y, double f_x, double f_y)
+{
+    if ((i_x < 1) || (i_x >= (d.nx - 1))) return kBadValue;
+    if ((i_y < 1) || (i_y >= (d.ny - 1))) return kBadValue;
+#define Z(a, b) dem_at(d, (a), (b))
+    double sx[4], sy[4], sxy[4]; // index (jj-1) + 2*(ii-1)
+    double wx2 = 0.0, wx3 = 0.0, wy2 = 0.0, wy3 = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int ii = (q >> 1) + 1, jj = (q & 1) + 1;
+        int yy = i_y + ii;
+        yy = yy < 3 ? 3 : (yy > d.ny - 2 ? d.ny - 2 : yy);
+        int xx = i_x + jj;
+        xx = xx < 3 ? 3 : (xx > d.nx - 2 ? d.nx - 2 : xx);
+        const float zc = Z(xx, yy);
+        float f;
+        double m1, m2, m3, m4;
+        const float zxm1 = Z(xx - 1, yy), zxp1 = Z(xx + 1, yy);
+        f = zxm1 - Z(xx - 2, yy); m1 = f;
+        f = zc - zxm1; m2 = f;
+        f = zxp1 - zc; m3 = f;
+        f = Z(xx + 2, yy) - zxp1; m4 = f;
+        if (aki_almost_equal(m1, m2) && aki_almost_equal(m3, m4)) sx[q] = 0.5 * (m2 + m3);
+        else {
+            wx2 = fabs(m4 - m3);
+            wx3 = fabs(m2 - m1);
+            sx[q] = div_n(wx2 * m2 + wx3 * m3, wx2 + wx3);
+        }
+        f = Z(xx, yy - 1) - Z(xx, yy - 2); m1 = f;
+        f = zc - Z(xx, yy - 1); m2 = f;
+        f = Z(xx, yy + 1) - zc; m3 = f;
+        f = Z(xx, yy + 2) - Z(xx, yy + 1); m4 = f;
+        if (aki_almost_equal(m1, m2) && aki_almost_equal(m3, m4)) sy[q] = 0.5 * (m2 + m3);
+        else {
+            wy2 = fabs(m4 - m3);
+            wy3 = fabs(m2 - m1);
+            sy[q] = div_n(wy2 * m2 + wy3 * m3, wy2 + wy3);
+        }
+        double d22, d23, d42, d43;
+        f = zxm1 - Z(xx - 1, yy - 1); d22 = f;
+        f = Z(xx - 1, yy + 1) - zxm1; d23 = f;
+        f = zxp1 - Z(xx + 1, yy - 1); d42 = f;
+        f = Z(xx + 1, yy + 1) - zxp1; d43 = f;
+        const double e22 = m2 - d22, e23 = m3 - d23, e32 = d42 - m2, e33 = d43 - m3;
+        if (aki_almost_equal(wx2, 0.0) && aki_almost_equal(wx3, 0.0)) { wx2 = 1.; wx3 = 1.; }
+        if (aki_almost_equal(wy2, 0.0) && aki_almost_equal(wy3, 0.0)) { wy2 = 1.; wy3 = 1.; }
+        sxy[q] = div_n(wx2 * (wy2 * e22 + wy3 * e23) + wx3 * (wy2 * e32 + wy3 * e33), (wx2 + wx3) * (wy2 + wy3));
+    }
+    const double b1 = Z(i_x, i_y), b2 = Z(i_x + 1, i_y), b3 = Z(i_x + 1, i_y + 1), b4 = Z(i_x, i_y + 1);
+#undef Z
+    // sx(jj,ii): (1,1)->[0], (2,1)->[1], (1,2)->[2], (2,2)->[3]
+    const double b5 = sx[0], b6 = sx[1], b7 = sx[3], b8 = sx[2];
+    const double b9 = sy[0], b10 = sy[1], b11 = sy[3], b12 = sy[2];
+    const double b13 = sxy[0], b14 = sxy[1], b15 = sxy[3], b16 = sxy[2];
+    const double c1 = b1 - b2, c2 = b3 - b4, c3 = b5 + b6, c4 = b7 + b8, c5 = b9 - b10, c6 = b11 - b12, c7 = b13 + b14, c8 = b15 + b16;
+    const double c9 = 2 * b5 + b6, c10 = b7 + 2 * b8, c11 = 2 * b13 + b14, c12 = b15 + 2 * b16, c13 = b5 - b8, c14 = b1 - b4;
+    const double c15 = b13 + b16, c16 = 2 * b13 + b16, c17 = b9 + b12, c18 = 2 * b9 + b12;
+    const double d1 = c1 + c2, d2 = c3 - c4, d3 = c5 - c6, d4 = c7 + c8, d5 = c9 - c10, d6 = 2 * c5 - c6, d7 = 2 * c7 + c8;
+    const double d8 = c11 + c12, d9 = 2 * c11 + c12;
+    const double f1 = 2 * d1 + d2, f2 = 2 * d3 + d4, f3 = 2 * d6 + d7, f4 = 3 * d1 + d5, f5 = 3 * d3 + d8, f6 = 3 * d6 + d9;
+    const double v1 = 2 * f1 + f2, v2 = -(3 * f1 + f3), v3 = 2 * c5 + c7, v4 = 2 * c1 + c3;
+    const double v5 = -(2 * f4 + f5), v6 = 3 * f4 + f6, v7 = -(3 * c5 + c11), v8 = -(3 * c1 + c9);
+    const double v9 = 2 * c13 + c15, v10 = -(3 * c13 + c16), v11 = b13, v12 = b5;
+    const double v13 = 2 * c14 + c17, v14 = -(3 * c14 + c18), v15 = b9, v16 = b1;
+    const double x = f_x, y = f_y;
+    const double p1 = ((v1 * y + v2) * y + v3) * y + v4;
+    const double p2 = ((v5 * y + v6) * y + v7) * y + v8;
+    const double p3 = ((v9 * y + v10) * y + v11) * y + v12;
+    const double p4 = ((v13 * y + v14) * y + v15) * y + v16;
+    return (float)(((p1 * x + p2) * x + p3) * x + p4);
+}
+
 // topozeroMethods.f:200-220
 B2_HD float interp_nearest(const DemView &d, int i_x, int i_y, double f_x, double f_y)
 {

@@ -778,7 +778,7 @@ template <int METHOD>
 static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, const TopoLayers &out, TopoStats *stats,
                             unsigned grid, unsigned grid_solve, cudaStream_t s, cudaEvent_t ev_mid)
 {
-    constexpr bool kSplit = (METHOD == 5 || METHOD == 2 || METHOD == 0);
+    constexpr bool kSplit = (METHOD == 5 || METHOD == 2 || METHOD == 0 || METHOD == 4);
     if (kSplit) {
         if (C.ref.use_ref) {
             k_topo_solve<METHOD, true><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
@@ -796,7 +796,7 @@ static void launch_pixels_m(const TopoConst &C, const LineState *states, int lin
     }
 }
 
-int topo_pixel_launches(int method) { return (method == 5 || method == 2 || method == 0) ? 2 : 1; }
+int topo_pixel_launches(int method) { return (method == 5 || method == 2 || method == 0 || method == 4) ? 2 : 1; }
 
 // launches k_topo_solve + k_topo_final (2 kernels); out.ctrack must be allocated (it carries the SCH height between them)
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
@@ -810,6 +810,7 @@ int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, i
     case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 4: launch_pixels_m<4>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     case 5: launch_pixels_m<5>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     default: return -1;
     }
@@ -844,6 +845,7 @@ int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int
     case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
+    case 4: launch_mask_m<4>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
     default: return -1;
     }

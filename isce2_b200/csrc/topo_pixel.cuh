@@ -55,6 +55,7 @@ B2_HD float interp_dem(const TopoConst &C, int ix, int iy, double fx, double fy)
     if (METHOD == 1) return interp_bilinear(C.dem, ix, iy, fx, fy);
     if (METHOD == 2) return interp_bicubic(C.dem, ix, iy, fx, fy);
     if (METHOD == 3) return interp_nearest(C.dem, ix, iy, fx, fy);
+    if (METHOD == 4) return interp_akima(C.dem, ix, iy, fx, fy);
     return interp_biquintic(C.dem, C.spl, ix, iy, fx, fy);
 }
 

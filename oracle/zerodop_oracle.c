@@ -557,6 +557,78 @@ static float sinc_eval_2d_f(const float *dem, const float *intarr, int idec, int
     return acc;
 }
 
+
+/* ---- Akima: components/isceobj/Util/src/akima_reg.F:54-317 as called by intp_akima (topozeroMethods.f:222-247) ----
+ * Kept as written, including (a) the slopes being taken at (ix+1..ix+2, iy+1..iy+2) while the values are taken at
+ * (ix..ix+1, iy..iy+1) (getParDer :70-73 vs polyfitAkima :166-169) and (b) wx2/wx3/wy2/wy3 keeping their value from
+ * the previous grid point when the "equal slopes" branch is taken (:81-86, :95-100; the Fortran leaves them
+ * unassigned there -- they are initialised to 0 here, which the subsequent guard turns into 1). */
+static int aki_almost_equal(double x, double y) { return fabs(x - y) <= 2.220446049250313e-16; }
+static double akima_eval(const float *dem, int nx, int ny, int ix, int iy, double fx, double fy)
+{
+    double sx[2][2], sy[2][2], sxy[2][2]; /* [jj][ii] */
+    double wx2 = 0.0, wx3 = 0.0, wy2 = 0.0, wy3 = 0.0;
+    for (int ii = 1; ii <= 2; ii++) {
+        int yy = iy + ii; if (yy < 3) yy = 3; if (yy > ny - 2) yy = ny - 2;
+        for (int jj = 1; jj <= 2; jj++) {
+            int xx = ix + jj; if (xx < 3) xx = 3; if (xx > nx - 2) xx = nx - 2;
+            float f;
+            double m1, m2, m3, m4;
+            f = DEM(xx - 1, yy) - DEM(xx - 2, yy); m1 = f;
+            f = DEM(xx, yy) - DEM(xx - 1, yy); m2 = f;
+            f = DEM(xx + 1, yy) - DEM(xx, yy); m3 = f;
+            f = DEM(xx + 2, yy) - DEM(xx + 1, yy); m4 = f;
+            if (aki_almost_equal(m1, m2) && aki_almost_equal(m3, m4)) sx[jj - 1][ii - 1] = 0.5 * (m2 + m3);
+            else {
+                wx2 = fabs(m4 - m3);
+                wx3 = fabs(m2 - m1);
+                sx[jj - 1][ii - 1] = (wx2 * m2 + wx3 * m3) / (wx2 + wx3);
+            }
+            f = DEM(xx, yy - 1) - DEM(xx, yy - 2); m1 = f;
+            f = DEM(xx, yy) - DEM(xx, yy - 1); m2 = f;
+            f = DEM(xx, yy + 1) - DEM(xx, yy); m3 = f;
+            f = DEM(xx, yy + 2) - DEM(xx, yy + 1); m4 = f;
+            if (aki_almost_equal(m1, m2) && aki_almost_equal(m3, m4)) sy[jj - 1][ii - 1] = 0.5 * (m2 + m3);
+            else {
+                wy2 = fabs(m4 - m3);
+                wy3 = fabs(m2 - m1);
+                sy[jj - 1][ii - 1] = (wy2 * m2 + wy3 * m3) / (wy2 + wy3);
+            }
+            /* cross derivative: m2, m3 below are the Y slopes just computed (the Fortran reuses the variables) */
+            double d22, d23, d42, d43;
+            f = DEM(xx - 1, yy) - DEM(xx - 1, yy - 1); d22 = f;
+            f = DEM(xx - 1, yy + 1) - DEM(xx - 1, yy); d23 = f;
+            f = DEM(xx + 1, yy) - DEM(xx + 1, yy - 1); d42 = f;
+            f = DEM(xx + 1, yy + 1) - DEM(xx + 1, yy); d43 = f;
+            double e22 = m2 - d22, e23 = m3 - d23, e32 = d42 - m2, e33 = d43 - m3;
+            if (aki_almost_equal(wx2, 0.0) && aki_almost_equal(wx3, 0.0)) { wx2 = 1.; wx3 = 1.; }
+            if (aki_almost_equal(wy2, 0.0) && aki_almost_equal(wy3, 0.0)) { wy2 = 1.; wy3 = 1.; }
+            sxy[jj - 1][ii - 1] = (wx2 * (wy2 * e22 + wy3 * e23) + wx3 * (wy2 * e32 + wy3 * e33)) / ((wx2 + wx3) * (wy2 + wy3));
+        }
+    }
+    double poly[17] = {0};
+    double b1 = DEM(ix, iy), b2 = DEM(ix + 1, iy), b3 = DEM(ix + 1, iy + 1), b4 = DEM(ix, iy + 1);
+    double b5 = sx[0][0], b6 = sx[1][0], b7 = sx[1][1], b8 = sx[0][1];
+    double b9 = sy[0][0], b10 = sy[1][0], b11 = sy[1][1], b12 = sy[0][1];
+    double b13 = sxy[0][0], b14 = sxy[1][0], b15 = sxy[1][1], b16 = sxy[0][1];
+    poly[11] = b13; poly[12] = b5; poly[15] = b9; poly[16] = b1;
+    double c1 = b1 - b2, c2 = b3 - b4, c3 = b5 + b6, c4 = b7 + b8, c5 = b9 - b10, c6 = b11 - b12, c7 = b13 + b14, c8 = b15 + b16;
+    double c9 = 2 * b5 + b6, c10 = b7 + 2 * b8, c11 = 2 * b13 + b14, c12 = b15 + 2 * b16, c13 = b5 - b8, c14 = b1 - b4;
+    double c15 = b13 + b16, c16 = 2 * b13 + b16, c17 = b9 + b12, c18 = 2 * b9 + b12;
+    double d1 = c1 + c2, d2 = c3 - c4, d3 = c5 - c6, d4 = c7 + c8, d5 = c9 - c10, d6 = 2 * c5 - c6, d7 = 2 * c7 + c8;
+    double d8 = c11 + c12, d9 = 2 * c11 + c12;
+    double f1 = 2 * d1 + d2, f2 = 2 * d3 + d4, f3 = 2 * d6 + d7, f4 = 3 * d1 + d5, f5 = 3 * d3 + d8, f6 = 3 * d6 + d9;
+    poly[1] = 2 * f1 + f2; poly[2] = -(3 * f1 + f3); poly[3] = 2 * c5 + c7; poly[4] = 2 * c1 + c3;
+    poly[5] = -(2 * f4 + f5); poly[6] = 3 * f4 + f6; poly[7] = -(3 * c5 + c11); poly[8] = -(3 * c1 + c9);
+    poly[9] = 2 * c13 + c15; poly[10] = -(3 * c13 + c16); poly[13] = 2 * c14 + c17; poly[14] = -(3 * c14 + c18);
+    const double x = fx, y = fy; /* xx - ix, yy - iy */
+    double p1 = ((poly[1] * y + poly[2]) * y + poly[3]) * y + poly[4];
+    double p2 = ((poly[5] * y + poly[6]) * y + poly[7]) * y + poly[8];
+    double p3 = ((poly[9] * y + poly[10]) * y + poly[11]) * y + poly[12];
+    double p4 = ((poly[13] * y + poly[14]) * y + poly[15]) * y + poly[16];
+    return ((p1 * x + p2) * x + p3) * x + p4;
+}
+
 /* topozeroMethods.f:123-247 wrappers (window checks -> BADVALUE) */
 float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x, double f_y, int nx, int ny)
 {
@@ -584,8 +656,14 @@ float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x,
         if ((iy < 1) || (iy > ny)) return ORC_BADVALUE;
         return DEM(ix, iy);
     }
+    case ORC_AKIMA: { /* :222-247 */
+        if ((i_x < 1) || (i_x >= (nx - 1))) return ORC_BADVALUE;
+        if ((i_y < 1) || (i_y >= (ny - 1))) return ORC_BADVALUE;
+        /* polyvalAkima(i_x, i_y, dx, dy): x = dx - i_x, y = dy - i_y */
+        return (float)akima_eval(dem, nx, ny, i_x, i_y, dx - i_x, dy - i_y);
+    }
     default:
-        return NAN; /* AKIMA not restated yet */
+        return NAN;
     }
 }
 
@@ -686,7 +764,7 @@ int orc_topo(const orc_topo_params *p, const float *dem_full, const orc_orbit *o
 
     if (p->orbitmethod == ORC_LEGENDRE ? orb->nvec < 9 : orb->nvec < 4) return -2; /* :104-131 'stop' */
     if (method != ORC_BILINEAR && method != ORC_BICUBIC && method != ORC_BIQUINTIC && method != ORC_NEAREST &&
-        method != ORC_SINC)
+        method != ORC_SINC && method != ORC_AKIMA)
         return -3;
     if (method == ORC_SINC) sinc_table();
     if (!slrng && !rho_image) return -4;

@@ -72,6 +72,7 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
                 case 1: topo_pixel<1, true>(C, L, rng, dop, winc, R); break;
                 case 2: topo_pixel<2, true>(C, L, rng, dop, winc, R); break;
                 case 3: topo_pixel<3, true>(C, L, rng, dop, winc, R); break;
+                case 4: topo_pixel<4, true>(C, L, rng, dop, winc, R); break;
                 default: topo_pixel<5, true>(C, L, rng, dop, winc, R); break;
                 }
             } else {
@@ -80,6 +81,7 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
                 case 1: topo_pixel<1, false>(C, L, rng, dop, winc, R); break;
                 case 2: topo_pixel<2, false>(C, L, rng, dop, winc, R); break;
                 case 3: topo_pixel<3, false>(C, L, rng, dop, winc, R); break;
+                case 4: topo_pixel<4, false>(C, L, rng, dop, winc, R); break;
                 default: topo_pixel<5, false>(C, L, rng, dop, winc, R); break;
                 }
             }

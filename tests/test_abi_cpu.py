@@ -77,7 +77,7 @@ def test_argument_validation_precedes_device_use():
     with pytest.raises(_capi.B200Error) as ei:
         _capi.topo_run(p, sc.dem, sc.orbit_t[:5], sc.orbit_pos[:5], sc.orbit_vel[:5], sc.doppler_coeffs, [[sc.r0, sc.dr]])
     assert ei.value.code == -4 and "9 state vectors" in str(ei.value)
-    p.dem_method = 4  # AKIMA: declared by the reference, not on the GPU yet -> explicit error, never a silent fallback
+    p.dem_method = 7  # not one of the reference's six methods: "Undefined interpolation method." (topozero.f90:96-99)
     p.orbit_method = 0
     with pytest.raises(_capi.B200Error) as ei:
         _capi.topo_run(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]])

@@ -25,7 +25,7 @@ def _check(o, e):
         assert (o[k] != e[k]).mean() < 1e-4, k
 
 
-@pytest.mark.parametrize("name,mid", [("BILINEAR", 1), ("BICUBIC", 2), ("NEAREST", 3), ("BIQUINTIC", 5), ("SINC", 0)])
+@pytest.mark.parametrize("name,mid", [("BILINEAR", 1), ("BICUBIC", 2), ("NEAREST", 3), ("BIQUINTIC", 5), ("SINC", 0), ("AKIMA", 4)])
 def test_pixel_functions_bit_exact(name, mid):
     sc = pu.rough_scene(12, 2048, dem_spacing_arcsec=1.0)
     o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method=name, want_mask=False))

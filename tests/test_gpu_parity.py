@@ -74,7 +74,7 @@ def test_device_primitives_known_answers(golden):
     assert int(r[6]) == 1 and np.all(np.isfinite(r[:6]))
 
 
-@pytest.mark.parametrize("method", ["BILINEAR", "BIQUINTIC", "BICUBIC", "NEAREST", "SINC"])
+@pytest.mark.parametrize("method", ["BILINEAR", "BIQUINTIC", "BICUBIC", "NEAREST", "SINC", "AKIMA"])
 def test_topo_parity_rough_terrain(method):
     sc = pu.rough_scene(64, 6000)
     g = pu.gpu_topo(sc, dem_method=method)

@@ -209,7 +209,7 @@ def test_golden_rdr2geo_and_geo2rdr(golden):
     for e in golden["rdr2geo"]:
         h = e["height"]
         dem, flat, flon, dlat, dlon = _flat_dem(e["llh"][0], e["llh"][1], h)
-        for method in ("BILINEAR", "BICUBIC", "BIQUINTIC", "NEAREST", "SINC"):
+        for method in ("BILINEAR", "BICUBIC", "BIQUINTIC", "NEAREST", "SINC", "AKIMA"):
             out = orc.topo(dem=dem, first_lat=flat, first_lon=flon, delta_lat=dlat, delta_lon=dlon,
                            orbit_t=rows[:, 0], orbit_pos=rows[:, 1:4], orbit_vel=rows[:, 4:7], length=2, width=2,
                            r0=e["rng"], dr=1.0, prf=1000.0, t0=e["t"], wvl=0.056, side=e["side"],
