@@ -217,6 +217,7 @@ struct b200_topo_plan {
     DeviceOrbit orb;
     float *d_dem = nullptr;
     float *d_sinc = nullptr;
+    double *d_dem64 = nullptr;
     void *d_raw = nullptr;
     int *d_maxkey = nullptr;
     double *d_rho = nullptr;  // block rows of the slant-range image
@@ -241,6 +242,7 @@ struct b200_topo_plan {
         dfree(orb.buf);
         dfree(d_dem);
         dfree(d_sinc);
+        dfree(d_dem64);
         dfree(d_raw);
         dfree(d_maxkey);
         dfree(d_rho);
@@ -387,6 +389,11 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         // never move a point by more than the 0.15 deg margin
         C.ref.use_ref = (elat + 0.03 <= C.ref.lat.dmax && elon + 0.03 <= C.ref.lon.dmax) ? 1 : 0;
         if (getenv("B200_FORCE_LIBM_TRIG")) C.ref.use_ref = 0; // developer switch for A/B measurements
+        // narrow blocks (a Sentinel-1 swath, a NISAR frame) take the truncated series; 0.008 rad of slack covers
+        // the 0.15 deg DEM margin (0.0026 rad) and the bulge of the footprint past its corner box (~1e-4 rad)
+        C.ref.lat.narrow = (elat + 0.008 <= kNarrowAngle) ? 1 : 0;
+        C.ref.lon.narrow = (elon + 0.008 <= kNarrowAngle) ? 1 : 0;
+        if (getenv("B200_FORCE_LONG_SERIES")) C.ref.lat.narrow = C.ref.lon.narrow = 0;
     }
     const double MARGIN = 0.15; // topozeroState.f:74-75
     min_lon -= MARGIN; max_lon += MARGIN; min_lat -= MARGIN; max_lat += MARGIN;
@@ -449,7 +456,14 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         CK(cudaMemcpyAsync(pl->d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
     }
-    C.dem = DemView{pl->d_dem, udemwidth, udemlength, pl->d_sinc};
+    int stride64 = 0;
+    if (p.dem_method == B200_DEM_BIQUINTIC) { // padded double copy for the 6x6 spline window (DemView::d64)
+        stride64 = udemwidth + 1;
+        CK(dmalloc(&pl->d_dem64, sizeof(double) * (size_t)(udemlength + 1) * (size_t)stride64));
+        launch_dem_pad64(pl->d_dem, udemwidth, udemlength, pl->d_dem64, stride64, s);
+        pl->launches++;
+    }
+    C.dem = DemView{pl->d_dem, udemwidth, udemlength, pl->d_sinc, pl->d_dem64, stride64};
     C.rho_image = pl->d_rho ? pl->d_rho - (size_t)pl->line0 * (size_t)p.width : nullptr;
 
     // ---- per-line state ----

@@ -13,6 +13,10 @@ struct DemView {
     const float *data; // [ny][nx], lon fastest == Fortran dem(nx, ny)
     int nx, ny;
     const float *sinc; // fintp table [8192][8] of the SINC interpolator (topozeroMethods.f:57-61), else NULL
+    // BIQUINTIC on the device: the same samples widened to double (exact) with one replicated column and row
+    // appended, [ny + 1][stride64]: the 6x6 window needs neither index clamps nor 36 float->double conversions
+    const double *d64;
+    int stride64;
 };
 
 #ifdef __CUDA_ARCH__
@@ -316,8 +320,24 @@ B2_HD float interp_biquintic(const DemView &d, const Spline6Table &T, int i_x, i
     double wx[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) wx[j] = b2_fma(b2_fma(b2_fma(T.c[3][j], f_x, T.c[2][j]), f_x, T.c[1][j]), f_x, T.c[0][j]);
-    const int x5 = (i_x + 4 > d.nx) ? d.nx : i_x + 4;
     double acc = 0.0;
+#ifdef __CUDA_ARCH__
+    // padded double copy: the replicated last column / row is what the clamp would have selected
+    const double *row = d.d64 + (size_t)(i_y - 2) * (size_t)d.stride64 + (size_t)(i_x - 2);
+#pragma unroll
+    for (int J = 0; J < 6; J++, row += d.stride64) {
+        double hc = wx[0] * __ldg(row);
+        hc = b2_fma(wx[1], __ldg(row + 1), hc);
+        hc = b2_fma(wx[2], __ldg(row + 2), hc);
+        hc = b2_fma(wx[3], __ldg(row + 3), hc);
+        hc = b2_fma(wx[4], __ldg(row + 4), hc);
+        hc = b2_fma(wx[5], __ldg(row + 5), hc);
+        double wy = b2_fma(b2_fma(b2_fma(T.c[3][J], f_y, T.c[2][J]), f_y, T.c[1][J]), f_y, T.c[0][J]);
+        acc = b2_fma(wy, hc, acc);
+    }
+    return (float)acc;
+#else
+    const int x5 = (i_x + 4 > d.nx) ? d.nx : i_x + 4;
 #pragma unroll
     for (int J = 0; J < 6; J++) { // latitude rows: six consecutive longitudes per row (one or two 32-byte sectors)
         int iy = i_y - 1 + J;
@@ -333,6 +353,7 @@ B2_HD float interp_biquintic(const DemView &d, const Spline6Table &T, int i_x, i
         acc = b2_fma(wy, hc, acc);
     }
     return (float)acc;
+#endif
 }
 
 } // namespace b2

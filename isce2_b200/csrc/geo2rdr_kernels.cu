@@ -251,7 +251,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
         for (int k = 1; k <= 51; k++) {
             n_it++;
             const Vec3 dr = sub(xyz, S.x);
-            rngpix = sqrt_n(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+            rngpix = sqrt_p(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
             const double dopfact = dot(dr, S.v);
             const double fdop = 0.5 * C.wvl * poly1d_fast(C.fd, inv_fd, rngpix);
             const double fdopder = 0.5 * C.wvl * poly1d_fast(C.fdd, inv_fdd, rngpix);
@@ -278,7 +278,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
             else if (tline > C.tend) outside = true;
             else {
                 const Vec3 dr = sub(xyz, S.x);
-                rngpix = sqrt_n(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+                rngpix = sqrt_p(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
                 if (rngpix < C.rngstart) outside = true;
                 else if (rngpix > C.rngend) outside = true;
                 else if (C.bistatic) { // :331-368
@@ -289,7 +289,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
                     else {
                         poly_state<METHOD>(op, tline, S);
                         const Vec3 d2 = sub(xyz, S.x);
-                        rngpix = sqrt_n(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z);
+                        rngpix = sqrt_p(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z);
                         if (rngpix < C.rngstart) outside = true;
                         else if (rngpix > C.rngend) outside = true;
                     }

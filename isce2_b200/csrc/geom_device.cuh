@@ -124,6 +124,28 @@ B2_HD double sqrt_n(double x, double *rs = nullptr)
 #endif
 }
 
+// same for an argument known to be a positive normal number (no zero guard: three instructions less)
+B2_HD double sqrt_p(double x, double *rs = nullptr)
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    double d = __fma_rn(-g, g, x);
+    g = __fma_rn(d, h, g);
+    if (rs) *rs = h + h;
+    return g;
+#else
+    return sqrt_n(x, rs);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Trigonometry about a reference angle.
 //
@@ -140,7 +162,43 @@ struct RefAngle {
     double a0;             // exact multiple of 2^-6 rad
     double sh, sl, ch, cl; // sin(a0) = sh + sl, cos(a0) = ch + cl
     double dmax;           // largest |angle - a0| the series below are good for
+    int narrow;            // 1: every angle of the block is within kNarrowAngle of a0 -> the short series suffice
 };
+
+// Series coefficients live in constant memory so that the FP64 instructions read them as c[bank][offset] operands
+// (as literals the compiler rebuilds each one with two UMOVs per use).
+#define B2_ATAN_COEF {-1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0, -1.0 / 15.0, 1.0 / 17.0, \
+                      -1.0 / 19.0, 1.0 / 21.0, -1.0 / 23.0}
+#define B2_SIN_COEF {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0}
+#define B2_COS_COEF {-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, \
+                     -1.0 / 87178291200.0}
+#define B2_CUBE_COEF {1.0 / 9.0, -4.0 / 243.0, 28.0 / 6561.0, -80.0 / 59049.0, 2288.0 / 4782969.0, \
+                      -23296.0 / 129140163.0, 82688.0 / 1162261467.0}
+#ifdef __CUDACC__
+__device__ __constant__ static double kAtanCoefDev[11] = B2_ATAN_COEF;
+__device__ __constant__ static double kSinCoefDev[6] = B2_SIN_COEF;
+__device__ __constant__ static double kCosCoefDev[7] = B2_COS_COEF;
+__device__ __constant__ static double kCubeCoefDev[7] = B2_CUBE_COEF;
+#endif
+static const double kAtanCoefHost[11] = B2_ATAN_COEF;
+static const double kSinCoefHost[6] = B2_SIN_COEF;
+static const double kCosCoefHost[7] = B2_COS_COEF;
+static const double kCubeCoefHost[7] = B2_CUBE_COEF;
+#ifdef __CUDA_ARCH__
+#define B2_ATAN_C(i) kAtanCoefDev[i]
+#define B2_SIN_C(i) kSinCoefDev[i]
+#define B2_COS_C(i) kCosCoefDev[i]
+#define B2_CUBE_C(i) kCubeCoefDev[i]
+#else
+#define B2_ATAN_C(i) kAtanCoefHost[i]
+#define B2_SIN_C(i) kSinCoefHost[i]
+#define B2_COS_C(i) kCosCoefHost[i]
+#define B2_CUBE_C(i) kCubeCoefHost[i]
+#endif
+
+// |angle - a0| below which the truncated series are used: the first dropped terms, t^13/13 = 2.4e-19,
+// d^11/11! = 3.9e-23 and d^10/10! = 9.4e-21, are below 0.3 % of an ulp of the results (ulp(0.5) = 1.1e-16)
+constexpr double kNarrowAngle = 0.045;
 
 // host only: extended-precision constants of a reference angle near `approx`
 inline RefAngle make_ref_angle(double approx)
@@ -153,6 +211,7 @@ inline RefAngle make_ref_angle(double approx)
     R.ch = (double)c;
     R.cl = (double)(c - (long double)R.ch);
     R.dmax = 0.12;
+    R.narrow = 0;
     return R;
 }
 
@@ -166,18 +225,21 @@ B2_HD double atan2_ref(const RefAngle &R, double y, double x)
     double D = b2_fma(x, R.ch, y * R.sh);
     double t = N * rcp_n(D);
     double t2 = t * t;
-    // odd Taylor series of atan through t^23 (|t| <= 0.12: remainder < 4e-25)
-    double pol = -1.0 / 23.0;
-    pol = b2_fma(pol, t2, 1.0 / 21.0);
-    pol = b2_fma(pol, t2, -1.0 / 19.0);
-    pol = b2_fma(pol, t2, 1.0 / 17.0);
-    pol = b2_fma(pol, t2, -1.0 / 15.0);
-    pol = b2_fma(pol, t2, 1.0 / 13.0);
-    pol = b2_fma(pol, t2, -1.0 / 11.0);
-    pol = b2_fma(pol, t2, 1.0 / 9.0);
-    pol = b2_fma(pol, t2, -1.0 / 7.0);
-    pol = b2_fma(pol, t2, 1.0 / 5.0);
-    pol = b2_fma(pol, t2, -1.0 / 3.0);
+    // odd Taylor series of atan through t^23 (|t| <= 0.12: remainder < 4e-25), through t^11 on narrow blocks
+    double pol = B2_ATAN_C(4);
+    if (!R.narrow) {
+        pol = B2_ATAN_C(10);
+        pol = b2_fma(pol, t2, B2_ATAN_C(9));
+        pol = b2_fma(pol, t2, B2_ATAN_C(8));
+        pol = b2_fma(pol, t2, B2_ATAN_C(7));
+        pol = b2_fma(pol, t2, B2_ATAN_C(6));
+        pol = b2_fma(pol, t2, B2_ATAN_C(5));
+        pol = b2_fma(pol, t2, B2_ATAN_C(4));
+    }
+    pol = b2_fma(pol, t2, B2_ATAN_C(3));
+    pol = b2_fma(pol, t2, B2_ATAN_C(2));
+    pol = b2_fma(pol, t2, B2_ATAN_C(1));
+    pol = b2_fma(pol, t2, B2_ATAN_C(0));
     double at = b2_fma(t * t2, pol, t); // t + t^3 * pol
     return R.a0 + at;
 }
@@ -188,20 +250,24 @@ B2_HD void sincos_ref(const RefAngle &R, double theta, double &sn, double &cs)
     double d = theta - R.a0; // exact: both are within a factor two of each other or d is tiny
     double d2 = d * d;
     // S = sin d = d + d^3 * ps ; Cm = 1 - cos d = d^2 * pc   (|d| <= 0.12: remainders < 1e-24)
-    double ps = 1.0 / 6227020800.0;                 // 1/13!
-    ps = b2_fma(ps, d2, -1.0 / 39916800.0);         // -1/11!
-    ps = b2_fma(ps, d2, 1.0 / 362880.0);            // 1/9!
-    ps = b2_fma(ps, d2, -1.0 / 5040.0);             // -1/7!
-    ps = b2_fma(ps, d2, 1.0 / 120.0);               // 1/5!
-    ps = b2_fma(ps, d2, -1.0 / 6.0);                // -1/3!
+    // (narrow blocks: through d^9 and d^8)
+    double ps = B2_SIN_C(3), pc = B2_COS_C(3);      // 1/9!, 1/8!
+    if (!R.narrow) {
+        ps = B2_SIN_C(5);                           // 1/13!
+        ps = b2_fma(ps, d2, B2_SIN_C(4));           // -1/11!
+        ps = b2_fma(ps, d2, B2_SIN_C(3));           // 1/9!
+        pc = B2_COS_C(6);                           // -1/14!
+        pc = b2_fma(pc, d2, B2_COS_C(5));           // 1/12!
+        pc = b2_fma(pc, d2, B2_COS_C(4));           // -1/10!
+        pc = b2_fma(pc, d2, B2_COS_C(3));           // 1/8!
+    }
+    ps = b2_fma(ps, d2, B2_SIN_C(2));               // -1/7!
+    ps = b2_fma(ps, d2, B2_SIN_C(1));               // 1/5!
+    ps = b2_fma(ps, d2, B2_SIN_C(0));               // -1/3!
     double S = b2_fma(d * d2, ps, d);
-    double pc = -1.0 / 87178291200.0;               // -1/14!
-    pc = b2_fma(pc, d2, 1.0 / 479001600.0);         // 1/12!
-    pc = b2_fma(pc, d2, -1.0 / 3628800.0);          // -1/10!
-    pc = b2_fma(pc, d2, 1.0 / 40320.0);             // 1/8!
-    pc = b2_fma(pc, d2, -1.0 / 720.0);              // -1/6!
-    pc = b2_fma(pc, d2, 1.0 / 24.0);                // 1/4!
-    pc = b2_fma(pc, d2, -0.5);                      // -1/2!
+    pc = b2_fma(pc, d2, B2_COS_C(2));               // -1/6!
+    pc = b2_fma(pc, d2, B2_COS_C(1));               // 1/4!
+    pc = b2_fma(pc, d2, B2_COS_C(0));               // -1/2!
     double Cm = -(d2 * pc);                         // 1 - cos d  (>= 0)
     // sin(a0 + d) = s0 + [c0*S - s0*Cm],  cos(a0 + d) = c0 - [s0*S + c0*Cm]; low words of s0, c0 folded in
     sn = R.sh + (b2_fma(R.ch, S, -(R.sh * Cm)) + b2_fma(R.cl, S, R.sl));
@@ -236,7 +302,7 @@ B2_HD Ellipsoid make_ellipsoid(double a, double e2)
 // latlon.F:44-49 (LLH_2_XYZ) from the sines / cosines of the angles
 B2_HD Vec3 llh_to_xyz_sc(const Ellipsoid &e, double sl, double cl, double so, double co, double h)
 {
-    double re = div_n(e.a, sqrt_n(1.0 - e.e2 * (sl * sl)));
+    double re = div_n(e.a, sqrt_p(1.0 - e.e2 * (sl * sl)));
     Vec3 v;
     v.x = (re + h) * cl * co;
     v.y = (re + h) * cl * so;
@@ -282,23 +348,23 @@ B2_HD void xyz_to_llh_core(const Ellipsoid &e, const Vec3 &v, double &k, double 
     double s = div_n(e.e4 * p * q, 4.0 * (r * r * r));
     double u;
     if (s < 4.0e-3) {
-        double ee = 82688.0 / 1162261467.0;
-        ee = b2_fma(ee, s, -23296.0 / 129140163.0);
-        ee = b2_fma(ee, s, 2288.0 / 4782969.0);
-        ee = b2_fma(ee, s, -80.0 / 59049.0);
-        ee = b2_fma(ee, s, 28.0 / 6561.0);
-        ee = b2_fma(ee, s, -4.0 / 243.0);
-        ee = b2_fma(ee, s, 1.0 / 9.0);
+        double ee = B2_CUBE_C(6);
+        ee = b2_fma(ee, s, B2_CUBE_C(5));
+        ee = b2_fma(ee, s, B2_CUBE_C(4));
+        ee = b2_fma(ee, s, B2_CUBE_C(3));
+        ee = b2_fma(ee, s, B2_CUBE_C(2));
+        ee = b2_fma(ee, s, B2_CUBE_C(1));
+        ee = b2_fma(ee, s, B2_CUBE_C(0));
         ee = ee * s;
         u = r * b2_fma(2.0, ee, 3.0);
     } else {
         double t = B2_CBRT(1.0 + s + sqrt(s * (2.0 + s)));
         u = r * (1.0 + t + 1.0 / t);
     }
-    double rv = sqrt_n(u * u + e.e4 * q);
+    double rv = sqrt_p(u * u + e.e4 * q);
     double w = div_n(e.e2 * (u + rv - q), 2.0 * rv);
-    k = sqrt_n(u + rv + w * w) - w;
-    d = div_n(k * sqrt_n(q2), k + e.e2);
+    k = sqrt_p(u + rv + w * w) - w;
+    d = div_n(k * sqrt_p(q2), k + e.e2);
 }
 
 // lat, lon (rad) and height; generic libm arctangent
@@ -423,9 +489,9 @@ B2_HD double sch_height(const LineState &L, const Vec3 &xyz)
     // e2 = 0: s = 0, t = 1, u = r * (1 + 1 + 1/1), rv = sqrt(u*u) == u (exact for u > 0), w = 0, k = sqrt(u + rv)
     double u = r * 3.0;
     double rk;
-    double k = sqrt_n(u + u, &rk);
-    double d = div_r(k * sqrt_n(q2), k, rk);
-    return div_r((k - 1.0) * sqrt_n(d * d + sz * sz), k, rk);
+    double k = sqrt_p(u + u, &rk);
+    double d = div_r(k * sqrt_p(q2), k, rk);
+    return div_r((k - 1.0) * sqrt_p(d * d + sz * sz), k, rk);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -137,6 +137,18 @@ __global__ void k_dem_prepare(const void *raw, int dtype, float *dem, size_t n, 
     if ((threadIdx.x & 31) == 0) atomic_max_float((float *)maxkey, m);
 }
 
+// padded double copy of the crop for the biquintic window (DemView::d64): out[r][c] = dem[min(r, ny-1)][min(c, nx-1)]
+__global__ void k_dem_pad64(const float *dem, int nx, int ny, double *out, int stride)
+{
+    const size_t n = (size_t)(ny + 1) * (size_t)stride;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / (size_t)stride), c = (int)(i - (size_t)r * (size_t)stride);
+        r = r < ny ? r : ny - 1;
+        c = c < nx ? c : nx - 1;
+        out[i] = (double)dem[(size_t)r * (size_t)nx + (size_t)c];
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // per-line state
 // -------------------------------------------------------------------------------------------------
@@ -767,6 +779,14 @@ void launch_dem_prepare(const void *raw, int dtype, float *dem, size_t n, int *m
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     k_dem_prepare<<<blocks, 256, 0, s>>>(raw, dtype, dem, n, maxkey);
+}
+
+void launch_dem_pad64(const float *dem, int nx, int ny, double *out, int stride, cudaStream_t s)
+{
+    const size_t n = (size_t)(ny + 1) * (size_t)stride;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    k_dem_pad64<<<blocks, 256, 0, s>>>(dem, nx, ny, out, stride);
 }
 
 void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int nlines, LineState *states, cudaStream_t s)

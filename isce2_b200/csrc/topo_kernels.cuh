@@ -40,6 +40,7 @@ float dem_max_decode(int key);
 
 void launch_topo_bbox(const TopoConst &C, const OrbitView &orb, double *d_out, cudaStream_t s);
 void launch_dem_prepare(const void *raw, int dtype, float *dem, size_t n, int *maxkey, cudaStream_t s);
+void launch_dem_pad64(const float *dem, int nx, int ny, double *out, int stride, cudaStream_t s);
 void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int nlines, LineState *states, cudaStream_t s);
 // ev_mid (optional) is recorded between the solve and the final kernel when they are separate launches
 int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,

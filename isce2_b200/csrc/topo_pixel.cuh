@@ -113,7 +113,7 @@ B2_HD void range_sphere(const TopoConst &C, const LineState &L, const PixelConst
 B2_HD float range_distance(const LineState &L, const Vec3 &xyz, double rng)
 {
     double dx = xyz.x - L.sat.x, dy = xyz.y - L.sat.y, dz = xyz.z - L.sat.z;
-    return (float)(sqrt_n(dx * dx + dy * dy + dz * dz) - rng);
+    return (float)(sqrt_p(dx * dx + dy * dy + dz * dz) - rng);
 }
 
 template <bool REF>
@@ -237,7 +237,7 @@ B2_HD void topo_final(const TopoConst &C, const LineState &L, double rng, double
     Vec3 e_north = Vec3{-slt * clo, -slt * slo, clt};
     Vec3 e_up = Vec3{clt * clo, clt * slo, slt};
     Vec3 enu = Vec3{dot(e_east, delta), dot(e_north, delta), dot(e_up, delta)};
-    double en = sqrt_n(enu.x * enu.x + enu.y * enu.y + enu.z * enu.z);
+    double en = sqrt_p(enu.x * enu.x + enu.y * enu.y + enu.z * enu.z);
     double cosalpha = div_n(fabs(enu.z), en);
     R.los0 = (float)(acos(cosalpha) * r2d);
     R.los1 = (float)((atan2(-enu.y, -enu.x) - 0.5 * C.pi) * r2d);
@@ -274,17 +274,17 @@ B2_HD void topo_final(const TopoConst &C, const LineState &L, double rng, double
         enu.x = div_n(enu.x, en);
         enu.y = div_n(enu.y, en);
         enu.z = div_n(enu.z, en);
-        double cinc = div_n(enu.x * alpha + enu.y * beta - enu.z, sqrt_n(1.0 + alpha * alpha + beta * beta));
+        double cinc = div_n(enu.x * alpha + enu.y * beta - enu.z, sqrt_p(1.0 + alpha * alpha + beta * beta));
         R.inc1 = (float)(acos(cinc) * r2d);
         // psi: angle between the image plane normal and the local slope normal (:694-700)
         Vec3 n_img = cross(delta, L.vel);
-        double nn = sqrt_n(n_img.x * n_img.x + n_img.y * n_img.y + n_img.z * n_img.z);
+        double nn = sqrt_p(n_img.x * n_img.x + n_img.y * n_img.y + n_img.z * n_img.z);
         if (nn != 0) n_img = Vec3{div_n(n_img.x, nn), div_n(n_img.y, nn), div_n(n_img.z, nn)};
         Vec3 tmp = Vec3{-C.ilrl * n_img.x, -C.ilrl * n_img.y, -C.ilrl * n_img.z};
         Vec3 n_img_enu = Vec3{dot(e_east, tmp), dot(e_north, tmp), dot(e_up, tmp)};
         Vec3 n_trg = Vec3{-alpha, -beta, 1.0};
-        double n1 = sqrt_n(n_trg.x * n_trg.x + n_trg.y * n_trg.y + n_trg.z * n_trg.z);
-        double n2 = sqrt_n(n_img_enu.x * n_img_enu.x + n_img_enu.y * n_img_enu.y + n_img_enu.z * n_img_enu.z);
+        double n1 = sqrt_p(n_trg.x * n_trg.x + n_trg.y * n_trg.y + n_trg.z * n_trg.z);
+        double n2 = sqrt_p(n_img_enu.x * n_img_enu.x + n_img_enu.y * n_img_enu.y + n_img_enu.z * n_img_enu.z);
         double cospsi = div_n(dot(n_trg, n_img_enu), n1 * n2);
         R.inc0 = (float)(acos(cospsi) * r2d);
     }
@@ -316,7 +316,7 @@ B2_HD double mask_resample(const TopoConst &C, const LineState &L, const double 
     double hh = interp_dem<METHOD>(C, idemlon, idemlat, fraclon, fraclat);
     Vec3 xyz = geodetic_to_xyz<REF>(C, (double)demlat, (double)demlon, hh);
     xyz = sub(xyz, L.sat);
-    return sqrt_n(xyz.x * xyz.x + xyz.y * xyz.y + xyz.z * xyz.z);
+    return sqrt_p(xyz.x * xyz.x + xyz.y * xyz.y + xyz.z * xyz.z);
 }
 
 } // namespace b2

@@ -51,6 +51,7 @@ int emu_topo(const EmuTopoArgs *A, const float *dem, const double *ot, const dou
         C.ref.lat = make_ref_angle((C.ufirstlat + 0.5 * C.deltalat * A->ny) * d2r);
         C.ref.lon = make_ref_angle((C.ufirstlon + 0.5 * C.deltalon * A->nx) * d2r);
         C.ref.use_ref = A->use_ref;
+        C.ref.lat.narrow = C.ref.lon.narrow = (A->use_ref == 2) ? 1 : 0; // 2: truncated series of narrow blocks
     }
     OrbitView orb{A->n_orbit, ot, opos, ovel};
     long long it = 0;

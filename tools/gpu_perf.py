@@ -31,8 +31,8 @@ def perf(lines=1500, width=25000, reps=3, rough=False):
             e = C.create_string_buffer(512)
             _capi._check(_capi.lib().b200_topo_plan_fetch(tp.handle, None, C.byref(res), e, 512), e)
             if best is None or res.ms_pixels < best[0]:
-                best = (res.ms_pixels, res.ms_mask, res.iterations / float(lines * width))
-        out[method] = dict(ms_pixels=round(best[0], 3), ms_mask=round(best[1], 3), K=round(best[2], 3),
+                best = (res.ms_pixels, res.ms_mask, res.iterations / float(lines * width), res.ms_solve)
+        out[method] = dict(ms_pixels=round(best[0], 3), ms_solve=round(best[3], 3), ms_mask=round(best[1], 3), K=round(best[2], 3),
                            gpix_s=round(lines * width / best[0] / 1e6, 3))
         if method == "BILINEAR":
             gp = _capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0 - 1.7, dr=sc.dr,
