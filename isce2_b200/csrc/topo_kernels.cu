@@ -189,20 +189,43 @@ __device__ __forceinline__ void load_line_state(LineState &sL, const LineState *
 //
 // Pixels converge after different numbers of iterations (3..10 on ordinary terrain, 36 in layover), so a fixed
 // one-thread-per-pixel mapping leaves a quarter of the lanes idle (ncu: 24.5 of 32 active).  Instead each warp owns a
-// strip of kStrip consecutive pixels of one line and its lanes pull the next unsolved pixel of the strip as soon as
-// their current one converges (ballot + prefix popcount; no atomics, no shared counters).  The strip's slant ranges
-// and Doppler values are evaluated up front into shared memory so that a refill costs a few instructions.
-constexpr int kStrip = 128;                                  // pixels per warp
+// run of consecutive pixels of one line and its lanes pull the next unsolved pixel of the run as soon as their
+// current one converges (ballot + prefix popcount; no atomics, no shared counters).  The slant ranges and Doppler
+// values of the upcoming pixels are evaluated ahead into shared memory so that a refill costs a few instructions:
+//   * k_topo_fused: the run is a strip of kStrip pixels staged up front (the final pass needs them again);
+//   * k_topo_solve: the run is a segment of up to kSegMax pixels streamed through a ring of kRing entries, which
+//     makes the idle tail at the end of a run (lanes waiting for the last pixels) 8x rarer than with 128-pixel strips.
+constexpr int kStrip = 128;                                    // pixels per warp (fused kernel)
 constexpr int kSolvePixelsPerCta = (kTopoBlock / 32) * kStrip; // 512
+constexpr int kRing = 128;                                     // staged look-ahead per warp (split solve kernel)
+constexpr int kStage = 64;                                     // pixels staged per refill of the ring
+constexpr int kSegMax = 1024;                                  // longest run of pixels per warp
 
-// Solve the strip_n pixels of one warp's strip (slant ranges / Doppler values in rng_s / dop_s): lanes pull the next
-// unsolved pixel as soon as their current one converges.  zrow[j] receives the SCH height of strip pixel j.
-template <int METHOD, bool REF>
-__device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState &sL, const double *rng_s, const double *dop_s,
-                                            int strip_n, double *zrow, int &conv, int &iters)
+template <bool STREAM>
+__device__ __forceinline__ void stage_pixels(const TopoConst &C, int line, int pix0, int from, int to, double *rng_s, double *dop_s)
+{
+    for (int j = from + (threadIdx.x & 31); j < to; j += 32) {
+        const int k = STREAM ? (j & (kRing - 1)) : j;
+        rng_s[k] = pixel_range(C, line, pix0 + j);
+        dop_s[k] = eval_poly2d(C.dop, (double)line, (double)(pix0 + j));
+    }
+}
+
+// Solve the strip_n pixels pix0 .. of one warp's run: lanes pull the next unsolved pixel as soon as their current one
+// converges.  zrow[j] receives the SCH height of run pixel j.  STREAM: rng_s / dop_s are rings (see above) that this
+// function keeps filled; otherwise the caller staged the whole run.
+template <int METHOD, bool REF, bool STREAM>
+__device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState &sL, int line, int pix0, double *rng_s,
+                                            double *dop_s, int strip_n, double *zrow, int &conv, int &iters)
 {
     const int lane = threadIdx.x & 31;
     const int nprimary = C.numiter + 1 < C.numiter + C.extraiter + 1 ? C.numiter + 1 : C.numiter + C.extraiter + 1;
+    int staged = strip_n;
+    if (STREAM) {
+        staged = strip_n < kRing ? strip_n : kRing;
+        stage_pixels<true>(C, line, pix0, 0, staged, rng_s, dop_s);
+        __syncwarp();
+    }
     PixelConst P;
     double lat = 0.0, lon = 0.0, z = 0.0, zsch = 0.0;
     int it = 0, slot = lane, next = 32;
@@ -246,15 +269,16 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
             }
             if (finished) zrow[slot] = zsch;
         }
-        // lanes without work take the next pixels of the strip, in lane order
+        // lanes without work take the next pixels of the run, in lane order
         const bool need = !active || finished;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (need) {
             const int j = next + __popc(m & ((1u << lane) - 1u));
             active = j < strip_n;
             if (active) {
+                const int k = STREAM ? (j & (kRing - 1)) : j;
                 slot = j;
-                P = make_pixel_const(C, sL, rng_s[j], dop_s[j]);
+                P = make_pixel_const(C, sL, rng_s[k], dop_s[k]);
                 lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny;
                 lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
                 z = 0.0;
@@ -263,34 +287,51 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
             }
         }
         next += __popc(m);
+        if (STREAM) {
+            // keep 32 staged pixels ahead of `next`: entries below `next` are consumed, so the kStage new ones may
+            // overwrite the ring positions of pixels [staged - kRing, staged - kRing + kStage)
+            if (staged < strip_n && next + 32 > staged) {
+                const int to = staged + kStage < strip_n ? staged + kStage : strip_n;
+                __syncwarp();
+                stage_pixels<true>(C, line, pix0, staged, to, rng_s, dop_s);
+                staged = to;
+                __syncwarp();
+            }
+        }
     }
 }
 
+// One warp per segment: a line is cut into segs_per_line equal runs of at most kSegMax pixels; warps are numbered
+// across lines, so a CTA's four warps may sit on different lines and each keeps its own line state.
+__host__ __device__ inline int solve_segs_per_line(int width) { return (width + kSegMax - 1) / kSegMax; }
+
 template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
-k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, double *__restrict__ zsch_out,
-             TopoStats *stats)
+k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines,
+             double *__restrict__ zsch_out, TopoStats *stats)
 {
-    __shared__ LineState sL;
-    __shared__ double s_rng[kTopoBlock / 32][kStrip];
-    __shared__ double s_dop[kTopoBlock / 32][kStrip];
-    const int bpl = (C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta; // CTAs per azimuth line
-    const int row = blockIdx.x / bpl;                                         // row within the block of lines
-    const int seg = blockIdx.x - row * bpl;
+    __shared__ LineState sL[kTopoBlock / 32];
+    __shared__ double s_rng[kTopoBlock / 32][kRing];
+    __shared__ double s_dop[kTopoBlock / 32][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int line = line0 + row;
-    const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
-    const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip; // may be <= 0
-    load_line_state(sL, states, row);
-    for (int j = lane; j < strip_n; j += 32) {
-        s_rng[warp][j] = pixel_range(C, line, strip0 + j);
-        s_dop[warp][j] = eval_poly2d(C.dop, (double)line, (double)(strip0 + j));
+    const int spl = solve_segs_per_line(C.width);
+    const int seg_len = (C.width + spl - 1) / spl;
+    const long long gw = (long long)blockIdx.x * (kTopoBlock / 32) + warp;
+    const int row = (int)(gw / spl);
+    if (row >= nlines) return;
+    const int seg = (int)(gw - (long long)row * spl);
+    const int pix0 = seg * seg_len;
+    const int seg_n = (C.width - pix0) < seg_len ? (C.width - pix0) : seg_len;
+    {
+        const double *src = reinterpret_cast<const double *>(states + row);
+        double *dst = reinterpret_cast<double *>(&sL[warp]);
+        for (int i = lane; i < (int)(sizeof(LineState) / sizeof(double)); i += 32) dst[i] = src[i];
     }
-    __syncthreads();
-    double *zrow = zsch_out + (size_t)row * (size_t)C.width + (size_t)strip0;
+    __syncwarp();
+    double *zrow = zsch_out + (size_t)row * (size_t)C.width + (size_t)pix0;
     int conv = 0, iters = 0;
-    solve_strip<METHOD, REF>(C, sL, s_rng[warp], s_dop[warp], strip_n, zrow, conv, iters);
-    // convergence statistics (:570): warps leave as they finish, no block-wide barrier
+    solve_strip<METHOD, REF, true>(C, sL[warp], line0 + row, pix0, s_rng[warp], s_dop[warp], seg_n, zrow, conv, iters);
+    // convergence statistics (:570)
     conv = warp_sum(conv);
     iters = warp_sum(iters);
     if (lane == 0 && iters) {
@@ -366,13 +407,10 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
     const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
     const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip;
     load_line_state(sL, states, row);
-    for (int j = lane; j < strip_n; j += 32) {
-        s_rng[warp][j] = pixel_range(C, line, strip0 + j);
-        s_dop[warp][j] = eval_poly2d(C.dop, (double)line, (double)(strip0 + j));
-    }
+    stage_pixels<false>(C, line, strip0, 0, strip_n, s_rng[warp], s_dop[warp]);
     __syncthreads();
     int conv = 0, iters = 0;
-    solve_strip<METHOD, REF>(C, sL, s_rng[warp], s_dop[warp], strip_n, s_z[warp], conv, iters);
+    solve_strip<METHOD, REF, false>(C, sL, line, strip0, s_rng[warp], s_dop[warp], strip_n, s_z[warp], conv, iters);
     __syncwarp();
     // final pass over the strip, consecutive lanes on consecutive pixels (coalesced layer stores)
     double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
@@ -795,17 +833,20 @@ void launch_line_setup(const TopoConst &C, const OrbitView &orb, int line0, int 
 }
 
 template <int METHOD>
-static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, const TopoLayers &out, TopoStats *stats,
-                            unsigned grid, unsigned grid_solve, cudaStream_t s, cudaEvent_t ev_mid)
+static void launch_pixels_m(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
+                            TopoStats *stats, unsigned grid, unsigned grid_solve, cudaStream_t s, cudaEvent_t ev_mid)
 {
     constexpr bool kSplit = (METHOD == 5 || METHOD == 2 || METHOD == 0 || METHOD == 4);
     if (kSplit) {
+        // one warp per segment of a line (see k_topo_solve)
+        const long long nwarps = (long long)solve_segs_per_line(C.width) * nlines;
+        grid_solve = (unsigned)((nwarps + kTopoBlock / 32 - 1) / (kTopoBlock / 32));
         if (C.ref.use_ref) {
-            k_topo_solve<METHOD, true><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
+            k_topo_solve<METHOD, true><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, nlines, out.ctrack, stats);
             if (ev_mid) cudaEventRecord(ev_mid, s);
             k_topo_final<METHOD, true><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         } else {
-            k_topo_solve<METHOD, false><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, out.ctrack, stats);
+            k_topo_solve<METHOD, false><<<grid_solve, kTopoBlock, 0, s>>>(C, states, line0, nlines, out.ctrack, stats);
             if (ev_mid) cudaEventRecord(ev_mid, s);
             k_topo_final<METHOD, false><<<grid, kTopoBlock, 0, s>>>(C, states, line0, out, stats);
         }
@@ -826,12 +867,12 @@ int launch_topo_pixels(const TopoConst &C, const LineState *states, int line0, i
     if (nblk > 0x7fffffffLL || !out.ctrack) return -2;
     const unsigned gs = (unsigned)(((C.width + kSolvePixelsPerCta - 1) / kSolvePixelsPerCta) * (long long)nlines);
     switch (C.method) {
-    case 0: launch_pixels_m<0>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
-    case 1: launch_pixels_m<1>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
-    case 2: launch_pixels_m<2>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
-    case 3: launch_pixels_m<3>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
-    case 4: launch_pixels_m<4>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
-    case 5: launch_pixels_m<5>(C, states, line0, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 0: launch_pixels_m<0>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 1: launch_pixels_m<1>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 2: launch_pixels_m<2>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 3: launch_pixels_m<3>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 4: launch_pixels_m<4>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
+    case 5: launch_pixels_m<5>(C, states, line0, nlines, out, stats, (unsigned)nblk, gs, s, ev_mid); break;
     default: return -1;
     }
     return 0;
