@@ -197,33 +197,62 @@ __device__ __forceinline__ void load_line_state(LineState &sL, const LineState *
 //     makes the idle tail at the end of a run (lanes waiting for the last pixels) 8x rarer than with 128-pixel strips.
 constexpr int kStrip = 128;                                    // pixels per warp (fused kernel)
 constexpr int kSolvePixelsPerCta = (kTopoBlock / 32) * kStrip; // 512
-constexpr int kRing = 128;                                     // staged look-ahead per warp (split solve kernel)
-constexpr int kStage = 64;                                     // pixels staged per refill of the ring
+constexpr int kRing = 64;                                      // staged look-ahead per warp (split solve kernel)
+constexpr int kStage = 32;                                     // pixels staged per refill of the ring
 constexpr int kSegMax = 1024;                                  // longest run of pixels per warp
 
+// Per-pixel constants of the upcoming pixels, evaluated with all lanes busy (a refill inside the solve loop typically
+// has only a handful of lanes active, so everything hoisted here is paid at 1/6 of the price).
+struct StagedPixels {
+    double *rng, *inv_rng, *dopfact, *a12; // fused kernel (STREAM = false): only rng and the raw Doppler (in dopfact)
+};
+
 template <bool STREAM>
-__device__ __forceinline__ void stage_pixels(const TopoConst &C, int line, int pix0, int from, int to, double *rng_s, double *dop_s)
+__device__ __forceinline__ void stage_pixels(const TopoConst &C, const LineState &L, int line, int pix0, int from, int to,
+                                             const StagedPixels &S)
 {
     for (int j = from + (threadIdx.x & 31); j < to; j += 32) {
-        const int k = STREAM ? (j & (kRing - 1)) : j;
-        rng_s[k] = pixel_range(C, line, pix0 + j);
-        dop_s[k] = eval_poly2d(C.dop, (double)line, (double)(pix0 + j));
+        const double rng = pixel_range(C, line, pix0 + j), dop = eval_poly2d(C.dop, (double)line, (double)(pix0 + j));
+        if (STREAM) {
+            const int k = j & (kRing - 1);
+            const PixelConst P = make_pixel_const(C, L, rng, dop);
+            S.rng[k] = P.rng;
+            S.inv_rng[k] = P.inv_rng;
+            S.dopfact[k] = P.dopfact;
+            S.a12[k] = P.a12;
+        } else {
+            S.rng[j] = rng;
+            S.dopfact[j] = dop;
+        }
     }
+}
+
+template <bool STREAM>
+__device__ __forceinline__ PixelConst staged_pixel(const TopoConst &C, const LineState &L, const StagedPixels &S, int k)
+{
+    if (!STREAM) return make_pixel_const(C, L, S.rng[k], S.dopfact[k]);
+    PixelConst P;
+    P.rng = S.rng[k];
+    P.inv_rng = S.inv_rng[k];
+    P.rng2 = P.rng * P.rng;
+    P.dopfact = S.dopfact[k];
+    P.a12 = S.a12[k];
+    return P;
 }
 
 // Solve the strip_n pixels pix0 .. of one warp's run: lanes pull the next unsolved pixel as soon as their current one
 // converges.  zrow[j] receives the SCH height of run pixel j.  STREAM: rng_s / dop_s are rings (see above) that this
 // function keeps filled; otherwise the caller staged the whole run.
 template <int METHOD, bool REF, bool STREAM>
-__device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState &sL, int line, int pix0, double *rng_s,
-                                            double *dop_s, int strip_n, double *zrow, int &conv, int &iters)
+__device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState &sL, int line, int pix0,
+                                            const StagedPixels &S, int strip_n, double *zrow, int &conv, int &iters)
 {
     const int lane = threadIdx.x & 31;
     const int nprimary = C.numiter + 1 < C.numiter + C.extraiter + 1 ? C.numiter + 1 : C.numiter + C.extraiter + 1;
     int staged = strip_n;
     if (STREAM) {
         staged = strip_n < kRing ? strip_n : kRing;
-        stage_pixels<true>(C, line, pix0, 0, staged, rng_s, dop_s);
+        stage_pixels<true>(C, sL, line, pix0, 0, staged, S);
         __syncwarp();
     }
     PixelConst P;
@@ -233,7 +262,7 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
     iters = 0;
     bool active = slot < strip_n;
     if (active) {
-        P = make_pixel_const(C, sL, rng_s[slot], dop_s[slot]);
+        P = staged_pixel<STREAM>(C, sL, S, slot);
         lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny; // :435-436
         lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
     }
@@ -278,7 +307,7 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
             if (active) {
                 const int k = STREAM ? (j & (kRing - 1)) : j;
                 slot = j;
-                P = make_pixel_const(C, sL, rng_s[k], dop_s[k]);
+                P = staged_pixel<STREAM>(C, sL, S, k);
                 lat = C.ufirstlat + 0.5 * C.deltalat * C.dem.ny;
                 lon = C.ufirstlon + 0.05 * C.deltalon * C.dem.nx;
                 z = 0.0;
@@ -293,7 +322,7 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
             if (staged < strip_n && next + 32 > staged) {
                 const int to = staged + kStage < strip_n ? staged + kStage : strip_n;
                 __syncwarp();
-                stage_pixels<true>(C, line, pix0, staged, to, rng_s, dop_s);
+                stage_pixels<true>(C, sL, line, pix0, staged, to, S);
                 staged = to;
                 __syncwarp();
             }
@@ -311,8 +340,7 @@ k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
              double *__restrict__ zsch_out, TopoStats *stats)
 {
     __shared__ LineState sL[kTopoBlock / 32];
-    __shared__ double s_rng[kTopoBlock / 32][kRing];
-    __shared__ double s_dop[kTopoBlock / 32][kRing];
+    __shared__ double s_px[kTopoBlock / 32][4][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int spl = solve_segs_per_line(C.width);
     const int seg_len = (C.width + spl - 1) / spl;
@@ -330,7 +358,8 @@ k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
     __syncwarp();
     double *zrow = zsch_out + (size_t)row * (size_t)C.width + (size_t)pix0;
     int conv = 0, iters = 0;
-    solve_strip<METHOD, REF, true>(C, sL[warp], line0 + row, pix0, s_rng[warp], s_dop[warp], seg_n, zrow, conv, iters);
+    const StagedPixels S{s_px[warp][0], s_px[warp][1], s_px[warp][2], s_px[warp][3]};
+    solve_strip<METHOD, REF, true>(C, sL[warp], line0 + row, pix0, S, seg_n, zrow, conv, iters);
     // convergence statistics (:570)
     conv = warp_sum(conv);
     iters = warp_sum(iters);
@@ -407,10 +436,12 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
     const int strip0 = seg * kSolvePixelsPerCta + warp * kStrip;
     const int strip_n = (C.width - strip0) < kStrip ? (C.width - strip0) : kStrip;
     load_line_state(sL, states, row);
-    stage_pixels<false>(C, line, strip0, 0, strip_n, s_rng[warp], s_dop[warp]);
     __syncthreads();
+    const StagedPixels S{s_rng[warp], nullptr, s_dop[warp], nullptr};
+    stage_pixels<false>(C, sL, line, strip0, 0, strip_n, S);
+    __syncwarp();
     int conv = 0, iters = 0;
-    solve_strip<METHOD, REF, false>(C, sL, line, strip0, s_rng[warp], s_dop[warp], strip_n, s_z[warp], conv, iters);
+    solve_strip<METHOD, REF, false>(C, sL, line, strip0, S, strip_n, s_z[warp], conv, iters);
     __syncwarp();
     // final pass over the strip, consecutive lanes on consecutive pixels (coalesced layer stores)
     double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
