@@ -339,3 +339,40 @@ def read_raster(img, as_dtype=None):
     if as_dtype is not None and arr.dtype != np.dtype(as_dtype):
         arr = np.asarray(arr).astype(as_dtype)
     return arr
+
+
+def read_view(path):
+    """Open the raster named `path` (no extension; ``path.xml`` / ``path.vrt`` beside it).  When the raster file itself
+    does not exist and ``path.vrt`` is a window into a parent raster (the per-burst views written by
+    TopsProc/runTopo.py:362-423 ``buildVRT``: one ``SimpleSource`` + ``SrcRect`` per band), the window of the parent
+    is returned without copying; the reference reads such views through GDAL (DataAccessorPy.py:125-171)."""
+    if path.endswith(".xml") or path.endswith(".vrt"):
+        path = path[:-4]
+    if os.path.exists(path) and os.path.exists(path + ".xml"):
+        img = Image()
+        img.load(path + ".xml")
+        img.filename = path
+        return img.memMap()
+    if not os.path.exists(path + ".vrt"):
+        raise FileNotFoundError(path)
+    root = ET.parse(path + ".vrt").getroot()
+    views = []
+    for b in root.findall("VRTRasterBand"):
+        src = b.find("SimpleSource")
+        if src is None:  # a raw VRT without its XML: describe the file from the band record
+            raise FileNotFoundError(path + ".xml")
+        fn = src.find("SourceFilename")
+        parent = fn.text.strip()
+        if fn.get("relativeToVRT", "0") == "1":
+            parent = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(path)), parent))
+        rect = src.find("SrcRect")
+        x0, y0 = int(float(rect.get("xOff"))), int(float(rect.get("yOff")))
+        nx, ny = int(float(rect.get("xSize"))), int(float(rect.get("ySize")))
+        band = int(src.find("SourceBand").text) - 1
+        arr = read_view(parent)
+        if arr.ndim == 3:
+            arr = arr[:, band, :]  # BIL parents only (the layers topo writes)
+        views.append(arr[y0:y0 + ny, x0:x0 + nx])
+    if len(views) == 1:
+        return views[0]
+    return np.stack(views, axis=1)

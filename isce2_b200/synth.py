@@ -269,3 +269,51 @@ def config_c2(length=13500, width=25000, **kw):
 
 def config_c3(length=60000, width=25000, **kw):
     return make_scene(length, width, sensor="nisar", name="C3_nisar_frame", **kw)
+
+
+def make_tops_acquisition(n_swaths=2, n_bursts=3, burst_lines=60, burst_samples=900, overlap_lines=8, overlap_samples=60,
+                          swath_lag_lines=5, sv_per_burst=None, **scene_kw):
+    """A TOPS-like acquisition cut out of one synthetic scene: `n_swaths` sub-swaths (each later in time and farther in
+    range than the previous one, overlapping by `overlap_samples`), `n_bursts` bursts each (overlapping by
+    `overlap_lines`).  Returns (scene, frames); a frame has ``.bursts`` and every burst the attributes the reference reads
+    from a ``BurstSLC`` (components/isceobj/Sensor/TOPS/BurstSLC.py): sensingStart/Stop, startingRange, farRange,
+    numberOfLines/Samples, rangePixelSize, azimuthTimeInterval, radarWavelength, orbit.  The union grid of the frames
+    (TopsProc/runTopo.py:159-172) is exactly the scene's grid."""
+    from types import SimpleNamespace
+
+    from .orbit import Orbit, StateVector
+
+    az_step = burst_lines - overlap_lines
+    rg_step = burst_samples - overlap_samples
+    length = swath_lag_lines * (n_swaths - 1) + az_step * (n_bursts - 1) + burst_lines
+    width = rg_step * (n_swaths - 1) + burst_samples
+    sc = make_scene(length, width, **scene_kw)
+    day = sc.sensing_start.replace(hour=0, minute=0, second=0, microsecond=0)
+    dt = 1.0 / sc.prf
+    svs = [StateVector(day + datetime.timedelta(seconds=float(t)), p, v) for t, p, v in zip(sc.orbit_t, sc.orbit_pos, sc.orbit_vel)]
+    frames = []
+    k = 0
+    for s in range(n_swaths):
+        bursts = []
+        for b in range(n_bursts):
+            top = s * swath_lag_lines + b * az_step
+            left = s * rg_step
+            orb = Orbit()
+            if sv_per_burst:  # annotation-style orbits: every burst carries only part of the state vectors
+                lo = (k * 2) % max(1, len(svs) - sv_per_burst + 1)
+                for sv in svs[lo:lo + sv_per_burst]:
+                    orb.addStateVector(sv)
+            else:
+                for sv in svs:
+                    orb.addStateVector(sv)
+            k += 1
+            start = sc.sensing_start + datetime.timedelta(seconds=top * dt)
+            bursts.append(SimpleNamespace(
+                sensingStart=start, sensingStop=start + datetime.timedelta(seconds=(burst_lines - 1) * dt),
+                startingRange=sc.r0 + left * sc.dr, farRange=sc.r0 + (left + burst_samples - 1) * sc.dr,
+                numberOfLines=burst_lines, numberOfSamples=burst_samples, rangePixelSize=sc.dr, azimuthTimeInterval=dt,
+                radarWavelength=sc.wvl, orbit=orb, window=(top, top + burst_lines, left, left + burst_samples)))
+        frames.append(SimpleNamespace(bursts=bursts, numberOfBursts=n_bursts,
+                                      sensingStart=bursts[0].sensingStart, sensingStop=bursts[-1].sensingStop,
+                                      startingRange=bursts[0].startingRange, farRange=bursts[0].farRange))
+    return sc, frames
