@@ -214,6 +214,71 @@ int b200_geo_plan_fetch(b200_geo_plan *plan, const b200_geo_outputs *out, b200_g
 void b200_geo_plan_destroy(b200_geo_plan *plan);
 
 /* ------------------------------------------------------------------------------------------ */
+/* geozero (geocoding on the zero-Doppler geometry) -- SURVEY 8(f) row N3                      */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces the CPython extension components/zerodop/geozero/bindings/geozeromodule.cpp (set*_Py of
+ * include/geozeromodule.h, module geozeroState of src/geozeroState.F:36-78) and its verb geozero_Py
+ * (src/geozero.f90).  One field per set*_Py. */
+typedef struct {
+    double major, e2;                          /* setEllipsoid*_Py                            */
+    double min_lat, max_lat, min_lon, max_lon; /* set{Minimum,Maximum}{Latitude,Longitude}_Py */
+    double drho, rho0;                         /* setRangePixelSpacing_Py, setRangeFirstSample_Py */
+    double wvl, t0, prf;                       /* setRadarWavelength_Py, setSensingStart_Py, setPRF_Py */
+    int length, width;                         /* setLength_Py / setWidth_Py (image to geocode) */
+    int look_side;                             /* setLookSide_Py: -1 right, +1 left           */
+    int nrnglooks, nazlooks;                   /* setNumber{Range,Azimuth}Looks_Py            */
+    double first_lat, first_lon, delta_lat, delta_lon; /* setFirst*_Py / setDelta*_Py (DEM, degrees) */
+    int dem_width, dem_length;                 /* setDemWidth_Py / setDemLength_Py            */
+    int device;                                /* not in the reference: CUDA device ordinal   */
+} b200_geozero_params;
+
+#define B200_GEOZERO_SINC 0 /* geozeroMethods.F:29-31 */
+#define B200_GEOZERO_BILINEAR 1
+#define B200_GEOZERO_BICUBIC 2
+#define B200_GEOZERO_NEAREST 3
+#define B200_SCHEME_BIL 0 /* [line][band][sample] */
+#define B200_SCHEME_BIP 1 /* [line][sample][band] */
+#define B200_SCHEME_BSQ 2 /* [band][line][sample] */
+
+typedef struct {
+    int geo_width, geo_length;                             /* getGeoWidth_Py / getGeoLength_Py            */
+    double geo_min_lat, geo_max_lat, geo_min_lon, geo_max_lon; /* get{Min,Max}imumGeo{Lat,Long}itude_Py      */
+    long long num_outside_dem, num_outside_image, num_valid;   /* the three prints at geozero.f90:407-409 (of the
+                                                                   last geocoded band)                        */
+    long long iterations;                                  /* fixed-point steps summed over pixels        */
+    float ms_setup;   /* device time: DEM crop upload + orbit polynomials + the per-pixel solve            */
+    float ms_kernels; /* device time of the last geocode call's gather kernels                              */
+    float ms_total;
+    int gpu_launches;
+} b200_geozero_result;
+
+/* size of the output grid (geozero.f90:163-170), so that the caller can allocate the output image */
+int b200_geozero_grid(const b200_geozero_params *p, int *geo_width, int *geo_length, char *err, size_t errlen);
+
+/* Plan = the geometry of one output grid: uploads the needed part of the DEM ([dem_length][dem_width] of
+ * dem_dtype, host memory) and solves every output pixel's (azimuth, range) image coordinate ONCE.  The reference
+ * repeats that solve for every band of every product (Geozero.py:216-241). */
+typedef struct b200_geozero_plan b200_geozero_plan;
+int b200_geozero_plan_create(const b200_geozero_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                             const b200_poly1d *dop, b200_geozero_plan **plan, char *err, size_t errlen);
+/* geocode one image: `image` holds nbands bands of [length][width] samples, float32 (is_complex = 0) or
+ * interleaved complex64 (is_complex = 1) in the given interleaving scheme; `out` receives the same bands and
+ * scheme on the [geo_length][geo_width] grid.  method = B200_GEOZERO_*. */
+int b200_geozero_plan_geocode(b200_geozero_plan *plan, const void *image, int is_complex, int nbands, int scheme, int method,
+                              void *out, float *ms_kernels, char *err, size_t errlen);
+/* cropped DEM (setLineSequential(demCropAccessor, dem_crop), integer*2), the solved image coordinates (1-based,
+ * fractional; NaN where the reference skips the pixel) and the counters; any pointer may be NULL */
+int b200_geozero_plan_fetch(b200_geozero_plan *plan, int16_t *dem_crop, double *az_idx, double *rng_idx,
+                            b200_geozero_result *res, char *err, size_t errlen);
+void b200_geozero_plan_destroy(b200_geozero_plan *plan);
+
+/* The verb: geozero_Py(demAccessor, inAccessor, demCropAccessor, outAccessor, inband, outband, iscomplex, method,
+ * lookSide), all bands in one call. */
+int b200_geozero_run(const b200_geozero_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                     const b200_poly1d *dop, const void *image, int is_complex, int nbands, int scheme, int method,
+                     void *out, int16_t *dem_crop, b200_geozero_result *res, char *err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilities                                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 int b200_abi_version(void);

@@ -1,5 +1,5 @@
 """isce2_b200 -- B200-native (sm_100a, hand-written FP64 CUDA) zero-Doppler radar geometry for ISCE2:
-topozero (rdr2geo) and geo2rdr behind the reference's Component API.
+topozero (rdr2geo), geo2rdr and geozero (geocode) behind the reference's Component API.
 
     from isce2_b200 import createTopozero, createGeo2rdr       # same objects as zerodop.topozero / zerodop.geo2rdr
 
@@ -25,20 +25,26 @@ def createGeo2rdr(name=''):
     return f(name)
 
 
+def createGeozero():
+    from .geozero import createGeozero as f
+    return f()
+
+
 def install_as_zerodop():
     """Make ``from zerodop.topozero import createTopozero`` / ``from zerodop.geo2rdr import createGeo2rdr`` resolve to
     this package (components/zerodop/topozero/__init__.py:33-35, components/zerodop/geo2rdr/__init__.py:3-5)."""
-    from . import geo2rdr as g, topozero as t
+    from . import geo2rdr as g, geozero as z, topozero as t
     pkg = sys.modules.get("zerodop")
     if pkg is None:
         pkg = types.ModuleType("zerodop")
         pkg.__path__ = []
         sys.modules["zerodop"] = pkg
-    for name, mod, factory in (("topozero", t, "createTopozero"), ("geo2rdr", g, "createGeo2rdr")):
+    for name, mod, factory in (("topozero", t, "createTopozero"), ("geo2rdr", g, "createGeo2rdr"),
+                               ("geozero", z, "createGeozero")):
         m = types.ModuleType(f"zerodop.{name}")
         setattr(m, factory, getattr(mod, factory))
         setattr(m, mod.__name__.rsplit(".", 1)[-1].capitalize(), mod)
-        m.__dict__.update({k: v for k, v in mod.__dict__.items() if k in ("Topo", "Geo2rdr")})
+        m.__dict__.update({k: v for k, v in mod.__dict__.items() if k in ("Topo", "Geo2rdr", "Geocode")})
         sys.modules[f"zerodop.{name}"] = m
         setattr(pkg, name, m)
     return pkg

@@ -87,11 +87,31 @@ class GeoResult(C.Structure):
                 ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
 
 
+class GeozeroParams(C.Structure):
+    _fields_ = [("major", C.c_double), ("e2", C.c_double), ("min_lat", C.c_double), ("max_lat", C.c_double),
+                ("min_lon", C.c_double), ("max_lon", C.c_double), ("drho", C.c_double), ("rho0", C.c_double),
+                ("wvl", C.c_double), ("t0", C.c_double), ("prf", C.c_double), ("length", C.c_int), ("width", C.c_int),
+                ("look_side", C.c_int), ("nrnglooks", C.c_int), ("nazlooks", C.c_int), ("first_lat", C.c_double),
+                ("first_lon", C.c_double), ("delta_lat", C.c_double), ("delta_lon", C.c_double), ("dem_width", C.c_int),
+                ("dem_length", C.c_int), ("device", C.c_int)]
+
+
+class GeozeroResult(C.Structure):
+    _fields_ = [("geo_width", C.c_int), ("geo_length", C.c_int), ("geo_min_lat", C.c_double), ("geo_max_lat", C.c_double),
+                ("geo_min_lon", C.c_double), ("geo_max_lon", C.c_double), ("num_outside_dem", C.c_longlong),
+                ("num_outside_image", C.c_longlong), ("num_valid", C.c_longlong), ("iterations", C.c_longlong),
+                ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
+
+
+GEOZERO_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3}
+SCHEMES = {"BIL": 0, "BIP": 1, "BSQ": 2}
+
 EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "b200_topo_plan_fetch",
            "b200_topo_plan_device_layers", "b200_topo_plan_destroy", "b200_geo2rdr_run", "b200_geo_plan_create",
            "b200_geo_plan_create_from_topo", "b200_geo_plan_execute", "b200_geo_plan_fetch", "b200_geo_plan_destroy",
            "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
-           "b200_fp64_peak", "b200_device_primitive"]
+           "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
+           "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run"]
 
 _lib = None
 
@@ -132,6 +152,16 @@ def lib():
     L.b200_free_pinned.restype = None
     L.b200_fp64_peak.argtypes = [C.c_int, _dp] + err
     L.b200_device_primitive.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Orbit), _dp, _dp] + err
+    L.b200_geozero_grid.argtypes = [C.POINTER(GeozeroParams), C.POINTER(C.c_int), C.POINTER(C.c_int)] + err
+    L.b200_geozero_plan_create.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d),
+                                           C.POINTER(C.c_void_p)] + err
+    L.b200_geozero_plan_geocode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, _fp] + err
+    L.b200_geozero_plan_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_int16), _dp, _dp, C.POINTER(GeozeroResult)] + err
+    L.b200_geozero_plan_destroy.argtypes = [C.c_void_p]
+    L.b200_geozero_plan_destroy.restype = None
+    L.b200_geozero_run.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d), C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int16),
+                                   C.POINTER(GeozeroResult)] + err
     _lib = L
     return L
 
@@ -431,3 +461,116 @@ def device_primitive(what, vec3_or_t, a=6378137.0, e2=0.0066943799901, orbit=Non
     _check(lib().b200_device_primitive(device, what, a, e2, C.byref(orb) if orb is not None else None,
                                        inp.ctypes.data_as(_dp), out.ctypes.data_as(_dp), e, 512), e)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# geozero
+# ---------------------------------------------------------------------------------------------------------------
+def geozero_params(*, dem_shape, first_lat, first_lon, delta_lat, delta_lon, snwe, length, width, r0, dr, prf, t0, wvl,
+                   side=-1, a=6378137.0, e2=0.0066943799901, nrnglooks=1, nazlooks=1, device=0):
+    """snwe = (min_lat, max_lat, min_lon, max_lon) in degrees, as Geocode.snwe."""
+    return GeozeroParams(a, e2, snwe[0], snwe[1], snwe[2], snwe[3], dr, r0, wvl, t0, prf, length, width, side, nrnglooks,
+                         nazlooks, first_lat, first_lon, delta_lat, delta_lon, dem_shape[1], dem_shape[0], device)
+
+
+def geozero_grid(params):
+    w, l = C.c_int(), C.c_int()
+    e = _errbuf()
+    _check(lib().b200_geozero_grid(C.byref(params), C.byref(w), C.byref(l), e, 512), e)
+    return l.value, w.value
+
+
+def _image_arg(image, width, length, nbands, scheme):
+    """(contiguous array, is_complex): float32 or complex64 samples in the file's own interleaving."""
+    a = np.asarray(image)
+    is_complex = np.iscomplexobj(a)
+    a = np.ascontiguousarray(a, np.complex64 if is_complex else np.float32)
+    if a.size != width * length * nbands:
+        raise ValueError(f"image has {a.size} samples, expected {nbands} x {length} x {width}")
+    return a, is_complex
+
+
+class GeozeroPlan:
+    """Geometry of one geocoding grid, solved once on the GPU; geocode() any number of images / bands with it."""
+
+    def __init__(self, params, dem, orbit_t, orbit_pos, orbit_vel, doppler_coeffs=(0.0,), doppler_mean=0.0, doppler_norm=1.0):
+        self.params = params
+        keep = _Keep()
+        dem, code = _dem_arg(dem)
+        orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+        dop = make_poly1d(keep, doppler_coeffs, doppler_mean, doppler_norm)
+        self.handle = C.c_void_p()
+        e = _errbuf()
+        _check(lib().b200_geozero_plan_create(C.byref(params), dem.ctypes.data_as(C.c_void_p), code, C.byref(orb), C.byref(dop),
+                                              C.byref(self.handle), e, 512), e)
+        self.geo_length, self.geo_width = geozero_grid(params)
+
+    def geocode(self, image, method="BILINEAR", nbands=1, scheme="BIL", out=None):
+        p = self.params
+        a, is_complex = _image_arg(image, p.width, p.length, nbands, scheme)
+        sch = scheme.upper()
+        shape = ((self.geo_length, self.geo_width) if nbands == 1 else
+                 (self.geo_length, nbands, self.geo_width) if sch == "BIL" else
+                 (self.geo_length, self.geo_width, nbands) if sch == "BIP" else (nbands, self.geo_length, self.geo_width))
+        if out is None:
+            out = np.empty(shape, a.dtype)
+        if out.dtype != a.dtype or out.size != int(np.prod(shape)) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous array of the image's sample type on the geocoded grid")
+        ms = C.c_float()
+        e = _errbuf()
+        _check(lib().b200_geozero_plan_geocode(self.handle, a.ctypes.data_as(C.c_void_p), int(is_complex), int(nbands),
+                                               SCHEMES[sch], GEOZERO_METHODS[method.upper()], out.ctypes.data_as(C.c_void_p),
+                                               C.byref(ms), e, 512), e)
+        self.ms_kernels = ms.value
+        return out
+
+    def fetch(self, want_indices=False, dem_crop=None):
+        n = (self.geo_length, self.geo_width)
+        crop = dem_crop if dem_crop is not None else np.empty(n, np.int16)
+        az = np.empty(n) if want_indices else None
+        rg = np.empty(n) if want_indices else None
+        res = GeozeroResult()
+        e = _errbuf()
+        _check(lib().b200_geozero_plan_fetch(self.handle, crop.ctypes.data_as(C.POINTER(C.c_int16)),
+                                             az.ctypes.data_as(_dp) if az is not None else None,
+                                             rg.ctypes.data_as(_dp) if rg is not None else None, C.byref(res), e, 512), e)
+        r = dict(dem_crop=crop, az_idx=az, rng_idx=rg)
+        r.update(_result_dict(res))
+        return r
+
+    def close(self):
+        if self.handle:
+            lib().b200_geozero_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def geozero_run(params, dem, orbit_t, orbit_pos, orbit_vel, image, method="BILINEAR", nbands=1, scheme="BIL",
+                doppler_coeffs=(0.0,), doppler_mean=0.0, doppler_norm=1.0, out=None, dem_crop=None):
+    """One call of the reference verb geozero_Py, all bands of one image."""
+    keep = _Keep()
+    dem, code = _dem_arg(dem)
+    orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+    dop = make_poly1d(keep, doppler_coeffs, doppler_mean, doppler_norm)
+    a, is_complex = _image_arg(image, params.width, params.length, nbands, scheme)
+    gl, gw = geozero_grid(params)
+    sch = scheme.upper()
+    shape = ((gl, gw) if nbands == 1 else (gl, nbands, gw) if sch == "BIL" else (gl, gw, nbands) if sch == "BIP" else (nbands, gl, gw))
+    if out is None:
+        out = np.empty(shape, a.dtype)
+    if dem_crop is None:
+        dem_crop = np.empty((gl, gw), np.int16)
+    res = GeozeroResult()
+    e = _errbuf()
+    _check(lib().b200_geozero_run(C.byref(params), dem.ctypes.data_as(C.c_void_p), code, C.byref(orb), C.byref(dop),
+                                  a.ctypes.data_as(C.c_void_p), int(is_complex), int(nbands), SCHEMES[sch],
+                                  GEOZERO_METHODS[method.upper()], out.ctypes.data_as(C.c_void_p),
+                                  dem_crop.ctypes.data_as(C.POINTER(C.c_int16)), C.byref(res), e, 512), e)
+    r = dict(geo=out, dem_crop=dem_crop)
+    r.update(_result_dict(res))
+    return r

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "geo2rdr_kernels.cuh"
+#include "geozero_kernels.cuh"
 #include "orbit_poly.h"
 #include "topo_kernels.cuh"
 
@@ -1074,6 +1075,382 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
     pl->launches = launches;
     pl->executed = true;
     rc = b200_geo_plan_fetch(pl, nullptr, res, err, errlen);
+    if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
+    return rc;
+}
+
+// =================================================================================================
+// geozero
+// =================================================================================================
+namespace {
+
+struct GeozeroGrid {
+    int min_lat_idx, max_lat_idx, min_lon_idx, max_lon_idx, geo_len, geo_wid;
+    double lat_firstr, lon_firstr, dlatr, dlonr;
+};
+
+// geozero.f90:118-119, 146-149, 159-170 (real*8 -> integer assignments truncate)
+GeozeroGrid geozero_grid(const b200_geozero_params &p)
+{
+    GeozeroGrid g;
+    const double pi = 4.0 * atan(1.0);
+    const double deg2rad = pi / 180.0;
+    g.dlonr = p.delta_lon * deg2rad;
+    g.dlatr = p.delta_lat * deg2rad;
+    g.lon_firstr = p.first_lon * deg2rad;
+    g.lat_firstr = p.first_lat * deg2rad;
+    const double min_latr = p.min_lat * deg2rad, max_latr = p.max_lat * deg2rad;
+    const double min_lonr = p.min_lon * deg2rad, max_lonr = p.max_lon * deg2rad;
+    g.min_lat_idx = (int)((min_latr - g.lat_firstr) / g.dlatr + 1);
+    g.min_lon_idx = (int)((min_lonr - g.lon_firstr) / g.dlonr);
+    g.max_lat_idx = (int)((max_latr - g.lat_firstr) / g.dlatr);
+    g.max_lon_idx = (int)((max_lonr - g.lon_firstr) / g.dlonr + 1);
+    g.geo_len = g.min_lat_idx - g.max_lat_idx;
+    g.geo_wid = g.max_lon_idx - g.min_lon_idx;
+    return g;
+}
+
+int geozero_check(const b200_geozero_params *p, char *err, size_t errlen)
+{
+    if (!p) return fail(err, errlen, B200_EINVAL, "params is NULL");
+    if (p->length < 1 || p->width < 1) return fail(err, errlen, B200_EINVAL, "bad image size %d x %d", p->length, p->width);
+    if (p->dem_width < 1 || p->dem_length < 1) return fail(err, errlen, B200_EINVAL, "bad DEM size");
+    if (p->delta_lat == 0.0 || p->delta_lon == 0.0) return fail(err, errlen, B200_EINVAL, "DEM posting is zero");
+    if (p->prf <= 0 || p->nazlooks < 1 || p->nrnglooks < 1) return fail(err, errlen, B200_EINVAL, "bad prf / looks");
+    if (p->look_side != -1 && p->look_side != 1) return fail(err, errlen, B200_EINVAL, "look side must be -1 or +1");
+    return B200_OK;
+}
+
+} // namespace
+
+struct b200_geozero_plan {
+    b200_geozero_params p{};
+    GeozeroGrid g{};
+    GeozeroConst C{};
+    GeozeroGeometry G{nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *d_dem = nullptr;
+    void *d_raw = nullptr;
+    int *d_maxkey = nullptr;
+    double *d_poly = nullptr;
+    OrbitPolyView op{};
+    DeviceOrbit dorb;
+    GeoMid *d_mid = nullptr;
+    GeozeroStats *d_stats = nullptr;
+    float *d_sinc = nullptr;
+    void *d_img = nullptr, *d_out = nullptr;
+    size_t img_bytes = 0, out_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float ms_setup = 0.f, ms_kernels = 0.f;
+    long long num_outside_dem = 0, num_outside_image = 0, num_valid = 0, iterations = 0;
+    int launches = 0;
+
+    ~b200_geozero_plan()
+    {
+        cudaSetDevice(p.device);
+        dfree(G.az_idx); dfree(G.rng_idx); dfree(G.dem_crop); dfree(G.row_sc); dfree(G.col_sc);
+        dfree(d_dem); dfree(d_raw); dfree(d_maxkey); dfree(d_poly); dfree(dorb.buf); dfree(d_mid); dfree(d_stats);
+        dfree(d_sinc); dfree(d_img); dfree(d_out);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" int b200_geozero_grid(const b200_geozero_params *p, int *geo_width, int *geo_length, char *err, size_t errlen)
+{
+    int rc = geozero_check(p, err, errlen);
+    if (rc != B200_OK) return rc;
+    const GeozeroGrid g = geozero_grid(*p);
+    if (geo_width) *geo_width = g.geo_wid;
+    if (geo_length) *geo_length = g.geo_len;
+    return B200_OK;
+}
+
+static int geozero_plan_build(b200_geozero_plan *pl, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                              const b200_poly1d *dop, char *err, size_t errlen)
+{
+    const b200_geozero_params &p = pl->p;
+    int rc;
+    // geozero always interpolates the orbit with the Hermite scheme (interpolateWGS84Orbit_f, geozero.f90:229, :341)
+    if ((rc = check_orbit(orbit, B200_ORBIT_HERMITE, err, errlen)) != B200_OK) return rc;
+    if (!dop || !dop->coeffs || dop->order < 0 || dop->order + 1 > kMaxPoly1dCoeffs)
+        return fail(err, errlen, B200_EINVAL, "bad doppler polynomial");
+    if (!dem) return fail(err, errlen, B200_EINVAL, "dem is NULL");
+    if (dem_dtype != B200_DEM_F32 && dem_dtype != B200_DEM_I16) return fail(err, errlen, B200_EINVAL, "bad dem_dtype");
+    pl->g = geozero_grid(p);
+    const GeozeroGrid &g = pl->g;
+    if (g.geo_len < 1 || g.geo_wid < 1)
+        return fail(err, errlen, B200_EINVAL, "empty output grid (%d lines x %d samples): check the bounding box", g.geo_len,
+                    g.geo_wid);
+    if ((rc = select_device(p.device, err, errlen)) != B200_OK) return rc;
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&pl->ev0));
+    CK(cudaEventCreate(&pl->ev1));
+    cudaStream_t s = pl->stream;
+    CK(cudaEventRecord(pl->ev0, s));
+
+    GeozeroConst &C = pl->C;
+    C.elp = make_ellipsoid(p.major, p.e2);
+    C.wvl = p.wvl;
+    C.tstart = p.t0; // :126-139
+    C.dtaz = p.nazlooks / p.prf;
+    const double tend = p.t0 + (p.length - 1) * C.dtaz;
+    C.tmid = 0.5 * (C.tstart + tend);
+    C.rngstart = p.rho0;
+    C.dmrg = p.nrnglooks * p.drho;
+    C.length = p.length;
+    C.width = p.width;
+    C.look_side = p.look_side;
+    C.lat_firstr = g.lat_firstr;
+    C.lon_firstr = g.lon_firstr;
+    C.dlatr = g.dlatr;
+    C.dlonr = g.dlonr;
+    C.max_lat_idx = g.max_lat_idx;
+    C.min_lon_idx = g.min_lon_idx;
+    C.geo_len = g.geo_len;
+    C.geo_wid = g.geo_wid;
+    C.demwidth = p.dem_width;
+    C.demlength = p.dem_length;
+    // doppler-vs-range polynomial and its derivative (:196-224)
+    C.fd.order = dop->order;
+    C.fd.mean = p.rho0 + dop->mean * p.drho;
+    C.fd.norm = dop->norm * p.drho;
+    for (int k = 0; k <= dop->order; k++) C.fd.c[k] = dop->coeffs[k] * p.prf;
+    if (C.fd.order == 0) {
+        C.fdd.order = 0;
+        C.fdd.mean = 0.0;
+        C.fdd.norm = 1.0;
+        C.fdd.c[0] = 0.0;
+    } else {
+        C.fdd.order = C.fd.order - 1;
+        C.fdd.mean = C.fd.mean;
+        C.fdd.norm = C.fd.norm;
+        for (int k = 1; k <= dop->order; k++) C.fdd.c[k - 1] = k * C.fd.c[k] / C.fd.norm;
+    }
+
+    // ---- the part of the DEM under the output grid ----
+    int r0 = g.max_lat_idx < 0 ? 0 : g.max_lat_idx, r1 = g.max_lat_idx + g.geo_len;
+    if (r1 > p.dem_length) r1 = p.dem_length;
+    int c0 = g.min_lon_idx < 0 ? 0 : g.min_lon_idx, c1 = g.min_lon_idx + g.geo_wid;
+    if (c1 > p.dem_width) c1 = p.dem_width;
+    C.dem_row0 = r0;
+    C.dem_col0 = c0;
+    C.dem_rows = r1 > r0 ? r1 - r0 : 0;
+    C.dem_cols = c1 > c0 ? c1 - c0 : 0;
+    // lines of the output grid that fall outside the DEM (:250-253 counts demwidth pixels per such line)
+    pl->num_outside_dem = 0;
+    for (int line = 0; line < g.geo_len; line++) {
+        const int idxlat = g.max_lat_idx + line;
+        if (idxlat < 0 || idxlat > p.dem_length - 1) pl->num_outside_dem += p.dem_width;
+    }
+    const size_t ncell = (size_t)C.dem_rows * (size_t)C.dem_cols;
+    if (ncell) {
+        const size_t esz = dem_dtype == B200_DEM_I16 ? 2 : 4;
+        CK(dmalloc(&pl->d_dem, sizeof(float) * ncell));
+        CK(dmalloc(&pl->d_maxkey, sizeof(int)));
+        const char *src = (const char *)dem + ((size_t)r0 * (size_t)p.dem_width + (size_t)c0) * esz;
+        void *dst = pl->d_dem;
+        if (dem_dtype == B200_DEM_I16) {
+            CK(dmalloc(&pl->d_raw, esz * ncell));
+            dst = pl->d_raw;
+        }
+        CK(cudaMemcpy2DAsync(dst, (size_t)C.dem_cols * esz, src, (size_t)p.dem_width * esz, (size_t)C.dem_cols * esz,
+                             (size_t)C.dem_rows, cudaMemcpyHostToDevice, s));
+        int init = (int)0x80000000;
+        CK(cudaMemcpyAsync(pl->d_maxkey, &init, sizeof init, cudaMemcpyHostToDevice, s));
+        launch_dem_prepare(dst, dem_dtype, pl->d_dem, ncell, pl->d_maxkey, s); // 'read' FLOAT caster (Geozero.py:204)
+        pl->launches++;
+    } else {
+        CK(dmalloc(&pl->d_dem, sizeof(float)));
+    }
+    C.dem = pl->d_dem;
+
+    // ---- orbit: mid-scene state (:229-236) and the per-window Hermite polynomials ----
+    if ((rc = upload_orbit(orbit, pl->dorb, s, err, errlen)) != B200_OK) return rc;
+    CK(dmalloc(&pl->d_mid, sizeof(GeoMid)));
+    launch_geo_setup(B200_ORBIT_HERMITE, pl->dorb.view, C.tmid, pl->d_mid, s);
+    pl->launches++;
+    GeoMid mid;
+    CK(cudaMemcpyAsync(&mid, pl->d_mid, sizeof mid, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (mid.stat_mid != 0) return fail(err, errlen, B200_EORBIT, "Cannot interpolate orbits at the center of scene.");
+    C.xyz_mid = Vec3{mid.xyz[0], mid.xyz[1], mid.xyz[2]};
+    C.vel_mid = Vec3{mid.vel[0], mid.vel[1], mid.vel[2]};
+    {
+        HostOrbitPoly hp;
+        if (!build_orbit_poly(B200_ORBIT_HERMITE, orbit->nvec, orbit->t, orbit->pos, orbit->vel, hp))
+            return fail(err, errlen, B200_EORBIT, "cannot build the orbit polynomials");
+        const size_t nt = (size_t)hp.n, nw = (size_t)hp.nwin, nc = hp.cp.size();
+        std::vector<double> blob(nt + 2 * nw + nc);
+        memcpy(blob.data(), orbit->t, sizeof(double) * nt);
+        memcpy(blob.data() + nt, hp.tc.data(), sizeof(double) * nw);
+        memcpy(blob.data() + nt + nw, hp.inv_h.data(), sizeof(double) * nw);
+        memcpy(blob.data() + nt + 2 * nw, hp.cp.data(), sizeof(double) * nc);
+        CK(dmalloc(&pl->d_poly, sizeof(double) * blob.size()));
+        CK(cudaMemcpyAsync(pl->d_poly, blob.data(), sizeof(double) * blob.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        pl->op = OrbitPolyView{hp.method, hp.n, hp.nwin, hp.ncoef, pl->d_poly, pl->d_poly + nt, pl->d_poly + nt + nw,
+                               pl->d_poly + nt + 2 * nw, nullptr};
+    }
+
+    // ---- geometry of the grid: solved once ----
+    const size_t npix = (size_t)g.geo_len * (size_t)g.geo_wid;
+    CK(dmalloc(&pl->G.az_idx, sizeof(double) * npix));
+    CK(dmalloc(&pl->G.rng_idx, sizeof(double) * npix));
+    CK(dmalloc(&pl->G.dem_crop, sizeof(short) * npix));
+    CK(dmalloc(&pl->G.row_sc, sizeof(double) * 2 * (size_t)g.geo_len));
+    CK(dmalloc(&pl->G.col_sc, sizeof(double) * 2 * (size_t)g.geo_wid));
+    CK(dmalloc(&pl->d_stats, sizeof(GeozeroStats)));
+    CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeozeroStats), s));
+    launch_geozero_axes(C, pl->G, s);
+    if (launch_geozero_solve(C, pl->op, pl->G, pl->d_stats, s) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the geozero solve kernel");
+    pl->launches += 2;
+    CK(cudaEventRecord(pl->ev1, s));
+    GeozeroStats st;
+    CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->ms_setup, pl->ev0, pl->ev1));
+    pl->iterations = (long long)st.iterations;
+    if (pl->d_raw) {
+        dfree(pl->d_raw);
+        pl->d_raw = nullptr;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_geozero_plan_create(const b200_geozero_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                                        const b200_poly1d *dop, b200_geozero_plan **plan, char *err, size_t errlen)
+{
+    if (!plan) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    int rc = geozero_check(p, err, errlen);
+    if (rc != B200_OK) return rc;
+    b200_geozero_plan *pl = new (std::nothrow) b200_geozero_plan;
+    if (!pl) return fail(err, errlen, B200_ENOMEM, "out of host memory");
+    pl->p = *p;
+    rc = geozero_plan_build(pl, dem, dem_dtype, orbit, dop, err, errlen);
+    if (rc != B200_OK) {
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return B200_OK;
+}
+
+extern "C" int b200_geozero_plan_geocode(b200_geozero_plan *pl, const void *image, int is_complex, int nbands, int scheme,
+                                         int method, void *out, float *ms_kernels, char *err, size_t errlen)
+{
+    if (!pl || !image || !out) return fail(err, errlen, B200_EINVAL, "plan/image/out is NULL");
+    if (nbands < 1) return fail(err, errlen, B200_EINVAL, "nbands must be >= 1");
+    if (scheme != B200_SCHEME_BIL && scheme != B200_SCHEME_BIP && scheme != B200_SCHEME_BSQ)
+        return fail(err, errlen, B200_EINVAL, "unknown interleaving scheme %d", scheme);
+    if (method < B200_GEOZERO_SINC || method > B200_GEOZERO_NEAREST)
+        return fail(err, errlen, B200_EINVAL, "Undefined interpolation method."); // geozero.f90:110-112
+    const b200_geozero_params &p = pl->p;
+    CK(cudaSetDevice(p.device));
+    cudaStream_t s = pl->stream;
+    const size_t esz = is_complex ? 8 : 4;
+    const size_t W = (size_t)p.width, L = (size_t)p.length, gw = (size_t)pl->g.geo_wid, gl = (size_t)pl->g.geo_len, nb = (size_t)nbands;
+    const size_t in_bytes = esz * W * L * nb, out_bytes = esz * gw * gl * nb;
+    if (pl->img_bytes < in_bytes) {
+        dfree(pl->d_img);
+        pl->d_img = nullptr;
+        CK(dmalloc(&pl->d_img, in_bytes));
+        pl->img_bytes = in_bytes;
+    }
+    if (pl->out_bytes < out_bytes) {
+        dfree(pl->d_out);
+        pl->d_out = nullptr;
+        CK(dmalloc(&pl->d_out, out_bytes));
+        pl->out_bytes = out_bytes;
+    }
+    if (method == B200_GEOZERO_SINC && !pl->d_sinc) { // prepareMethods (geozeroMethods.F:46-64)
+        std::vector<float> tab((size_t)kSincSub * kSincLen);
+        sinc_make_table(tab.data());
+        CK(dmalloc(&pl->d_sinc, sizeof(float) * tab.size()));
+        CK(cudaMemcpyAsync(pl->d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaMemcpyAsync(pl->d_img, image, in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->ev0, s));
+    for (int b = 0; b < nbands; b++) {
+        BandView iv, ov;
+        if (scheme == B200_SCHEME_BIL) {
+            iv = BandView{(size_t)b * W, nb * W, 1};
+            ov = BandView{(size_t)b * gw, nb * gw, 1};
+        } else if (scheme == B200_SCHEME_BIP) {
+            iv = BandView{(size_t)b, nb * W, nb};
+            ov = BandView{(size_t)b, nb * gw, nb};
+        } else {
+            iv = BandView{(size_t)b * W * L, W, 1};
+            ov = BandView{(size_t)b * gw * gl, gw, 1};
+        }
+        // the counters the reference prints are those of one band; keep the last band's
+        CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeozeroStats), s));
+        if (launch_geozero_interp(pl->C, pl->G, method, is_complex, pl->d_img, iv, pl->d_out, ov, pl->d_sinc, pl->d_stats, s) != 0)
+            return fail(err, errlen, B200_EINVAL, "cannot launch the geozero gather kernel");
+        pl->launches++;
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    GeozeroStats st;
+    CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out, pl->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    pl->num_outside_image = (long long)st.outside_image;
+    pl->num_valid = (long long)st.valid;
+    if (ms_kernels) *ms_kernels = pl->ms_kernels;
+    return B200_OK;
+}
+
+extern "C" int b200_geozero_plan_fetch(b200_geozero_plan *pl, int16_t *dem_crop, double *az_idx, double *rng_idx,
+                                       b200_geozero_result *res, char *err, size_t errlen)
+{
+    if (!pl) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    const size_t npix = (size_t)pl->g.geo_len * (size_t)pl->g.geo_wid;
+    if (dem_crop) CK(cudaMemcpyAsync(dem_crop, pl->G.dem_crop, sizeof(short) * npix, cudaMemcpyDeviceToHost, s));
+    if (az_idx) CK(cudaMemcpyAsync(az_idx, pl->G.az_idx, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
+    if (rng_idx) CK(cudaMemcpyAsync(rng_idx, pl->G.rng_idx, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (res) {
+        const b200_geozero_params &p = pl->p;
+        res->geo_width = pl->g.geo_wid;
+        res->geo_length = pl->g.geo_len;
+        res->geo_min_lat = (p.first_lat + pl->g.min_lat_idx * p.delta_lat); // geozero.f90:419-422
+        res->geo_max_lat = (p.first_lat + pl->g.max_lat_idx * p.delta_lat);
+        res->geo_min_lon = (p.first_lon + pl->g.min_lon_idx * p.delta_lon);
+        res->geo_max_lon = (p.first_lon + pl->g.max_lon_idx * p.delta_lon);
+        res->num_outside_dem = pl->num_outside_dem;
+        res->num_outside_image = pl->num_outside_image;
+        res->num_valid = pl->num_valid;
+        res->iterations = pl->iterations;
+        res->ms_setup = pl->ms_setup;
+        res->ms_kernels = pl->ms_kernels;
+        res->ms_total = 0.f;
+        res->gpu_launches = pl->launches;
+    }
+    return B200_OK;
+}
+
+extern "C" void b200_geozero_plan_destroy(b200_geozero_plan *pl) { delete pl; }
+
+extern "C" int b200_geozero_run(const b200_geozero_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                                const b200_poly1d *dop, const void *image, int is_complex, int nbands, int scheme, int method,
+                                void *out, int16_t *dem_crop, b200_geozero_result *res, char *err, size_t errlen)
+{
+    const double t0 = now_ms();
+    b200_geozero_plan *pl = nullptr;
+    int rc = b200_geozero_plan_create(p, dem, dem_dtype, orbit, dop, &pl, err, errlen);
+    if (rc != B200_OK) return rc;
+    rc = b200_geozero_plan_geocode(pl, image, is_complex, nbands, scheme, method, out, nullptr, err, errlen);
+    if (rc == B200_OK) rc = b200_geozero_plan_fetch(pl, dem_crop, nullptr, nullptr, res, err, errlen);
+    delete pl;
     if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
     return rc;
 }

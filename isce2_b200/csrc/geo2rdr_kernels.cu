@@ -8,6 +8,7 @@
 //
 // Compiled with -fmad=false (see geom_device.cuh).
 #include "geo2rdr_kernels.cuh"
+#include "orbit_poly_device.cuh"
 
 namespace b2 {
 
@@ -158,73 +159,6 @@ k_geo2rdr(const __grid_constant__ GeoConst C, OrbitView orb_g, int line0, int nl
 // its first step is the reference's own first step so that the reference's out-of-span test on the first iterate
 // (geo2rdr.f90:287-291, the only iterate that can overshoot by seconds) is reproduced.  Final range / validity tests
 // are the reference's (:308-329), evaluated at the converged state.
-struct OrbState {
-    Vec3 x, v, a;
-};
-
-template <int METHOD>
-__device__ __forceinline__ int poly_window(const OrbitPolyView &op, double time)
-{
-    // first i with t[i] >= time (orbit.c:203-206); epochs are ascending
-    int i = 0;
-    while (i < op.n && __ldg(op.t + i) < time) i++;
-    const int back = (METHOD == 0) ? 2 : 5, span = (METHOD == 0) ? 4 : 9;
-    int w = i - back;
-    w = w < 0 ? 0 : w;
-    w = w > op.n - span ? op.n - span : w;
-    return w;
-}
-
-template <int METHOD>
-__device__ __forceinline__ void poly_state(const OrbitPolyView &op, double time, OrbState &S)
-{
-    const int w = poly_window<METHOD>(op, time);
-    const double ih = __ldg(op.inv_h + w);
-    const double s = (time - __ldg(op.tc + w)) * ih;
-    constexpr int NC = (METHOD == 0) ? 8 : 9;
-    double xo[3], vo[3], ao[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const double *cp = op.cp + ((size_t)w * 3 + c) * NC;
-        if (METHOD == 0) { // position, first and second derivative from one coefficient set
-            double p = __ldg(cp), dp = 0.0, ddp = 0.0;
-#pragma unroll
-            for (int k = 1; k < NC; k++) {
-                ddp = __fma_rn(ddp, s, dp);
-                dp = __fma_rn(dp, s, p);
-                p = __fma_rn(p, s, __ldg(cp + k));
-            }
-            xo[c] = p;
-            vo[c] = dp * ih;
-            ao[c] = 2.0 * ddp * ih * ih;
-        } else { // Legendre: velocity is its own polynomial; acceleration = d/dt of it
-            const double *cv = op.cv + ((size_t)w * 3 + c) * NC;
-            double p = __ldg(cp), q = __ldg(cv), dq = 0.0;
-#pragma unroll
-            for (int k = 1; k < NC; k++) {
-                dq = __fma_rn(dq, s, q);
-                q = __fma_rn(q, s, __ldg(cv + k));
-                p = __fma_rn(p, s, __ldg(cp + k));
-            }
-            xo[c] = p;
-            vo[c] = q;
-            ao[c] = dq * ih;
-        }
-    }
-    S.x = Vec3{xo[0], xo[1], xo[2]};
-    S.v = Vec3{vo[0], vo[1], vo[2]};
-    S.a = Vec3{ao[0], ao[1], ao[2]};
-}
-
-__device__ __forceinline__ double poly1d_fast(const Poly1dDev &p, double inv_norm, double x)
-{
-    if (p.order == 0) return p.c[0];
-    const double xv = (x - p.mean) * inv_norm;
-    double v = p.c[p.order];
-    for (int i = p.order - 1; i >= 0; i--) v = __fma_rn(v, xv, p.c[i]);
-    return v;
-}
-
 template <int METHOD, typename T>
 __global__ void __launch_bounds__(kGeoBlock)
 k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, int nlines, GeoLayers L, GeoStats *stats)

@@ -66,6 +66,20 @@ class OrcGeoResult(C.Structure):
                 ("total_iters", C.c_longlong)]
 
 
+class OrcGeozeroParams(C.Structure):
+    _fields_ = [("major", C.c_double), ("e2", C.c_double), ("min_lat", C.c_double), ("min_lon", C.c_double),
+                ("max_lat", C.c_double), ("max_lon", C.c_double), ("drho", C.c_double), ("rho0", C.c_double),
+                ("wvl", C.c_double), ("t0", C.c_double), ("prf", C.c_double), ("length", C.c_int), ("width", C.c_int),
+                ("nrnglooks", C.c_int), ("nazlooks", C.c_int), ("lat_first", C.c_double), ("lon_first", C.c_double),
+                ("dlat", C.c_double), ("dlon", C.c_double), ("demwidth", C.c_int), ("demlength", C.c_int)]
+
+
+class OrcGeozeroResult(C.Structure):
+    _fields_ = [("geowidth", C.c_int), ("geolength", C.c_int), ("geomin_lat", C.c_double), ("geomax_lat", C.c_double),
+                ("geomin_lon", C.c_double), ("geomax_lon", C.c_double), ("num_outside_dem", C.c_longlong),
+                ("num_outside_image", C.c_longlong), ("num_valid", C.c_longlong), ("total_iters", C.c_longlong)]
+
+
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is mounted)."""
     src = os.path.join(HERE, "zerodop_oracle.c")
@@ -116,6 +130,10 @@ def lib():
         L.orc_geo2rdr.restype = C.c_int
         L.orc_geo2rdr.argtypes = [C.POINTER(OrcGeoParams), _dp, _dp, _dp, C.POINTER(OrcOrbit), C.POINTER(OrcPoly1d),
                                   C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(OrcGeoResult), C.c_int]
+        L.orc_geozero_grid.argtypes = [C.POINTER(OrcGeozeroParams)] + [C.POINTER(C.c_int)] * 6
+        L.orc_geozero.restype = C.c_int
+        L.orc_geozero.argtypes = [C.POINTER(OrcGeozeroParams), _fp, C.POINTER(OrcOrbit), C.POINTER(OrcPoly1d), _fp, C.c_int,
+                                  C.c_int, C.c_int, _fp, C.POINTER(C.c_int16), _dp, _dp, C.POINTER(OrcGeozeroResult), C.c_int]
         _lib = L
     return _lib
 
@@ -258,3 +276,48 @@ def scene_topo_kwargs(sc, **over):
               side=sc.side, peg_heading=sc.peg_heading, doppler_coeffs=sc.doppler_coeffs, a=sc.a, e2=sc.e2)
     kw.update(over)
     return kw
+
+
+GEOZERO_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3}
+
+
+def geozero_params(*, dem_shape, first_lat, first_lon, delta_lat, delta_lon, snwe, length, width, r0, dr, prf, t0, wvl,
+                   a=6378137.0, e2=0.0066943799901, nrnglooks=1, nazlooks=1):
+    return OrcGeozeroParams(a, e2, snwe[0], snwe[2], snwe[1], snwe[3], dr, r0, wvl, t0, prf, length, width, nrnglooks,
+                            nazlooks, first_lat, first_lon, delta_lat, delta_lon, dem_shape[1], dem_shape[0])
+
+
+def geozero_grid(p):
+    v = [C.c_int() for _ in range(6)]
+    lib().orc_geozero_grid(C.byref(p), *[C.byref(x) for x in v])
+    return dict(zip(("geo_len", "geo_wid", "min_lat_idx", "max_lat_idx", "min_lon_idx", "max_lon_idx"), [x.value for x in v]))
+
+
+def geozero(*, dem, image, orbit_t, orbit_pos, orbit_vel, method="BILINEAR", side=-1, doppler_coeffs=(0.0,),
+            doppler_mean=0.0, doppler_norm=1.0, nthreads=0, want_indices=True, **grid_kw):
+    """One band through geozero.  image: [length][width] float32 or complex64; returns dict(geo, dem_crop, az_idx, rng_idx, ...)."""
+    dem = np.ascontiguousarray(dem, np.float32)
+    image = np.ascontiguousarray(image)
+    iscomplex = np.iscomplexobj(image)
+    image = image.astype(np.complex64 if iscomplex else np.float32, copy=False)
+    length, width = image.shape
+    p = geozero_params(dem_shape=dem.shape, length=length, width=width, **grid_kw)
+    g = geozero_grid(p)
+    shape = (g["geo_len"], g["geo_wid"])
+    out = np.zeros(shape, image.dtype)
+    crop = np.zeros(shape, np.int16)
+    az = np.full(shape, np.nan) if want_indices else None
+    rg = np.full(shape, np.nan) if want_indices else None
+    orb = Orbit(orbit_t, orbit_pos, orbit_vel)
+    dop = Poly1D(doppler_coeffs, doppler_mean, doppler_norm)
+    res = OrcGeozeroResult()
+    rc = lib().orc_geozero(C.byref(p), _f(dem), C.byref(orb.c), C.byref(dop.c), image.ctypes.data_as(_fp), int(iscomplex),
+                           GEOZERO_METHODS[method.upper()], int(side), out.ctypes.data_as(_fp),
+                           crop.ctypes.data_as(C.POINTER(C.c_int16)), _d(az) if az is not None else None,
+                           _d(rg) if rg is not None else None, C.byref(res), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"orc_geozero failed rc={rc}")
+    r = dict(geo=out, dem_crop=crop, az_idx=az, rng_idx=rg, grid=g)
+    for k, _ in OrcGeozeroResult._fields_:
+        r[k] = getattr(res, k)
+    return r

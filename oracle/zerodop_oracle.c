@@ -1253,3 +1253,316 @@ int orc_geo2rdr(const orc_geo_params *p, const double *latimg, const double *lon
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* geozero: components/zerodop/geozero/src/geozero.f90:1-435            */
+/* ------------------------------------------------------------------ */
+/* Fortran default COMPLEX (2 x real*4) and its promotion to COMPLEX*16 in mixed expressions with real*8.
+ * complex * real and complex / real scale both components (what gfortran emits for a real operand). */
+typedef struct { float re, im; } cx4;
+typedef struct { double re, im; } cx8;
+static inline cx8 c8(cx4 a) { cx8 r = {a.re, a.im}; return r; }
+static inline cx4 c4(cx8 a) { cx4 r = {(float)a.re, (float)a.im}; return r; }
+static inline cx8 c8_scale(cx8 a, double s) { cx8 r = {a.re * s, a.im * s}; return r; }
+static inline cx8 c8_div(cx8 a, double s) { cx8 r = {a.re / s, a.im / s}; return r; }
+static inline cx8 c8_add(cx8 a, cx8 b) { cx8 r = {a.re + b.re, a.im + b.im}; return r; }
+static inline cx4 c4_sub(cx4 a, cx4 b) { cx4 r = {a.re - b.re, a.im - b.im}; return r; }
+static inline cx4 c4_add(cx4 a, cx4 b) { cx4 r = {a.re + b.re, a.im + b.im}; return r; }
+
+/* ifg(width,length): IFG(r, a) = sample r (1-based, range) of line a (1-based, azimuth) */
+#define IFG(r, a) ifg[(size_t)((a) - 1) * (size_t)width + (size_t)((r) - 1)]
+
+/* uniform_interp.f90:46-77 as called from geozeroMethods.F:103-117: bilinear_cx(dy, dx, ifg) */
+static cx4 gz_bilinear_cx(double x, double y, const cx4 *ifg, int width)
+{
+    double x1 = floor(x), x2 = ceil(x), y1 = ceil(y), y2 = floor(y);
+    cx4 q11 = IFG((int)y1, (int)x1), q12 = IFG((int)y2, (int)x1), q21 = IFG((int)y1, (int)x2), q22 = IFG((int)y2, (int)x2);
+    if (y1 == y2 && x1 == x2) return q11;
+    if (y1 == y2)
+        return c4(c8_add(c8_scale(c8(q11), (x2 - x) / (x2 - x1)), c8_scale(c8(q21), (x - x1) / (x2 - x1))));
+    if (x1 == x2)
+        return c4(c8_add(c8_scale(c8(q11), (y2 - y) / (y2 - y1)), c8_scale(c8(q12), (y - y1) / (y2 - y1))));
+    const double den = (x2 - x1) * (y2 - y1);
+    cx8 s = c8_div(c8_scale(c8_scale(c8(q11), (x2 - x)), (y2 - y)), den);
+    s = c8_add(s, c8_div(c8_scale(c8_scale(c8(q21), (x - x1)), (y2 - y)), den));
+    s = c8_add(s, c8_div(c8_scale(c8_scale(c8(q12), (x2 - x)), (y - y1)), den));
+    s = c8_add(s, c8_div(c8_scale(c8_scale(c8(q22), (x - x1)), (y - y1)), den));
+    return c4(s);
+}
+
+/* uniform_interp.f90:203-292 as called from geozeroMethods.F:119-130: bicubic_cx(dy, dx, ifg); all locals are default
+ * COMPLEX, so every assignment rounds to real*4 components; the dzdy column typo (:243-245) is kept */
+static cx4 gz_bicubic_cx(double x, double y, const cx4 *ifg, int width)
+{
+    const int x1 = (int)floor(x), x2 = (int)ceil(x), y1 = (int)floor(y), y2 = (int)ceil(y);
+    cx4 zz[4], dzdx[4], dzdy[4], dzdxy[4], q[16], cl[16], c[4][4];
+    zz[0] = IFG(y1, x1);
+    zz[3] = IFG(y2, x1);
+    zz[1] = IFG(y1, x2);
+    zz[2] = IFG(y2, x2);
+#define HALF(a) c4(c8_div(c8(a), 2.0))
+    dzdx[0] = HALF(c4_sub(IFG(y1, x1 + 1), IFG(y1, x1 - 1)));
+    dzdx[1] = HALF(c4_sub(IFG(y1, x2 + 1), IFG(y1, x2 - 1)));
+    dzdx[2] = HALF(c4_sub(IFG(y2, x2 + 1), IFG(y2, x2 - 1)));
+    dzdx[3] = HALF(c4_sub(IFG(y2, x1 + 1), IFG(y2, x1 - 1)));
+    dzdy[0] = HALF(c4_sub(IFG(y1 + 1, x1), IFG(y1 - 1, x1)));
+    dzdy[1] = HALF(c4_sub(IFG(y1 + 1, x2 + 1), IFG(y1 - 1, x2)));
+    dzdy[2] = HALF(c4_sub(IFG(y2 + 1, x2 + 1), IFG(y2 - 1, x2)));
+    dzdy[3] = HALF(c4_sub(IFG(y2 + 1, x1 + 1), IFG(y2 - 1, x1)));
+#undef HALF
+#define CROSS(yy, xx) c4(c8_scale(c8(c4_add(c4_sub(c4_sub(IFG((yy) + 1, (xx) + 1), IFG((yy) - 1, (xx) + 1)), IFG((yy) + 1, (xx) - 1)), \
+                                            IFG((yy) - 1, (xx) - 1))), 0.25))
+    dzdxy[0] = CROSS(y1, x1);
+    dzdxy[3] = CROSS(y2, x1);
+    dzdxy[1] = CROSS(y1, x2);
+    dzdxy[2] = CROSS(y2, x2);
+#undef CROSS
+    for (int i = 0; i < 4; i++) {
+        q[i] = zz[i];
+        q[i + 4] = dzdx[i];
+        q[i + 8] = dzdy[i];
+        q[i + 12] = dzdxy[i];
+    }
+    for (int i = 0; i < 16; i++) {
+        cx4 qq = {0.f, 0.f};
+        for (int k = 0; k < 16; k++) qq = c4(c8_add(c8(qq), c8_scale(c8(q[k]), WT_FLAT[k * 16 + i])));
+        cl[i] = qq;
+    }
+    int l = 0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) c[i][j] = cl[l++];
+    const double t = (x - x1), u = (y - y1);
+    cx4 r = {0.f, 0.f};
+    for (int i = 3; i >= 0; i--) {
+        /* bicubic_cx = t*bicubic_cx+((c(i,4)*u+c(i,3))*u+c(i,2))*u+c(i,1): (t*r + (...)*u) + c(i,1) */
+        cx8 h = c8_add(c8_scale(c8(c[i][3]), u), c8(c[i][2]));
+        h = c8_scale(c8_add(c8_scale(h, u), c8(c[i][1])), u);
+        r = c4(c8_add(c8_add(c8_scale(c8(r), t), h), c8(c[i][0])));
+    }
+    return r;
+}
+
+/* uniform_interp.f90:456-484 through geozeroMethods.F:91-101 (intp_sinc: i_xx = i_x - 1, i_yy = i_y - 1) */
+static cx4 gz_sinc_cx(const cx4 *ifg, const float *intarr, int intpx, int intpy, double frpx, double frpy, int width, int length)
+{
+    const int idec = SINC_SUB, ilen = SINC_LEN;
+    cx4 acc = {0.f, 0.f};
+    if ((intpx >= ilen - 1 && intpx < width) && (intpy >= ilen - 1 && intpy < length)) {
+        int ifracx = (int)(frpx * idec), ifracy = (int)(frpy * idec);
+        ifracx = ifracx < 0 ? 0 : (ifracx > idec - 1 ? idec - 1 : ifracx);
+        ifracy = ifracy < 0 ? 0 : (ifracy > idec - 1 ? idec - 1 : ifracy);
+        double fweightsum = 0.0;
+        for (int k = 0; k < ilen; k++)
+            for (int m = 0; m < ilen; m++) {
+                const float fw4 = intarr[k + ifracx * ilen] * intarr[m + ifracy * ilen];
+                const double fweight = fw4;
+                /* arrin is 0-based: arrin(a,b) = ifg(a+1,b+1) */
+                acc = c4(c8_add(c8(acc), c8_scale(c8(IFG(intpx - k + 1, intpy - m + 1)), fweight)));
+                fweightsum = fweightsum + fweight;
+            }
+        acc = c4(c8_div(c8(acc), fweightsum));
+    }
+    return acc;
+}
+
+void orc_geozero_grid(const orc_geozero_params *p, int *geo_len, int *geo_wid, int *min_lat_idx, int *max_lat_idx,
+                      int *min_lon_idx, int *max_lon_idx)
+{
+    const double pi = 4.0 * atan(1.0);
+    const double deg2rad = pi / 180.0;
+    /* :146-149, :163-170: real*8 -> integer assignment truncates */
+    const double dlonr = p->dlon * deg2rad, dlatr = p->dlat * deg2rad;
+    const double lon_firstr = p->lon_first * deg2rad, lat_firstr = p->lat_first * deg2rad;
+    const double min_latr = p->min_lat * deg2rad, max_latr = p->max_lat * deg2rad;
+    const double min_lonr = p->min_lon * deg2rad, max_lonr = p->max_lon * deg2rad;
+    *min_lat_idx = (int)((min_latr - lat_firstr) / dlatr + 1);
+    *min_lon_idx = (int)((min_lonr - lon_firstr) / dlonr);
+    *max_lat_idx = (int)((max_latr - lat_firstr) / dlatr);
+    *max_lon_idx = (int)((max_lonr - lon_firstr) / dlonr + 1);
+    *geo_len = *min_lat_idx - *max_lat_idx;
+    *geo_wid = *max_lon_idx - *min_lon_idx;
+}
+
+int orc_geozero(const orc_geozero_params *p, const float *dem_full, const orc_orbit *orb, const orc_poly1d *dopAcc,
+                const float *in, int iscomplex, int method, int lookSide, float *out, int16_t *dem_crop,
+                double *oaz, double *orng, orc_geozero_result *res, int nthreads)
+{
+    const double pi = 4.0 * atan(1.0);
+    const double deg2rad = pi / 180.0;
+    const double BAD_VALUE = -10000.0; /* :70 */
+    const int width = p->width, length = p->length, demwidth = p->demwidth, demlength = p->demlength;
+    float f_delay; /* geozeroMethods.F:66-79 */
+    if (method == ORC_SINC) f_delay = SINC_LEN / 2.0f;
+    else if (method == ORC_BILINEAR) f_delay = 2.0f;
+    else if (method == ORC_BICUBIC) f_delay = 3.0f;
+    else if (method == ORC_NEAREST) f_delay = 2.0f;
+    else return -1;
+    if (orb->nvec < 4) return -2;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    const float *fintp = method == ORC_SINC ? sinc_table() : NULL;
+    /* :126-139 */
+    const double tstart = p->t0;
+    const double dtaz = p->nazlooks / p->prf;
+    const double tend = p->t0 + (length - 1) * dtaz;
+    const double tmid = 0.5 * (tstart + tend);
+    const double rngstart = p->rho0;
+    const double dmrg = p->nrnglooks * p->drho;
+    const double dlonr = p->dlon * deg2rad, dlatr = p->dlat * deg2rad;
+    const double lon_firstr = p->lon_first * deg2rad, lat_firstr = p->lat_first * deg2rad;
+    int geo_len, geo_wid, min_lat_idx, max_lat_idx, min_lon_idx, max_lon_idx;
+    orc_geozero_grid(p, &geo_len, &geo_wid, &min_lat_idx, &max_lat_idx, &min_lon_idx, &max_lon_idx);
+    if (geo_len <= 0 || geo_wid <= 0) return -3;
+
+    /* the band as COMPLEX ifg(width,length) (geozeroReadWrite.F:50-68) */
+    cx4 *ifg = malloc(sizeof(cx4) * (size_t)width * (size_t)length);
+    if (!ifg) return -4;
+    for (size_t i = 0; i < (size_t)width * (size_t)length; i++) {
+        ifg[i].re = iscomplex ? in[2 * i] : in[i];
+        ifg[i].im = iscomplex ? in[2 * i + 1] : 0.f;
+    }
+
+    /* doppler polynomials :196-224 (same construction as geo2rdr) */
+    double fd_c[64], fdd_c[64];
+    if (dopAcc->order > 62) { free(ifg); return -6; }
+    orc_poly1d fdvsrng = {dopAcc->order, p->rho0 + dopAcc->mean * p->drho, dopAcc->norm * p->drho, fd_c};
+    for (int k = 1; k <= dopAcc->order + 1; k++) {
+        double temp = dopAcc->coeffs[k - 1];
+        temp = temp * p->prf;
+        fd_c[k - 1] = temp;
+    }
+    orc_poly1d fddotvsrng;
+    fddotvsrng.coeffs = fdd_c;
+    if (fdvsrng.order == 0) {
+        fddotvsrng.order = 0;
+        fddotvsrng.mean = 0.0;
+        fddotvsrng.norm = 1.0;
+        fdd_c[0] = 0.0;
+    } else {
+        fddotvsrng.order = fdvsrng.order - 1;
+        fddotvsrng.mean = fdvsrng.mean;
+        fddotvsrng.norm = fdvsrng.norm;
+        for (int k = 1; k <= dopAcc->order; k++) {
+            double temp = fd_c[k];
+            temp = k * temp / fdvsrng.norm;
+            fdd_c[k - 1] = temp;
+        }
+    }
+    /* :229-236 (geozero always interpolates with the Hermite scheme: interpolateWGS84Orbit_f) */
+    double xyz_mid[3], vel_mid[3];
+    if (orc_interp_hermite(orb, tmid, xyz_mid, vel_mid) != 0) { free(ifg); return -7; }
+
+    long long numOutsideDEM = 0, numOutsideImage = 0, cnt = 0, total_iters = 0;
+    const int nout = iscomplex ? 2 : 1;
+    for (int line = 1; line <= geo_len; line++) { /* :244 */
+        float *orow = out + (size_t)(line - 1) * geo_wid * nout;
+        int16_t *drow = dem_crop ? dem_crop + (size_t)(line - 1) * geo_wid : NULL;
+        double *azrow = oaz ? oaz + (size_t)(line - 1) * geo_wid : NULL;
+        double *rgrow = orng ? orng + (size_t)(line - 1) * geo_wid : NULL;
+        for (int i = 0; i < geo_wid * nout; i++) orow[i] = 0.f;
+        if (drow) for (int i = 0; i < geo_wid; i++) drow[i] = 0;
+        if (azrow) for (int i = 0; i < geo_wid; i++) azrow[i] = NAN;
+        if (rgrow) for (int i = 0; i < geo_wid; i++) rgrow[i] = NAN;
+        const int idxlat = max_lat_idx + (line - 1);
+        if (idxlat < 0 || idxlat > (demlength - 1)) { /* :250-253 */
+            numOutsideDEM += demwidth;
+            continue;
+        }
+        const float *dem = dem_full + (size_t)idxlat * demwidth; /* getLine(demAccessor, dem, idxlat+1) */
+#pragma omp parallel for schedule(static) reduction(+ : numOutsideImage, cnt, total_iters)
+        for (int pixel = 1; pixel <= geo_wid; pixel++) {
+            cx4 z = {0.f, 0.f};
+            double llh[3], xyz[3], satx[3], satv[3], dr[3], look_side_vec[3];
+            double tline, tprev, rngpix = 0.0;
+            int skip = 0;
+            llh[2] = 0.0;
+            llh[0] = lat_firstr + idxlat * dlatr;
+            const int idxlon = min_lon_idx + (pixel - 1);
+            llh[1] = lon_firstr + idxlon * dlonr;
+            if (!(idxlon < 0 || idxlon > (demwidth - 1))) {
+                llh[2] = dem[idxlon];
+                if (llh[2] < -1500) skip = 1; /* bad SRTM pixels :290-292 */
+            }
+            if (!skip) {
+                orc_latlon(p->major, p->e2, xyz, llh, 1);
+                tline = tmid;
+                for (int i = 0; i < 3; i++) { satx[i] = xyz_mid[i]; satv[i] = vel_mid[i]; }
+                /* look side test :306-320 */
+                for (int i = 0; i < 3; i++) dr[i] = xyz[i] - satx[i];
+                v_cross(dr, satv, look_side_vec);
+                const double look_side_sign = v_dot(look_side_vec, satx);
+                const int pixel_side = look_side_sign > 0 ? -1 : 1;
+                if (pixel_side != lookSide) skip = 1;
+            }
+            if (!skip) {
+                for (int k = 1; k <= 21; k++) { /* :322-356 */
+                    total_iters++;
+                    tprev = tline;
+                    for (int i = 0; i < 3; i++) dr[i] = xyz[i] - satx[i];
+                    rngpix = v_norm(dr);
+                    double dopfact = v_dot(dr, satv) / rngpix;
+                    double fdop = 0.5 * p->wvl * orc_eval_poly1d(&fdvsrng, rngpix);
+                    double fdopder = 0.5 * p->wvl * orc_eval_poly1d(&fddotvsrng, rngpix);
+                    double c1 = dopfact - fdop;
+                    double c2 = v_dot(satv, satv) / rngpix;
+                    double c3 = dopfact * (fdop / rngpix + fdopder);
+                    tline = tline + c1 / (c2 - c3);
+                    int stat = orc_interp_hermite(orb, tline, satx, satv);
+                    if (stat != 0) {
+                        tline = BAD_VALUE;
+                        rngpix = BAD_VALUE;
+                        break;
+                    }
+                    if (fabs(tline - tprev) < 5.0e-7) break;
+                }
+                const double az_idx = ((tline - tstart) / dtaz) + 1;
+                const double rng_idx = ((rngpix - rngstart) / dmrg) + 1;
+                if (rng_idx <= f_delay || rng_idx >= width - f_delay || az_idx <= f_delay || az_idx >= length - f_delay) {
+                    numOutsideImage++;
+                } else {
+                    cnt++;
+                    const int int_rdx = (int)(rng_idx + f_delay);
+                    const double fr_rdx = rng_idx + f_delay - int_rdx;
+                    const int int_rdy = (int)(az_idx + f_delay);
+                    const double fr_rdy = az_idx + f_delay - int_rdy;
+                    if (azrow) azrow[pixel - 1] = az_idx;
+                    if (rgrow) rgrow[pixel - 1] = rng_idx;
+                    if (method == ORC_SINC) {
+                        z = gz_sinc_cx(ifg, fintp, int_rdx - 1, int_rdy - 1, fr_rdx, fr_rdy, width, length);
+                    } else if (method == ORC_BILINEAR) {
+                        const double dx = int_rdx + fr_rdx - f_delay, dy = int_rdy + fr_rdy - f_delay;
+                        z = gz_bilinear_cx(dy, dx, ifg, width);
+                    } else if (method == ORC_BICUBIC) {
+                        const double dx = int_rdx + fr_rdx - f_delay, dy = int_rdy + fr_rdy - f_delay;
+                        z = gz_bicubic_cx(dy, dx, ifg, width);
+                    } else {
+                        const int dx = (int)lround(int_rdx + fr_rdx - f_delay), dy = (int)lround(int_rdy + fr_rdy - f_delay);
+                        z = IFG(dx, dy);
+                    }
+                }
+            }
+            if (iscomplex) {
+                orow[2 * (pixel - 1)] = z.re;
+                orow[2 * (pixel - 1) + 1] = z.im;
+            } else {
+                orow[pixel - 1] = z.re; /* writeRealLine: real(carr) */
+            }
+            if (drow) drow[pixel - 1] = (int16_t)llh[2]; /* dem_crop is integer*2 (:22) */
+        }
+    }
+    free(ifg);
+    if (res) {
+        res->geowidth = geo_wid;
+        res->geolength = geo_len;
+        res->geomin_lat = (p->lat_first + min_lat_idx * p->dlat); /* :419-422 */
+        res->geomax_lat = (p->lat_first + max_lat_idx * p->dlat);
+        res->geomin_lon = (p->lon_first + min_lon_idx * p->dlon);
+        res->geomax_lon = (p->lon_first + max_lon_idx * p->dlon);
+        res->num_outside_dem = numOutsideDEM;
+        res->num_outside_image = numOutsideImage;
+        res->num_valid = cnt;
+        res->total_iters = total_iters;
+    }
+    return 0;
+}
