@@ -247,6 +247,7 @@ typedef struct {
                                                                    last geocoded band)                        */
     long long iterations;                                  /* fixed-point steps summed over pixels        */
     float ms_setup;   /* device time: DEM crop upload + orbit polynomials + the per-pixel solve            */
+    float ms_solve;   /* ... of which the per-pixel solve kernels alone                                     */
     float ms_kernels; /* device time of the last geocode call's gather kernels                              */
     float ms_total;
     int gpu_launches;

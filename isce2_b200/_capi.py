@@ -100,7 +100,8 @@ class GeozeroResult(C.Structure):
     _fields_ = [("geo_width", C.c_int), ("geo_length", C.c_int), ("geo_min_lat", C.c_double), ("geo_max_lat", C.c_double),
                 ("geo_min_lon", C.c_double), ("geo_max_lon", C.c_double), ("num_outside_dem", C.c_longlong),
                 ("num_outside_image", C.c_longlong), ("num_valid", C.c_longlong), ("iterations", C.c_longlong),
-                ("ms_setup", C.c_float), ("ms_kernels", C.c_float), ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
+                ("ms_setup", C.c_float), ("ms_solve", C.c_float), ("ms_kernels", C.c_float), ("ms_total", C.c_float),
+                ("gpu_launches", C.c_int)]
 
 
 GEOZERO_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3}
@@ -473,10 +474,12 @@ def geozero_params(*, dem_shape, first_lat, first_lon, delta_lat, delta_lon, snw
                          nazlooks, first_lat, first_lon, delta_lat, delta_lon, dem_shape[1], dem_shape[0], device)
 
 
-def geozero_grid(params):
+def geozero_grid(params, require_nonempty=False):
     w, l = C.c_int(), C.c_int()
     e = _errbuf()
     _check(lib().b200_geozero_grid(C.byref(params), C.byref(w), C.byref(l), e, 512), e)
+    if require_nonempty and (l.value < 1 or w.value < 1):
+        raise B200Error(-1, f"empty output grid ({l.value} lines x {w.value} samples): check the bounding box")
     return l.value, w.value
 
 
@@ -558,7 +561,7 @@ def geozero_run(params, dem, orbit_t, orbit_pos, orbit_vel, image, method="BILIN
     orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
     dop = make_poly1d(keep, doppler_coeffs, doppler_mean, doppler_norm)
     a, is_complex = _image_arg(image, params.width, params.length, nbands, scheme)
-    gl, gw = geozero_grid(params)
+    gl, gw = geozero_grid(params, require_nonempty=True)
     sch = scheme.upper()
     shape = ((gl, gw) if nbands == 1 else (gl, nbands, gw) if sch == "BIL" else (gl, gw, nbands) if sch == "BIP" else (nbands, gl, gw))
     if out is None:

@@ -1140,8 +1140,8 @@ struct b200_geozero_plan {
     void *d_img = nullptr, *d_out = nullptr;
     size_t img_bytes = 0, out_bytes = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float ms_setup = 0.f, ms_kernels = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+    float ms_setup = 0.f, ms_solve = 0.f, ms_kernels = 0.f;
     long long num_outside_dem = 0, num_outside_image = 0, num_valid = 0, iterations = 0;
     int launches = 0;
 
@@ -1153,6 +1153,7 @@ struct b200_geozero_plan {
         dfree(d_sinc); dfree(d_img); dfree(d_out);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_mid) cudaEventDestroy(ev_mid);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -1187,6 +1188,7 @@ static int geozero_plan_build(b200_geozero_plan *pl, const void *dem, int dem_dt
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&pl->ev0));
     CK(cudaEventCreate(&pl->ev1));
+    CK(cudaEventCreate(&pl->ev_mid));
     cudaStream_t s = pl->stream;
     CK(cudaEventRecord(pl->ev0, s));
 
@@ -1303,6 +1305,7 @@ static int geozero_plan_build(b200_geozero_plan *pl, const void *dem, int dem_dt
     CK(dmalloc(&pl->G.col_sc, sizeof(double) * 2 * (size_t)g.geo_wid));
     CK(dmalloc(&pl->d_stats, sizeof(GeozeroStats)));
     CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeozeroStats), s));
+    CK(cudaEventRecord(pl->ev_mid, s));
     launch_geozero_axes(C, pl->G, s);
     if (launch_geozero_solve(C, pl->op, pl->G, pl->d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the geozero solve kernel");
@@ -1313,6 +1316,7 @@ static int geozero_plan_build(b200_geozero_plan *pl, const void *dem, int dem_dt
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&pl->ms_setup, pl->ev0, pl->ev1));
+    CK(cudaEventElapsedTime(&pl->ms_solve, pl->ev_mid, pl->ev1));
     pl->iterations = (long long)st.iterations;
     if (pl->d_raw) {
         dfree(pl->d_raw);
@@ -1431,6 +1435,7 @@ extern "C" int b200_geozero_plan_fetch(b200_geozero_plan *pl, int16_t *dem_crop,
         res->num_valid = pl->num_valid;
         res->iterations = pl->iterations;
         res->ms_setup = pl->ms_setup;
+        res->ms_solve = pl->ms_solve;
         res->ms_kernels = pl->ms_kernels;
         res->ms_total = 0.f;
         res->gpu_launches = pl->launches;

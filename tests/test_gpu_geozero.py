@@ -102,7 +102,7 @@ def test_geozero_multiband_schemes_native_doppler_and_left_looking():
               doppler_coeffs=dop, **_grid_kw(sc, snwe))
     o0 = orc.geozero(image=b0, method="BILINEAR", **kw)
     o1 = orc.geozero(image=b1, method="BILINEAR", **kw)
-    assert o0["num_valid"] > 0.5 * o0["geo"].size
+    assert o0["num_valid"] > 0.15 * o0["geo"].size  # the footprint is a tilted strip inside its lat/lon box
     p = _gparams(sc, snwe, sc.dem)
     for scheme, stack, axis in (("BIL", np.stack([b0, b1], axis=1), 1), ("BIP", np.stack([b0, b1], axis=2), 2),
                                 ("BSQ", np.stack([b0, b1], axis=0), 0)):
@@ -113,9 +113,10 @@ def test_geozero_multiband_schemes_native_doppler_and_left_looking():
         _compare(np.ascontiguousarray(g1), o1["geo"], b1, "BILINEAR")
         assert np.array_equal(r["dem_crop"], o0["dem_crop"])
         assert abs(r["num_valid"] - o1["num_valid"]) <= 2
-    # zero-Doppler geometry of the same pass differs: the native-Doppler terms are live
+    # the native-Doppler terms are live: the zero-Doppler solution of this squinted pass lies a hundred lines away
+    # (fd * wvl * R / (2 v^2) in seconds), which moves the footprint inside the box
     z = orc.geozero(image=b0, method="BILINEAR", **{**kw, "doppler_coeffs": (0.0,)})
-    assert np.nanmax(np.abs(z["az_idx"] - o0["az_idx"])) > 1.0
+    assert abs(z["num_valid"] - o0["num_valid"]) > 0.05 * o0["num_valid"]
 
 
 def test_geozero_edges_voids_int16_dem_and_errors():

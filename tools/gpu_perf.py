@@ -59,7 +59,45 @@ def parity(L=96, W=8192):
     return rep
 
 
+def geozero_perf(lines=13500, width=25000, reps=3):
+    """Geocode a full-swath product (float32 and complex64) onto the 1-arcsec DEM grid under the C2 footprint."""
+    sc = synth.make_scene(lines, width)
+    # the scene builder pads the DEM by 0.2 deg around the footprint: geocode the DEM's inner part
+    nlat, nlon = sc.dem.shape
+    snwe = (sc.first_lat + (nlat - 1 - 600) * sc.delta_lat, sc.first_lat + 600 * sc.delta_lat,
+            sc.first_lon + 600 * sc.delta_lon, sc.first_lon + (nlon - 1 - 600) * sc.delta_lon)
+    p = _capi.geozero_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                             delta_lon=sc.delta_lon, snwe=snwe, length=lines, width=width, r0=sc.r0, dr=sc.dr, prf=sc.prf,
+                             t0=sc.t0, wvl=sc.wvl, side=sc.side)
+    _capi.GeozeroPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel).close()  # module load, workspace cache
+    t0 = time.perf_counter()
+    plan = _capi.GeozeroPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel)
+    t_plan = time.perf_counter() - t0
+    r0 = plan.fetch()
+    npx = r0["geo_length"] * r0["geo_width"]
+    out = {"grid": [r0["geo_length"], r0["geo_width"]], "Mpx": npx / 1e6, "ms_setup": round(r0["ms_setup"], 3), "ms_solve": round(r0["ms_solve"], 3),
+           "plan_wall_ms": round(1e3 * t_plan, 1), "iters_per_px": round(r0["iterations"] / npx, 3)}
+    rng = np.random.default_rng(1)
+    real = rng.normal(size=(lines, width)).astype(np.float32)
+    for name, img in (("f32", real), ("c64", (real + 1j * real[::-1]).astype(np.complex64))):
+        for m in ("NEAREST", "BILINEAR", "BICUBIC", "SINC"):
+            best, wall = 1e30, 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                plan.geocode(img, method=m)
+                wall = min(wall, time.perf_counter() - t0)
+                best = min(best, plan.ms_kernels)
+            r = plan.fetch()
+            out[f"{name}_{m}"] = {"ms_gather": round(best, 3), "wall_ms": round(1e3 * wall, 1), "valid_frac": round(r["num_valid"] / npx, 3),
+                                  "gpix_s": round(npx / best / 1e6, 2)}
+    plan.close()
+    return out
+
+
 if __name__ == "__main__":
+    if "--geozero" in sys.argv:
+        print(json.dumps({"geozero": geozero_perf()}), flush=True)
+        sys.exit(0)
     tag = os.environ.get("B200GEOM_LIB", "default")
     print(json.dumps({"lib": tag, "perf": perf()}), flush=True)
     if "--rough" in sys.argv:
