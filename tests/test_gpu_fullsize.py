@@ -91,3 +91,35 @@ def test_c2_full_swath_round_trip_and_line_block_identity():
     assert np.abs(strip["hgt"] - c["hgt"]).max() < pu.TOL_HGT_M
     assert (np.abs(strip["lat"] - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2 and np.abs(strip["lat"] - c["lat"]).max() < 2e-7
     assert (np.abs(strip["lon"] - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= 2 and np.abs(strip["lon"] - c["lon"]).max() < 2e-7
+
+
+def test_c3_nisar_frame_round_trip_at_full_size():
+    """BASELINE configs[3]: 60000 x 25000 (1.5 Gpixel), left-looking, native Doppler, Legendre orbit, BIQUINTIC +
+    incidence + mask: ~90 GB resident on one B200.  Same closure property as above, with the Doppler polynomial of the
+    scene handed to geo2rdr in its own convention (cycles / PRF versus range pixel, Geo2rdr.py:264-297)."""
+    sc = synth.config_c3()
+    assert (sc.length, sc.width) == (60000, 25000)
+    p = _capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                          delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
+                          side=sc.side, peg_heading=sc.peg_heading, dem_method="BIQUINTIC", orbit_method="LEGENDRE")
+    tp = _capi.TopoPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]],
+                        want_los=True, want_inc=True, want_mask=True)
+    ms = tp.execute()
+    gp = _capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0, dr=sc.dr, prf=sc.prf,
+                          t0=sc.t0, wvl=sc.wvl, side=sc.side, orbit_method="LEGENDRE", out_f32=True)
+    g = _capi.GeoPlan(gp, topo_plan=tp)
+    dop = [d / sc.prf for d in sc.doppler_coeffs[0]]
+    g.execute(gp, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, doppler_coeffs=dop, want=("azoff",))
+    r = g.fetch()
+    n = sc.length * sc.width
+    bad = r["azoff"] == np.float32(-999999.0)
+    assert int(bad.sum()) == n - r["num_valid"] and not bad[1:-1, 1:-1].any()
+    assert float(np.abs(r["azoff"][~bad]).max()) < pu.TOL_OFFSET_PX
+    g.close()
+    res = _capi.TopoResult()
+    import ctypes as C
+    e = C.create_string_buffer(512)
+    _capi._check(_capi.lib().b200_topo_plan_fetch(tp.handle, None, C.byref(res), e, 512), e)
+    tp.close()
+    assert res.converged > 0.999 * n and 3.0 < res.iterations / n < 12.0
+    print("c3 topo device ms", ms)
