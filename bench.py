@@ -101,54 +101,92 @@ class Ranks:
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every 10 ms from a thread (the timed
+    region of a multi-GPU run lasts ~0.1 s, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device):
-        self.rows = []
+        self.rows = []   # (time, sm_mhz, max_mhz, power_w, set(reasons))
         self.proc = None
+        self.stop_flag = False
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates by PCI bus id; CUDA_VISIBLE_DEVICES is not set by torchrun, so ordinals agree
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-i", str(device), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    mask = 0
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                except Exception:
+                    pw = 0.0
+                self.rows.append((time.time(), sm, self.max_mhz, pw, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t_lo, t_hi):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t_lo or ts > t_hi + 0.2:
-                continue
-            parts = [p.strip() for p in line.split(",")]
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
+                self.rows.append((time.time(), float(parts[0]), float(parts[1]), float(parts[2]),
+                                  {nm for nm, v in zip(self.NAMES, parts[3:7]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self, t_lo, t_hi):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        rows = [r for r in self.rows if t_lo <= r[0] <= t_hi + 0.05]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"], "source": self.source}
+        reasons = set()
+        for r in rows:
+            reasons |= r[4]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "power_w_max": float(max(r[3] for r in rows)), "samples": len(rows), "reasons": sorted(reasons),
+                "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -368,7 +406,7 @@ def run_b200(args, ranks):
         return r
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(args.warmup, 2)):
         e2e_step()
     ranks.barrier()
     e2e_times = []

@@ -155,26 +155,50 @@ k_geo2rdr(const __grid_constant__ GeoConst C, OrbitView orb_g, int line0, int nl
 // The reference iterates  t <- t - fn/fnprime  with fnprime = -v.v + (fdop/r + fdop')(dr.v): the acceleration term
 // is multiplied by zero (geo2rdr.f90:271), so it converges linearly (ratio ~0.1) and stops at |dt| < 5e-9 s, i.e. up
 // to ~6e-10 s (3e-7 azimuth pixels) short of the root of fn(t) = dr.v - fdop(r) r.  This kernel solves the same
-// equation for the same root with the true derivative (acceleration from the orbit polynomial) until |dt| < 1e-10 s;
-// its first step is the reference's own first step so that the reference's out-of-span test on the first iterate
-// (geo2rdr.f90:287-291, the only iterate that can overshoot by seconds) is reproduced.  Final range / validity tests
-// are the reference's (:308-329), evaluated at the converged state.
+// equation for the same root with the true derivative (acceleration from the orbit polynomial; the mid-scene
+// finite-difference acceleration of :206 for the first step) until |dt| < 1e-10 s: 3 steps instead of the reference's
+// 9-11.  The reference's own first iterate is still formed, because it is the only one that can overshoot the orbit
+// span by seconds and the reference invalidates the pixel when it does (geo2rdr.f90:287-291).  Final range / validity
+// tests are the reference's (:308-329), evaluated at the converged state.
+// Each thread walks kGeoPixPerThread pixels of its line (stride kGeoBlock, so that a warp's loads and stores stay
+// coalesced) and loads the next pixel's lat / lon / hgt before it solves the current one: with one pixel per thread
+// the warps of a CTA all sat on the DRAM latency of their three input loads at the same moment (ncu: 43 % of the stall
+// samples on the first use of lat / lon / hgt).
+constexpr int kGeoPixPerThread = 4;
+
 template <int METHOD, typename T>
 __global__ void __launch_bounds__(kGeoBlock)
 k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, int nlines, GeoLayers L, GeoStats *stats)
 {
-    const int bpl = (C.demwidth + kGeoBlock - 1) / kGeoBlock;
+    constexpr int kSpan = kGeoBlock * kGeoPixPerThread;
+    const int bpl = (C.demwidth + kSpan - 1) / kSpan;
     const int row = blockIdx.x / bpl;
-    const int pix = (blockIdx.x - row * bpl) * blockDim.x + threadIdx.x;
+    const int pix0 = (blockIdx.x - row * bpl) * kSpan + threadIdx.x;
+    const size_t rowoff = (size_t)row * (size_t)C.demwidth;
+    const int line = line0 + row;
+    const double BAD_VALUE = (double)(-999999.0f);
+    const double t_lo = __ldg(op.t), t_hi = __ldg(op.t + op.n - 1);
+    const double inv_fd = C.fd.order ? rcp_n(C.fd.norm) : 0.0, inv_fdd = C.fdd.order ? rcp_n(C.fdd.norm) : 0.0;
     unsigned int n_out = 0, n_valid = 0, n_conv = 0, n_it = 0;
-    if (pix < C.demwidth) {
-        const double BAD_VALUE = (double)(-999999.0f);
-        const int line = line0 + row;
-        const size_t o = (size_t)row * (size_t)C.demwidth + (size_t)pix;
+    double nlat = 0.0, nlon = 0.0, nhgt = 0.0;
+    if (pix0 < C.demwidth) {
+        nlat = L.lat[rowoff + pix0];
+        nlon = L.lon[rowoff + pix0];
+        nhgt = L.hgt[rowoff + pix0];
+    }
+#pragma unroll 1
+    for (int j = 0; j < kGeoPixPerThread; j++) {
+        const int pix = pix0 + j * kGeoBlock;
+        if (pix >= C.demwidth) break;
+        const double lat = nlat, lon = nlon, hgt = nhgt;
+        if (j + 1 < kGeoPixPerThread && pix + kGeoBlock < C.demwidth) { // prefetch the next pixel's inputs
+            nlat = L.lat[rowoff + pix + kGeoBlock];
+            nlon = L.lon[rowoff + pix + kGeoBlock];
+            nhgt = L.hgt[rowoff + pix + kGeoBlock];
+        }
+        const size_t o = rowoff + (size_t)pix;
         double azt = BAD_VALUE, rgm = BAD_VALUE, rgoff = BAD_VALUE, azoff = BAD_VALUE;
-        const Vec3 xyz = llh_to_xyz(C.elp, L.lat[o] * C.deg2rad, L.lon[o] * C.deg2rad, L.hgt[o]);
-        const double t_lo = __ldg(op.t), t_hi = __ldg(op.t + op.n - 1);
-        const double inv_fd = C.fd.order ? rcp_n(C.fd.norm) : 0.0, inv_fdd = C.fdd.order ? rcp_n(C.fdd.norm) : 0.0;
+        const Vec3 xyz = llh_to_xyz(C.elp, lat * C.deg2rad, lon * C.deg2rad, hgt);
         double tline = C.tmid, rngpix = 0.0;
         OrbState S;
         S.x = C.xyz_mid;
@@ -190,10 +214,18 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
             const double fdop = 0.5 * C.wvl * poly1d_fast(C.fd, inv_fd, rngpix);
             const double fdopder = 0.5 * C.wvl * poly1d_fast(C.fdd, inv_fdd, rngpix);
             const double fn = dopfact - fdop * rngpix;
-            // k == 1: the reference's derivative (no acceleration term); afterwards the true one
-            const double c1 = (k == 1 ? 0.0 : dot(S.a, dr)) - dot(S.v, S.v);
+            const double vv = dot(S.v, S.v);
             const double c2 = div_n(fdop, rngpix) + fdopder;
-            const double tnew = tline - div_n(fn, c1 + c2 * dopfact);
+            if (k == 1) {
+                // the reference's own first iterate (derivative without the acceleration term, geo2rdr.f90:271) is the only
+                // one that can overshoot the orbit span by seconds: its out-of-span test (:287-291) is reproduced on it
+                const double tref = tline - div_n(fn, (0.0 - vv) + c2 * dopfact);
+                if ((tref < t_lo) || (tref > t_hi) || !(tref == tref)) {
+                    bad = true;
+                    break;
+                }
+            }
+            const double tnew = tline - div_n(fn, (dot(S.a, dr) - vv) + c2 * dopfact); // true Newton step
             const double step = tnew - tline;
             tline = tnew;
             if ((tline < t_lo) || (tline > t_hi) || !(tline == tline)) { // interpolator stat != 0 (orbit.c:224-233)
@@ -202,7 +234,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
             }
             poly_state<METHOD>(op, tline, S);
             if (fabs(step) < 1.0e-10) {
-                n_conv = 1;
+                n_conv++;
                 break;
             }
         }
@@ -230,9 +262,9 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
                 }
             }
         }
-        if (outside) n_out = 1;
+        if (outside) n_out++;
         else {
-            n_valid = 1;
+            n_valid++;
             rgm = rngpix;
             azt = tline;
             rgoff = div_n(rngpix - C.rngstart, C.dmrg) - 1.0 * ((pix + 1) - 1);
@@ -278,7 +310,8 @@ int launch_geo2rdr(const GeoConst &C, const OrbitView &orb, int line0, int nline
 int launch_geo2rdr_poly(const GeoConst &C, const OrbitPolyView &op, int line0, int nlines, const GeoLayers &L, int out_f32,
                         GeoStats *stats, cudaStream_t s)
 {
-    const long long nblk = (long long)((C.demwidth + kGeoBlock - 1) / kGeoBlock) * nlines;
+    constexpr int kSpan = kGeoBlock * kGeoPixPerThread;
+    const long long nblk = (long long)((C.demwidth + kSpan - 1) / kSpan) * nlines;
     if (nblk > 0x7fffffffLL) return -2;
     const unsigned g = (unsigned)nblk;
     if (op.method == 0) {
