@@ -265,9 +265,7 @@ struct b200_topo_plan {
         dfree(scr.cs);
         dfree(scr.lats);
         dfree(scr.lons);
-        dfree(scr.rho);
         dfree(scr.orng);
-        dfree(scr.ctr);
         dfree(scr.ctr_sorted);
         dfree(scr.oflag);
         if (ev0) cudaEventDestroy(ev0);
@@ -489,9 +487,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
         CK(dmalloc(&pl->scr.cs, sizeof(double) * (size_t)g * p.width));
         CK(dmalloc(&pl->scr.lats, sizeof(double) * (size_t)g * p.width));
         CK(dmalloc(&pl->scr.lons, sizeof(double) * (size_t)g * p.width));
-        CK(dmalloc(&pl->scr.rho, sizeof(double) * (size_t)g * p.width));
         CK(dmalloc(&pl->scr.orng, sizeof(double) * (size_t)g * ow));
-        CK(dmalloc(&pl->scr.ctr, sizeof(double) * (size_t)g * ow));
         CK(dmalloc(&pl->scr.ctr_sorted, sizeof(double) * (size_t)g * ow));
         CK(dmalloc(&pl->scr.orng_sorted, sizeof(double) * (size_t)g * ow));
         CK(dmalloc(&pl->scr.pm, sizeof(double) * (size_t)g * ow));

@@ -713,8 +713,7 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
     const int w = C.width, ow = 2 * w + 1; // :134-135
     double *cs_s = scr.cs + (size_t)blockIdx.x * w, *lats_s = scr.lats + (size_t)blockIdx.x * w,
            *lons_s = scr.lons + (size_t)blockIdx.x * w;
-    double *rho = scr.rho + (size_t)blockIdx.x * w;
-    double *orng = scr.orng + (size_t)blockIdx.x * ow, *ctr = scr.ctr + (size_t)blockIdx.x * ow;
+    double *orng = scr.orng + (size_t)blockIdx.x * ow;
     double *ctr_sorted = scr.ctr_sorted + (size_t)blockIdx.x * ow, *orng_sorted = scr.orng_sorted + (size_t)blockIdx.x * ow;
     double *pm = scr.pm + (size_t)blockIdx.x * ow, *sm = scr.sm + (size_t)blockIdx.x * ow;
     int *rank = scr.rank + (size_t)blockIdx.x * ow;
@@ -730,13 +729,14 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double *ctrack_in = out.ctrack + (size_t)row * w;
         const double *lat_in = out.lat + (size_t)row * w, *lon_in = out.lon + (size_t)row * w;
         const float *elev = out.elev + (size_t)row * w;
-        // ---- ctrack extent :730-732, slant ranges of the line ----
+        // ---- ctrack extent :730-732 and "is the line free of fold-over" in one pass over the line ----
         double mn = INFINITY, mx = -INFINITY;
+        int unsorted = 0;
         for (int i = threadIdx.x; i < w; i += blockDim.x) {
-            double v = ctrack_in[i];
+            const double v = ctrack_in[i];
             mn = fmin(mn, v);
             mx = fmax(mx, v);
-            rho[i] = pixel_range(C, line, i);
+            if (i > 0 && ctrack_in[i - 1] > v) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -757,13 +757,13 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             a = warp_max(a);
             if (threadIdx.x == 0) s_mm[1] = a;
         }
-        __syncthreads();
+        const bool ctrack_sorted = __syncthreads_or(unsorted) == 0;
         const double ctrackmin = s_mm[0] - demmax, ctrackmax = s_mm[1] + demmax;
         const double dctrack = (ctrackmax - ctrackmin) / (ow - 1.0);
 
         // ---- stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
         const double *cs = ctrack_in, *lats = lat_in, *lons = lon_in;
-        if (!block_is_sorted(ctrack_in, w, &s_flag)) {
+        if (!ctrack_sorted) {
             block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
             block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < w; i += blockDim.x) {
@@ -779,14 +779,27 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         // ---- DEM surface on the regular cross-track grid :745-782 ----
         const double cs0 = cs[0], csn = cs[w - 1];
         const double gscale = (csn > cs0) ? (double)(w - 1) / (csn - cs0) : 0.0;
-        for (int p = threadIdx.x; p < ow; p += blockDim.x) {
-            const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
-            ctr[p] = aa;
-            const int guess = (int)((aa - cs0) * gscale);
-            int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, guess), w);
-            orng[p] = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
+        // The slant ranges of consecutive samples are compared as they are produced: a warp owns 32 consecutive samples
+        // per sweep, so all but the first one find their predecessor in the neighbouring lane; the warp-boundary pairs
+        // (one in 32) are compared afterwards from memory.  Lines without fold-over never read orng back otherwise.
+        int orng_unsorted = 0;
+        for (int base = 0; base < ow; base += blockDim.x) {
+            const int p = base + (int)threadIdx.x;
+            double val = 0.0;
+            if (p < ow) {
+                const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
+                const int guess = (int)((aa - cs0) * gscale);
+                int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, guess), w);
+                val = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
+                orng[p] = val;
+            }
+            const double prev = __shfl_up_sync(0xffffffffu, val, 1);
+            if ((threadIdx.x & 31) != 0 && p < ow && prev > val) orng_unsorted = 1;
         }
         __syncthreads();
+        for (int b = 32 * ((int)threadIdx.x + 1); b < ow; b += 32 * blockDim.x)
+            if (orng[b - 1] > orng[b]) orng_unsorted = 1;
+        const bool orng_sorted_already = __syncthreads_or(orng_unsorted) == 0;
 
         // ---- shadow (:791-809) on float32 elevang in pixel order ----
         for (int i = threadIdx.x; i < (w + 3) / 4; i += blockDim.x) smask[i] = 0u;
@@ -797,14 +810,13 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         // ---- stable co-sort (orng; ctrack) :787 and layover (:834-852) on the range-sorted ctrack ----
         // ctrack increases with the sample index by construction, so when the slant ranges are already ascending the
         // sorted ctrack is ascending too and neither layover scan can flag anything: the line is done.
-        const bool orng_sorted_already = block_is_sorted(orng, ow, &s_flag);
         if (!orng_sorted_already) {
             block_prefix_max_suffix_min(orng, ow, pm, sm, s_warp_d);
             block_stable_ranks(orng, ow, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < ow; i += blockDim.x) {
                 const int r = rank[i];
                 orng_sorted[r] = orng[i];
-                ctr_sorted[r] = ctr[i];
+                ctr_sorted[r] = ctrackmin + ((i + 1) - 1) * dctrack; // the cross-track position of sample i (:747)
                 oflag[i] = 0;
             }
             __syncthreads();
@@ -815,13 +827,13 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         }
 
         // ---- scatter to radar pixels through the slant-range line (:855-865) ----
-        const double rho0 = rho[0], rhon = rho[w - 1];
+        const double rho0 = pixel_range(C, line, 0), rhon = pixel_range(C, line, w - 1);
         const double rscale = (rhon > rho0) ? (double)(w - 1) / (rhon - rho0) : 0.0;
         for (int i = threadIdx.x; i < (orng_sorted_already ? 0 : ow); i += blockDim.x) {
             if (oflag[i]) {
                 const double val = orng_sorted[i];
                 const int guess = (int)((val - rho0) * rscale);
-                const int j = ref_search_result(search_count_le([&](int m) { return rho[m]; }, w, val, guess), w);
+                const int j = ref_search_result(search_count_le([&](int m) { return pixel_range(C, line, m); }, w, val, guess), w);
                 // mask(j) < omask(i) => mask(j) += 2  <=>  set bit 1 (mask is 0/1 before any layover hit)
                 const int bidx = j - 1;
                 atomicOr(&smask[bidx >> 2], 2u << (8 * (bidx & 3)));

@@ -28,8 +28,8 @@ struct TopoStats {
 };
 
 struct MaskScratch { // per persistent CTA
-    double *cs, *lats, *lons, *rho;                 // [grid][width]
-    double *orng, *ctr, *ctr_sorted, *orng_sorted;  // [grid][2*width+1]
+    double *cs, *lats, *lons;                       // [grid][width]
+    double *orng, *ctr_sorted, *orng_sorted;        // [grid][2*width+1]
     double *pm, *sm;                                // [grid][2*width+1] prefix max / suffix min
     int *rank;                                      // [grid][2*width+1]
     unsigned char *oflag;                           // [grid][2*width+1]
