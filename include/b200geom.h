@@ -280,6 +280,42 @@ int b200_geozero_run(const b200_geozero_params *p, const void *dem, int dem_dtyp
                      void *out, int16_t *dem_crop, b200_geozero_result *res, char *err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------ */
+/* resamp_slc (consumer of the geo2rdr offsets) -- SURVEY 8(f) row N4                          */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces the CPython extension components/stdproc/stdproc/resamp_slc/bindings (set*_Py of resamp_slcmodule.h, module
+ * resamp_slcState of src/resamp_slcState.F) and its verb resamp_slc_Py (src/resamp_slc.f90).  Complex data, sinc
+ * interpolation: the only branch the reference implements (resamp_slc.f90:69-74, :270-274). */
+typedef struct {
+    int in_width, in_length;   /* setInputWidth_Py / setInputLines_Py   */
+    int out_width, out_length; /* setOutputWidth_Py / setOutputLines_Py */
+    double wvl;                /* setRadarWavelength_Py                 */
+    double slr;                /* setSlantRangePixelSpacing_Py          */
+    double r0;                 /* setStartingRange_Py                   */
+    double ref_wvl, ref_r0, ref_slr; /* setReference{Wavelength,StartingRange,SlantRangePixelSpacing}_Py */
+    int flatten;               /* setFlatten_Py                         */
+    int device;                /* not in the reference: CUDA device ordinal */
+} b200_resamp_params;
+
+typedef struct {
+    long long num_valid; /* output pixels inside the input image (the others are zero, resamp_slc.f90:197-207) */
+    float ms_kernels;    /* device time of the carrier + resampling kernels */
+    float ms_total;      /* wall time of the call, copies included */
+    int gpu_launches;
+} b200_resamp_result;
+
+#define B200_RESID_F64 0 /* residual offsets as double (what the 'read' DOUBLE caster delivers) */
+#define B200_RESID_F32 1 /* residual offsets as stored by geo2rdr outputPrecision 'single' (.off FLOAT rasters) */
+
+/* The verb: resamp_slc_Py(slcInAccessor, slcOutAccessor, residazAccessor, residrgAccessor) after
+ * set{Range,Azimuth}Carrier_Py, set{Range,Azimuth}OffsetsPoly_Py, setDopplerPoly_Py.  Any polynomial may be NULL (the
+ * zero polynomial Resamp_slc.py:86-140 substitutes).  slc_in: [in_length][in_width] interleaved complex float32;
+ * resid_az / resid_rg: [out_length][out_width] of resid_dtype, or NULL (accessor == 0); slc_out: [out_length][out_width]. */
+int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2d *rg_carrier, const b200_poly2d *az_carrier,
+                        const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets, const b200_poly2d *doppler,
+                        const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype, float *slc_out,
+                        b200_resamp_result *res, char *err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilities                                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 int b200_abi_version(void);

@@ -30,6 +30,11 @@ def createGeozero():
     return f()
 
 
+def createResamp_slc():
+    from .resamp_slc import createResamp_slc as f
+    return f()
+
+
 def install_as_zerodop():
     """Make ``from zerodop.topozero import createTopozero`` / ``from zerodop.geo2rdr import createGeo2rdr`` resolve to
     this package (components/zerodop/topozero/__init__.py:33-35, components/zerodop/geo2rdr/__init__.py:3-5)."""

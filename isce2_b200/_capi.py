@@ -104,6 +104,16 @@ class GeozeroResult(C.Structure):
                 ("gpu_launches", C.c_int)]
 
 
+class ResampParams(C.Structure):
+    _fields_ = [("in_width", C.c_int), ("in_length", C.c_int), ("out_width", C.c_int), ("out_length", C.c_int),
+                ("wvl", C.c_double), ("slr", C.c_double), ("r0", C.c_double), ("ref_wvl", C.c_double), ("ref_r0", C.c_double),
+                ("ref_slr", C.c_double), ("flatten", C.c_int), ("device", C.c_int)]
+
+
+class ResampResult(C.Structure):
+    _fields_ = [("num_valid", C.c_longlong), ("ms_kernels", C.c_float), ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
+
+
 GEOZERO_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3}
 SCHEMES = {"BIL": 0, "BIP": 1, "BSQ": 2}
 
@@ -112,7 +122,8 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_geo_plan_create_from_topo", "b200_geo_plan_execute", "b200_geo_plan_fetch", "b200_geo_plan_destroy",
            "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
-           "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run"]
+           "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
+           "b200_resamp_slc_run"]
 
 _lib = None
 
@@ -163,6 +174,8 @@ def lib():
     L.b200_geozero_run.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d), C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int16),
                                    C.POINTER(GeozeroResult)] + err
+    L.b200_resamp_slc_run.argtypes = [C.POINTER(ResampParams)] + [C.POINTER(Poly2d)] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.POINTER(ResampResult)] + err
     _lib = L
     return L
 
@@ -575,5 +588,61 @@ def geozero_run(params, dem, orbit_t, orbit_pos, orbit_vel, image, method="BILIN
                                   GEOZERO_METHODS[method.upper()], out.ctypes.data_as(C.c_void_p),
                                   dem_crop.ctypes.data_as(C.POINTER(C.c_int16)), C.byref(res), e, 512), e)
     r = dict(geo=out, dem_crop=dem_crop)
+    r.update(_result_dict(res))
+    return r
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# resamp_slc
+# ---------------------------------------------------------------------------------------------------------------
+def _poly2d_arg(keep, p):
+    """None, a (coeffs, mean_range, mean_azimuth, norm_range, norm_azimuth) tuple as poly.poly2d_fields returns, or a
+    plain 2-D coefficient list."""
+    if p is None:
+        return None
+    if isinstance(p, tuple) and len(p) == 5:
+        return make_poly2d(keep, *p)
+    return make_poly2d(keep, p)
+
+
+def resamp_slc_run(slc, out_shape, *, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_r0=None, ref_slr=None, flatten=False,
+                   rg_carrier=None, az_carrier=None, rg_offsets=None, az_offsets=None, doppler=None, resid_az=None,
+                   resid_rg=None, out=None, device=0):
+    """One call of the reference verb resamp_slc_Py.  slc: complex64 [in_length][in_width]; resid_*: float64 or float32
+    [out_length][out_width] (both of one type) or None; returns dict(slc=..., num_valid=..., ms_kernels=...)."""
+    keep = _Keep()
+    a = np.ascontiguousarray(slc, np.complex64)
+    if a.ndim != 2:
+        raise ValueError("slc must be a single-band image")
+    ol, ow = int(out_shape[0]), int(out_shape[1])
+    p = ResampParams(a.shape[1], a.shape[0], ow, ol, wvl, slr, r0, wvl if ref_wvl is None else ref_wvl,
+                     r0 if ref_r0 is None else ref_r0, slr if ref_slr is None else ref_slr, int(bool(flatten)), device)
+    polys = [_poly2d_arg(keep, q) for q in (rg_carrier, az_carrier, rg_offsets, az_offsets, doppler)]
+    rdt = None
+    res_ptr = []
+    for r in (resid_az, resid_rg):
+        if r is None:
+            res_ptr.append(None)
+            continue
+        r = np.asarray(r)
+        dt = np.float32 if r.dtype == np.float32 else np.float64
+        if rdt is not None and dt != rdt:
+            raise ValueError("residual azimuth and range offsets must have one data type")
+        rdt = dt
+        r = np.ascontiguousarray(r, dt)
+        if r.shape != (ol, ow):
+            raise ValueError(f"residual offsets have shape {r.shape}, expected {(ol, ow)}")
+        keep.refs.append(r)
+        res_ptr.append(r.ctypes.data_as(C.c_void_p))
+    if out is None:
+        out = np.empty((ol, ow), np.complex64)
+    if out.dtype != np.complex64 or out.shape != (ol, ow) or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("out must be a C-contiguous complex64 array of the output size")
+    res = ResampResult()
+    e = _errbuf()
+    _check(lib().b200_resamp_slc_run(C.byref(p), *[(C.byref(q) if q is not None else None) for q in polys],
+                                     a.ctypes.data_as(C.c_void_p), res_ptr[0], res_ptr[1], 1 if rdt == np.float32 else 0,
+                                     out.ctypes.data_as(C.c_void_p), C.byref(res), e, 512), e)
+    r = dict(slc=out)
     r.update(_result_dict(res))
     return r

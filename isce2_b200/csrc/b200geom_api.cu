@@ -20,6 +20,7 @@
 #include "geo2rdr_kernels.cuh"
 #include "geozero_kernels.cuh"
 #include "orbit_poly.h"
+#include "resamp_kernels.cuh"
 #include "topo_kernels.cuh"
 
 using namespace b2;
@@ -1454,6 +1455,142 @@ extern "C" int b200_geozero_run(const b200_geozero_params *p, const void *dem, i
     delete pl;
     if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
     return rc;
+}
+
+// =================================================================================================
+// resamp_slc
+// =================================================================================================
+namespace {
+
+// normalised sinc table of resamp_slcMethods.f:57-83 (every sub-sample phase scaled to unit sum in real*8, then real*4)
+void resamp_sinc_table(float *fintp)
+{
+    const double pi = 4.0 * atan(1.0);
+    const int n = kSincSub * kSincLen;
+    std::vector<double> r_filter((size_t)n + 1, 0.0);
+    const double r_soff = n / 2.0;
+    for (int i = 0; i < n; i++) { // sinc_coef(beta = 1, relfiltlen = 8, decfactor = 8192, pedestal = 0, weight = 1)
+        const double r_wa = i - r_soff;
+        const double r_s = r_wa * 1.0 / (1.0 * kSincSub);
+        const double r_fct = (r_s != 0.0) ? sin(pi * r_s) / (pi * r_s) : 1.0;
+        const double r_wgt = (1.0 - 0.5) + 0.5 * cos((pi * r_wa) / r_soff);
+        r_filter[i] = r_fct * r_wgt;
+    }
+    for (int i = 0; i < kSincSub; i++) {
+        double ssum = 0.0;
+        for (int j = 0; j < kSincLen; j++) ssum = ssum + r_filter[i + j * kSincSub];
+        for (int j = 0; j < kSincLen; j++) r_filter[i + j * kSincSub] = r_filter[i + j * kSincSub] / ssum;
+    }
+    for (int i = 0; i < kSincLen; i++)
+        for (int j = 0; j < kSincSub; j++) fintp[i + j * kSincLen] = (float)r_filter[j + i * kSincSub];
+}
+
+int fill_poly2d_or_zero(const b200_poly2d *src, Poly2dDev &dst, const char *what, char *err, size_t errlen)
+{
+    if (src) return fill_poly2d(src, dst, what, err, errlen);
+    memset(&dst, 0, sizeof dst); // order 0, coefficient 0 (Resamp_slc.py:86-140)
+    dst.norm_range = dst.norm_azimuth = dst.inv_norm_range = dst.inv_norm_azimuth = 1.0;
+    return B200_OK;
+}
+
+bool poly2d_is_zero(const Poly2dDev &p)
+{
+    const int n = (p.range_order + 1) * (p.azimuth_order + 1);
+    for (int i = 0; i < n; i++)
+        if (p.c[i] != 0.0) return false;
+    return true;
+}
+
+struct ResampBuffers {
+    float2 *d_in = nullptr, *d_out = nullptr;
+    void *d_raz = nullptr, *d_rrg = nullptr;
+    float *d_sinc = nullptr;
+    ResampStats *d_stats = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~ResampBuffers()
+    {
+        dfree(d_in); dfree(d_out); dfree(d_raz); dfree(d_rrg); dfree(d_sinc); dfree(d_stats);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+} // namespace
+
+extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2d *rg_carrier, const b200_poly2d *az_carrier,
+                                   const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets, const b200_poly2d *doppler,
+                                   const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype,
+                                   float *slc_out, b200_resamp_result *res, char *err, size_t errlen)
+{
+    const double t0 = now_ms();
+    if (!p || !slc_in || !slc_out) return fail(err, errlen, B200_EINVAL, "params / input / output image is NULL");
+    if (p->in_width < 1 || p->in_length < 1 || p->out_width < 1 || p->out_length < 1)
+        return fail(err, errlen, B200_EINVAL, "bad image sizes");
+    if (resid_dtype != B200_RESID_F64 && resid_dtype != B200_RESID_F32) return fail(err, errlen, B200_EINVAL, "bad resid_dtype");
+    ResampConst C{};
+    C.inwidth = p->in_width; C.inlength = p->in_length; C.outwidth = p->out_width; C.outlength = p->out_length;
+    C.wvl = p->wvl; C.slr = p->slr; C.r0 = p->r0; C.refwvl = p->ref_wvl; C.refr0 = p->ref_r0; C.refslr = p->ref_slr;
+    C.flatten = p->flatten;
+    C.pi = 4.0 * atan(1.0);
+    int rc;
+    if ((rc = fill_poly2d_or_zero(rg_carrier, C.rg_carrier, "range carrier", err, errlen)) != B200_OK) return rc;
+    if ((rc = fill_poly2d_or_zero(az_carrier, C.az_carrier, "azimuth carrier", err, errlen)) != B200_OK) return rc;
+    if ((rc = fill_poly2d_or_zero(rg_offsets, C.rg_off, "range offsets", err, errlen)) != B200_OK) return rc;
+    if ((rc = fill_poly2d_or_zero(az_offsets, C.az_off, "azimuth offsets", err, errlen)) != B200_OK) return rc;
+    if ((rc = fill_poly2d_or_zero(doppler, C.dop, "doppler", err, errlen)) != B200_OK) return rc;
+    C.has_carrier = (poly2d_is_zero(C.rg_carrier) && poly2d_is_zero(C.az_carrier)) ? 0 : 1;
+    if (p->flatten && (p->wvl == 0.0 || p->ref_wvl == 0.0)) return fail(err, errlen, B200_EINVAL, "flattening needs the wavelengths");
+    if ((rc = select_device(p->device, err, errlen)) != B200_OK) return rc;
+
+    ResampBuffers B;
+    CK(cudaStreamCreateWithFlags(&B.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&B.ev0));
+    CK(cudaEventCreate(&B.ev1));
+    cudaStream_t s = B.stream;
+    const size_t nin = (size_t)p->in_width * (size_t)p->in_length, nout = (size_t)p->out_width * (size_t)p->out_length;
+    const size_t rsz = resid_dtype == B200_RESID_F32 ? 4 : 8;
+    CK(dmalloc(&B.d_in, sizeof(float2) * nin));
+    CK(dmalloc(&B.d_out, sizeof(float2) * nout));
+    CK(dmalloc(&B.d_sinc, sizeof(float) * kSincSub * kSincLen));
+    CK(dmalloc(&B.d_stats, sizeof(ResampStats)));
+    std::vector<float> tab((size_t)kSincSub * kSincLen);
+    resamp_sinc_table(tab.data());
+    CK(cudaMemcpyAsync(B.d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(B.d_in, slc_in, sizeof(float2) * nin, cudaMemcpyHostToDevice, s));
+    if (resid_az) {
+        CK(dmalloc(&B.d_raz, rsz * nout));
+        CK(cudaMemcpyAsync(B.d_raz, resid_az, rsz * nout, cudaMemcpyHostToDevice, s));
+    }
+    if (resid_rg) {
+        CK(dmalloc(&B.d_rrg, rsz * nout));
+        CK(cudaMemcpyAsync(B.d_rrg, resid_rg, rsz * nout, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemsetAsync(B.d_stats, 0, sizeof(ResampStats), s));
+    CK(cudaEventRecord(B.ev0, s));
+    int launches = 0;
+    // with both carriers identically zero the up-front pass multiplies every sample by (1, -0): the identity
+    if (C.has_carrier) {
+        launch_resamp_carrier(C, B.d_in, B.d_in, s);
+        launches++;
+    }
+    if (launch_resamp_slc(C, B.d_in, B.d_raz, B.d_rrg, resid_dtype == B200_RESID_F32, B.d_sinc, B.d_out, B.d_stats, s) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the resampling kernel");
+    launches++;
+    CK(cudaEventRecord(B.ev1, s));
+    ResampStats st;
+    CK(cudaMemcpyAsync(&st, B.d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(slc_out, B.d_out, sizeof(float2) * nout, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    if (res) {
+        res->num_valid = (long long)st.valid;
+        CK(cudaEventElapsedTime(&res->ms_kernels, B.ev0, B.ev1));
+        res->gpu_launches = launches;
+        res->ms_total = (float)(now_ms() - t0);
+    }
+    return B200_OK;
 }
 
 // =================================================================================================

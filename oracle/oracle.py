@@ -80,6 +80,12 @@ class OrcGeozeroResult(C.Structure):
                 ("num_outside_image", C.c_longlong), ("num_valid", C.c_longlong), ("total_iters", C.c_longlong)]
 
 
+class OrcResampParams(C.Structure):
+    _fields_ = [("inwidth", C.c_int), ("inlength", C.c_int), ("outwidth", C.c_int), ("outlength", C.c_int),
+                ("wvl", C.c_double), ("slr", C.c_double), ("r0", C.c_double), ("refwvl", C.c_double), ("refr0", C.c_double),
+                ("refslr", C.c_double), ("flatten", C.c_int)]
+
+
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is mounted)."""
     src = os.path.join(HERE, "zerodop_oracle.c")
@@ -134,6 +140,9 @@ def lib():
         L.orc_geozero.restype = C.c_int
         L.orc_geozero.argtypes = [C.POINTER(OrcGeozeroParams), _fp, C.POINTER(OrcOrbit), C.POINTER(OrcPoly1d), _fp, C.c_int,
                                   C.c_int, C.c_int, _fp, C.POINTER(C.c_int16), _dp, _dp, C.POINTER(OrcGeozeroResult), C.c_int]
+        L.orc_resamp_sinc_table.argtypes = [_fp]
+        L.orc_resamp_slc.restype = C.c_int
+        L.orc_resamp_slc.argtypes = [C.POINTER(OrcResampParams)] + [C.POINTER(OrcPoly2d)] * 5 + [_fp, _dp, _dp, _fp, C.c_int]
         _lib = L
     return _lib
 
@@ -321,3 +330,33 @@ def geozero(*, dem, image, orbit_t, orbit_pos, orbit_vel, method="BILINEAR", sid
     for k, _ in OrcGeozeroResult._fields_:
         r[k] = getattr(res, k)
     return r
+
+
+def _poly2d_or_none(p):
+    """p: None, a Poly2D of this module, or (coeffs[, mean_range, mean_azimuth, norm_range, norm_azimuth])."""
+    if p is None or isinstance(p, Poly2D):
+        return p
+    if isinstance(p, (list, tuple)) and len(p) and not np.isscalar(p[0]) and np.ndim(p[0]) == 2:
+        return Poly2D(*p)
+    return Poly2D(p)
+
+
+def resamp_slc(*, slc, out_shape, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_r0=None, ref_slr=None, flatten=False,
+               rg_carrier=None, az_carrier=None, rg_offsets=None, az_offsets=None, doppler=None, resid_az=None, resid_rg=None,
+               nthreads=0):
+    """resamp_slc.f90 on one complex64 image; polynomials as oracle.Poly2D / coefficient lists / None (zero)."""
+    slc = np.ascontiguousarray(slc, np.complex64)
+    inlength, inwidth = slc.shape
+    outlength, outwidth = out_shape
+    p = OrcResampParams(inwidth, inlength, outwidth, outlength, wvl, slr, r0, wvl if ref_wvl is None else ref_wvl,
+                        r0 if ref_r0 is None else ref_r0, slr if ref_slr is None else ref_slr, int(bool(flatten)))
+    polys = [_poly2d_or_none(q) for q in (rg_carrier, az_carrier, rg_offsets, az_offsets, doppler)]
+    ra = np.ascontiguousarray(resid_az, np.float64) if resid_az is not None else None
+    rr = np.ascontiguousarray(resid_rg, np.float64) if resid_rg is not None else None
+    out = np.zeros((outlength, outwidth), np.complex64)
+    rc = lib().orc_resamp_slc(C.byref(p), *[(C.byref(q.c) if q is not None else None) for q in polys],
+                              slc.ctypes.data_as(_fp), _d(ra) if ra is not None else None, _d(rr) if rr is not None else None,
+                              out.ctypes.data_as(_fp), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"orc_resamp_slc failed rc={rc}")
+    return out

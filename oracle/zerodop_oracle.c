@@ -1566,3 +1566,156 @@ int orc_geozero(const orc_geozero_params *p, const float *dem_full, const orc_or
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* resamp_slc: components/stdproc/stdproc/resamp_slc/src/resamp_slc.f90  */
+/* ------------------------------------------------------------------ */
+/* resamp_slcMethods.f:57-83: sinc_coef as in topozero, then every sub-sample phase normalised to unit sum before the
+ * real*4 table is filled */
+static float *g_fintp_resamp = NULL;
+static const float *resamp_sinc_table(void)
+{
+#pragma omp critical(orc_resamp_sinc_table)
+    if (!g_fintp_resamp) {
+        const double pi = 4.0 * atan(1.0);
+        const double r_beta = 1.0, r_relfiltlen = 1.0 * SINC_LEN, r_pedestal = 0.0;
+        const int i_decfactor = SINC_SUB;
+        const int i_intplength = (int)lround(r_relfiltlen / r_beta);
+        const int i_filtercoef = i_intplength * i_decfactor;
+        const double r_wgthgt = (1.0 - r_pedestal) / 2.0;
+        const double r_soff = i_filtercoef / 2.0;
+        double *r_filter = calloc((size_t)i_filtercoef + 1, sizeof(double));
+        for (int i = 0; i < i_filtercoef; i++) {
+            double r_wa = i - r_soff;
+            double r_s = r_wa * r_beta / (1.0 * i_decfactor);
+            double r_fct = (r_s != 0.0) ? sin(pi * r_s) / (pi * r_s) : 1.0;
+            double r_wgt = (1.0 - r_wgthgt) + r_wgthgt * cos((pi * r_wa) / r_soff);
+            r_filter[i] = r_fct * r_wgt;
+        }
+        for (int i = 0; i < SINC_SUB; i++) {
+            double ssum = 0.0;
+            for (int j = 0; j < SINC_LEN; j++) ssum = ssum + r_filter[i + j * SINC_SUB];
+            for (int j = 0; j < SINC_LEN; j++) r_filter[i + j * SINC_SUB] = r_filter[i + j * SINC_SUB] / ssum;
+        }
+        float *f = malloc(sizeof(float) * SINC_SUB * SINC_LEN);
+        for (int i = 0; i < SINC_LEN; i++)
+            for (int j = 0; j < SINC_SUB; j++) f[i + j * SINC_LEN] = (float)r_filter[j + i * SINC_SUB];
+        free(r_filter);
+        g_fintp_resamp = f;
+    }
+    return g_fintp_resamp;
+}
+void orc_resamp_sinc_table(float *out) { memcpy(out, resamp_sinc_table(), sizeof(float) * SINC_SUB * SINC_LEN); }
+
+/* default COMPLEX product (real*4 components, each product and the sum rounded separately) */
+static inline cx4 c4_mul(cx4 a, cx4 b)
+{
+    cx4 r;
+    float t1 = a.re * b.re, t2 = a.im * b.im, t3 = a.re * b.im, t4 = a.im * b.re;
+    r.re = t1 - t2;
+    r.im = t3 + t4;
+    return r;
+}
+/* MODULO(a, p) for reals as gfortran expands it: fmod, then shifted into the sign of p */
+static inline double f_modulo(double a, double p)
+{
+    double r = fmod(a, p);
+    if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+    return r;
+}
+static double eval2d_or_zero(const orc_poly2d *poly, double azi, double rng)
+{
+    return poly ? orc_eval_poly2d(poly, azi, rng) : 0.0;
+}
+
+int orc_resamp_slc(const orc_resamp_params *p, const orc_poly2d *rgCarrier, const orc_poly2d *azCarrier,
+                   const orc_poly2d *rgOffsetsPoly, const orc_poly2d *azOffsetsPoly, const orc_poly2d *dopplerPoly,
+                   const float *in, const double *residaz_img, const double *residrg_img, float *out, int nthreads)
+{
+    const double PI = 4.0 * atan(1.0);
+    const int inwidth = p->inwidth, inlength = p->inlength, outwidth = p->outwidth, outlength = p->outlength;
+    const int sinchalf = SINC_LEN / 2, sincone = SINC_LEN + 1;
+    if (inwidth < 1 || inlength < 1 || outwidth < 1 || outlength < 1) return -1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    const float *fintp = resamp_sinc_table();
+    cx4 *cin = malloc(sizeof(cx4) * (size_t)inwidth * (size_t)inlength);
+    if (!cin) return -4;
+#define CIN(i, j) cin[(size_t)((j) - 1) * (size_t)inwidth + (size_t)((i) - 1)]
+    /* all carriers are removed from the data up front (:122-141) */
+    for (int j = 1; j <= inlength; j++) {
+        const double r_at = j;
+#pragma omp parallel for schedule(static)
+        for (int i = 1; i <= inwidth; i++) {
+            const double r_rt = i;
+            double r_ph = eval2d_or_zero(rgCarrier, r_at, r_rt) + eval2d_or_zero(azCarrier, r_at, r_rt);
+            r_ph = f_modulo(r_ph, 2.0 * PI);
+            cx4 cl = {in[2 * ((size_t)(j - 1) * inwidth + (i - 1))], in[2 * ((size_t)(j - 1) * inwidth + (i - 1)) + 1]};
+            cx4 rot = {(float)cos(r_ph), (float)(-sin(r_ph))};
+            CIN(i, j) = c4_mul(cl, rot);
+        }
+    }
+    for (int j = 1; j <= outlength; j++) { /* :166 */
+        const double *residaz = residaz_img ? residaz_img + (size_t)(j - 1) * outwidth : NULL;
+        const double *residrg = residrg_img ? residrg_img + (size_t)(j - 1) * outwidth : NULL;
+        float *cout = out + 2 * (size_t)(j - 1) * outwidth;
+#pragma omp parallel for schedule(static)
+        for (int i = 1; i <= outwidth; i++) {
+            cx4 chip[9][9]; /* chip(ii,jj) -> chip[jj-1][ii-1] */
+            cout[2 * (i - 1)] = 0.f;
+            cout[2 * (i - 1) + 1] = 0.f;
+            double r_rt = i, r_at = j;
+            const double r_ro = eval2d_or_zero(rgOffsetsPoly, r_at, r_rt) + (residrg ? residrg[i - 1] : 0.0);
+            const double r_ao = eval2d_or_zero(azOffsetsPoly, r_at, r_rt) + (residaz ? residaz[i - 1] : 0.0);
+            const int k = (int)floor(i + r_ro);
+            const double fracr = i + r_ro - k;
+            if ((k <= sinchalf) || (k >= (inwidth - sinchalf))) continue;
+            const int kk = (int)floor(j + r_ao);
+            const double fraca = j + r_ao - kk;
+            if ((kk <= sinchalf) || (kk >= (inlength - sinchalf))) continue;
+            const double r_dop = eval2d_or_zero(dopplerPoly, r_at + r_ao, r_rt + r_ro); /* :211 */
+            for (int jj = 1; jj <= sincone; jj++) {
+                const int chipj = kk + jj - 1 - sinchalf;
+                cx4 cval = {(float)cos((jj - 5.0) * r_dop), (float)(-sin((jj - 5.0) * r_dop))};
+                for (int ii = 1; ii <= sincone; ii++) {
+                    const int chipi = k + ii - 1 - sinchalf;
+                    chip[jj - 1][ii - 1] = c4_mul(CIN(chipi, chipj), cval);
+                }
+            }
+            double r_ph = r_dop * fraca;
+            r_rt = i + r_ro;
+            r_at = j + r_ao;
+            r_ph = r_ph + eval2d_or_zero(rgCarrier, r_at, r_rt) + eval2d_or_zero(azCarrier, r_at, r_rt);
+            if (p->flatten != 0)
+                r_ph = r_ph + (4.0 * PI / p->wvl) * ((p->r0 - p->refr0) + (i - 1.0) * (p->slr - p->refslr) + r_ro * p->slr) +
+                       (4.0 * PI * (p->refr0 + (i - 1.0) * p->refslr)) * (1.0 / p->refwvl - 1.0 / p->wvl);
+            r_ph = f_modulo(r_ph, 2.0 * PI);
+            /* intp_sinc_cx(chip, 5, 5, fracr, fraca, 9, 9) -> sinc_eval_2d_cx(chip, fintp, 8192, 8, 8, 8, ...) with
+             * arrin(a, b) = chip(a+1, b+1): uniform_interp.f90:456-484 */
+            cx4 acc = {0.f, 0.f};
+            {
+                const int idec = SINC_SUB, ilen = SINC_LEN, intpx = 8, intpy = 8;
+                int ifracx = (int)(fracr * idec), ifracy = (int)(fraca * idec);
+                ifracx = ifracx < 0 ? 0 : (ifracx > idec - 1 ? idec - 1 : ifracx);
+                ifracy = ifracy < 0 ? 0 : (ifracy > idec - 1 ? idec - 1 : ifracy);
+                double fweightsum = 0.0;
+                for (int kq = 0; kq < ilen; kq++)
+                    for (int m = 0; m < ilen; m++) {
+                        const float fw4 = fintp[kq + ifracx * ilen] * fintp[m + ifracy * ilen];
+                        const double fweight = fw4;
+                        acc = c4(c8_add(c8(acc), c8_scale(c8(chip[intpy - m][intpx - kq]), fweight)));
+                        fweightsum = fweightsum + fweight;
+                    }
+                acc = c4(c8_div(c8(acc), fweightsum));
+            }
+            cx4 rot = {(float)cos(r_ph), (float)sin(r_ph)};
+            cx4 o = c4_mul(acc, rot);
+            cout[2 * (i - 1)] = o.re;
+            cout[2 * (i - 1) + 1] = o.im;
+        }
+    }
+#undef CIN
+    free(cin);
+    return 0;
+}
