@@ -315,6 +315,14 @@ int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2d *rg_carri
                         const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype, float *slc_out,
                         b200_resamp_result *res, char *err, size_t errlen);
 
+/* Fused form for the stack shape (contrib/stack/topsStack: geo2rdr.py then resamp_withCarrier.py per burst and date): the
+ * azimuth / range offsets an executed geo2rdr plan left in HBM are the residual images, without the round trip through the
+ * .off rasters (a -999999 offset resamples to zero, exactly as through the files).  The output grid is the plan's. */
+int b200_resamp_slc_from_geo_plan(const b200_resamp_params *p, b200_geo_plan *geo, const b200_poly2d *rg_carrier,
+                                  const b200_poly2d *az_carrier, const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets,
+                                  const b200_poly2d *doppler, const float *slc_in, float *slc_out, b200_resamp_result *res,
+                                  char *err, size_t errlen);
+
 /* ------------------------------------------------------------------------------------------ */
 /* utilities                                                                                   */
 /* ------------------------------------------------------------------------------------------ */

@@ -123,7 +123,7 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
-           "b200_resamp_slc_run"]
+           "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan"]
 
 _lib = None
 
@@ -176,6 +176,8 @@ def lib():
                                    C.POINTER(GeozeroResult)] + err
     L.b200_resamp_slc_run.argtypes = [C.POINTER(ResampParams)] + [C.POINTER(Poly2d)] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p, C.POINTER(ResampResult)] + err
+    L.b200_resamp_slc_from_geo_plan.argtypes = [C.POINTER(ResampParams), C.c_void_p] + [C.POINTER(Poly2d)] * 5 + [
+        C.c_void_p, C.c_void_p, C.POINTER(ResampResult)] + err
     _lib = L
     return L
 
@@ -643,6 +645,28 @@ def resamp_slc_run(slc, out_shape, *, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, 
     _check(lib().b200_resamp_slc_run(C.byref(p), *[(C.byref(q) if q is not None else None) for q in polys],
                                      a.ctypes.data_as(C.c_void_p), res_ptr[0], res_ptr[1], 1 if rdt == np.float32 else 0,
                                      out.ctypes.data_as(C.c_void_p), C.byref(res), e, 512), e)
+    r = dict(slc=out)
+    r.update(_result_dict(res))
+    return r
+
+
+def resamp_slc_from_geo_plan(geo_plan, slc, *, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_r0=None, ref_slr=None,
+                             flatten=False, rg_carrier=None, az_carrier=None, rg_offsets=None, az_offsets=None, doppler=None,
+                             out=None):
+    """geo2rdr -> resamp_slc without leaving the GPU: the offsets of the executed GeoPlan are the residual images."""
+    keep = _Keep()
+    a = np.ascontiguousarray(slc, np.complex64)
+    gp = geo_plan.last_params
+    ol, ow = geo_plan.nlines, gp.dem_width
+    p = ResampParams(a.shape[1], a.shape[0], ow, ol, wvl, slr, r0, wvl if ref_wvl is None else ref_wvl,
+                     r0 if ref_r0 is None else ref_r0, slr if ref_slr is None else ref_slr, int(bool(flatten)), gp.device)
+    polys = [_poly2d_arg(keep, q) for q in (rg_carrier, az_carrier, rg_offsets, az_offsets, doppler)]
+    if out is None:
+        out = np.empty((ol, ow), np.complex64)
+    res = ResampResult()
+    e = _errbuf()
+    _check(lib().b200_resamp_slc_from_geo_plan(C.byref(p), geo_plan.handle, *[(C.byref(q) if q is not None else None) for q in polys],
+                                               a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.byref(res), e, 512), e)
     r = dict(slc=out)
     r.update(_result_dict(res))
     return r

@@ -1519,10 +1519,11 @@ struct ResampBuffers {
 
 } // namespace
 
-extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2d *rg_carrier, const b200_poly2d *az_carrier,
-                                   const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets, const b200_poly2d *doppler,
-                                   const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype,
-                                   float *slc_out, b200_resamp_result *res, char *err, size_t errlen)
+// resid_on_device: resid_az / resid_rg are device pointers on p->device (the offsets a geo2rdr plan left in HBM)
+static int resamp_core(const b200_resamp_params *p, const b200_poly2d *rg_carrier, const b200_poly2d *az_carrier,
+                       const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets, const b200_poly2d *doppler,
+                       const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype, bool resid_on_device,
+                       float *slc_out, b200_resamp_result *res, char *err, size_t errlen)
 {
     const double t0 = now_ms();
     if (!p || !slc_in || !slc_out) return fail(err, errlen, B200_EINVAL, "params / input / output image is NULL");
@@ -1559,13 +1560,18 @@ extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2
     resamp_sinc_table(tab.data());
     CK(cudaMemcpyAsync(B.d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(B.d_in, slc_in, sizeof(float2) * nin, cudaMemcpyHostToDevice, s));
-    if (resid_az) {
-        CK(dmalloc(&B.d_raz, rsz * nout));
-        CK(cudaMemcpyAsync(B.d_raz, resid_az, rsz * nout, cudaMemcpyHostToDevice, s));
-    }
-    if (resid_rg) {
-        CK(dmalloc(&B.d_rrg, rsz * nout));
-        CK(cudaMemcpyAsync(B.d_rrg, resid_rg, rsz * nout, cudaMemcpyHostToDevice, s));
+    const void *d_raz = resid_az, *d_rrg = resid_rg;
+    if (!resid_on_device) {
+        if (resid_az) {
+            CK(dmalloc(&B.d_raz, rsz * nout));
+            CK(cudaMemcpyAsync(B.d_raz, resid_az, rsz * nout, cudaMemcpyHostToDevice, s));
+            d_raz = B.d_raz;
+        }
+        if (resid_rg) {
+            CK(dmalloc(&B.d_rrg, rsz * nout));
+            CK(cudaMemcpyAsync(B.d_rrg, resid_rg, rsz * nout, cudaMemcpyHostToDevice, s));
+            d_rrg = B.d_rrg;
+        }
     }
     CK(cudaMemsetAsync(B.d_stats, 0, sizeof(ResampStats), s));
     CK(cudaEventRecord(B.ev0, s));
@@ -1575,7 +1581,7 @@ extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2
         launch_resamp_carrier(C, B.d_in, B.d_in, s);
         launches++;
     }
-    if (launch_resamp_slc(C, B.d_in, B.d_raz, B.d_rrg, resid_dtype == B200_RESID_F32, B.d_sinc, B.d_out, B.d_stats, s) != 0)
+    if (launch_resamp_slc(C, B.d_in, d_raz, d_rrg, resid_dtype == B200_RESID_F32, B.d_sinc, B.d_out, B.d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the resampling kernel");
     launches++;
     CK(cudaEventRecord(B.ev1, s));
@@ -1591,6 +1597,33 @@ extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2
         res->ms_total = (float)(now_ms() - t0);
     }
     return B200_OK;
+}
+
+extern "C" int b200_resamp_slc_run(const b200_resamp_params *p, const b200_poly2d *rg_carrier, const b200_poly2d *az_carrier,
+                                   const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets, const b200_poly2d *doppler,
+                                   const float *slc_in, const void *resid_az, const void *resid_rg, int resid_dtype,
+                                   float *slc_out, b200_resamp_result *res, char *err, size_t errlen)
+{
+    return resamp_core(p, rg_carrier, az_carrier, rg_offsets, az_offsets, doppler, slc_in, resid_az, resid_rg, resid_dtype, false,
+                       slc_out, res, err, errlen);
+}
+
+extern "C" int b200_resamp_slc_from_geo_plan(const b200_resamp_params *p, b200_geo_plan *geo, const b200_poly2d *rg_carrier,
+                                             const b200_poly2d *az_carrier, const b200_poly2d *rg_offsets,
+                                             const b200_poly2d *az_offsets, const b200_poly2d *doppler, const float *slc_in,
+                                             float *slc_out, b200_resamp_result *res, char *err, size_t errlen)
+{
+    if (!p || !geo) return fail(err, errlen, B200_EINVAL, "params / geo2rdr plan is NULL");
+    if (!geo->executed || !geo->d_out[2] || !geo->d_out[3])
+        return fail(err, errlen, B200_EINVAL, "the geo2rdr plan must have been executed with azimuth and range offsets requested");
+    if (geo->p.device != p->device) return fail(err, errlen, B200_EINVAL, "the geo2rdr plan lives on another device");
+    if (p->out_width != geo->p.dem_width || p->out_length != geo->nlines)
+        return fail(err, errlen, B200_EINVAL, "output grid %d x %d differs from the plan's offset rasters %d x %d", p->out_length,
+                    p->out_width, geo->nlines, geo->p.dem_width);
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(geo->stream));
+    return resamp_core(p, rg_carrier, az_carrier, rg_offsets, az_offsets, doppler, slc_in, geo->d_out[2], geo->d_out[3],
+                       geo->out_f32 ? B200_RESID_F32 : B200_RESID_F64, true, slc_out, res, err, errlen);
 }
 
 // =================================================================================================

@@ -144,3 +144,30 @@ def test_resamp_component_with_geo2rdr_offset_rasters(tmp_path):
     bad.inputWidth = sc.width + 1
     with pytest.raises(Exception, match="does not match specified width"):
         bad.resamp_slc(imageOut=imgOut)
+
+
+def test_fused_geo2rdr_to_resamp_equals_the_path_through_the_offset_rasters():
+    sc = pu.rough_scene(200, 1500)
+    c = pu.cpu_topo(sc, dem_method="BILINEAR", want_inc=False, want_mask=False)
+    sec = synth.config_c1_secondary(length=sc.length, width=sc.width)
+    kw = pu.secondary_kwargs(sc, sec, recenter=0.37)
+    slc = _slc(sc.length, sc.width, 4)
+    rkw = dict(wvl=sc.wvl, slr=sc.dr, flatten=True, az_carrier=[[0.0, 1e-4], [0.3, 0.0], [2e-4, 0.0]], doppler=[[0.02, 1e-6]])
+    for f32 in (True, False):
+        gp = _capi.geo_params(length=kw["length"], width=kw["width"], dem_shape=c["lat"].shape, r0=kw["r0"], dr=kw["dr"],
+                              prf=kw["prf"], t0=kw["t0"], wvl=kw["wvl"], side=kw["side"], out_f32=f32)
+        plan = _capi.GeoPlan(gp, lat=c["lat"], lon=c["lon"], hgt=c["hgt"])
+        plan.execute(gp, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"], want=("azoff", "rgoff"))
+        fused = _capi.resamp_slc_from_geo_plan(plan, slc, **rkw)
+        offs = plan.fetch()
+        plan.close()
+        host = _capi.resamp_slc_run(slc, slc.shape, resid_az=offs["azoff"], resid_rg=offs["rgoff"], **rkw)
+        assert np.array_equal(fused["slc"], host["slc"]) and fused["num_valid"] == host["num_valid"] > 0.3 * slc.size
+        # invalid geo2rdr pixels (-999999) resample to zero
+        assert not fused["slc"][offs["rgoff"] == -999999.0].any()
+    plan = _capi.GeoPlan(gp, lat=c["lat"], lon=c["lon"], hgt=c["hgt"])
+    with pytest.raises(_capi.B200Error, match="executed"):
+        _capi.lib()  # keep the library loaded
+        plan.last_params = gp
+        _capi.resamp_slc_from_geo_plan(plan, slc, **rkw)
+    plan.close()
