@@ -169,6 +169,11 @@ __global__ void k_line_setup(const __grid_constant__ TopoConst C, OrbitView orb,
 #ifndef B2_TOPO_MINBLOCKS
 #define B2_TOPO_MINBLOCKS 8
 #endif
+// the split solve kernel: 7 CTAs / SM = 72 registers; at 64 it spills 130 bytes into the iteration loop (measured
+// 9.40 vs 9.58 ms per 1500 x 25000 lines with the biquintic interpolator)
+#ifndef B2_SOLVE_MINBLOCKS
+#define B2_SOLVE_MINBLOCKS 7
+#endif
 #ifndef B2_FINAL_MINBLOCKS
 #define B2_FINAL_MINBLOCKS 6
 #endif
@@ -335,7 +340,7 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
 __host__ __device__ inline int solve_segs_per_line(int width) { return (width + kSegMax - 1) / kSegMax; }
 
 template <int METHOD, bool REF>
-__global__ void __launch_bounds__(kTopoBlock, B2_TOPO_MINBLOCKS)
+__global__ void __launch_bounds__(kTopoBlock, B2_SOLVE_MINBLOCKS)
 k_topo_solve(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines,
              double *__restrict__ zsch_out, TopoStats *stats)
 {
