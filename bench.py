@@ -310,11 +310,34 @@ def alloc_host(shape, dtype, capi):
         return np.empty(shape, dtype), False
 
 
+def bind_to_gpu_local_cpus(dev):
+    """Multi-GPU runs: keep the rank (and therefore its page-locked staging buffers, first-touched below) on the CPUs
+    NVML reports as local to its GPU, so that host<->device copies do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(dev))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, ranks):
     from isce2_b200 import _capi as capi
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; this arm has no CPU fallback (use --impl reference for the CPU baseline)")
     dev = ranks.local_rank % capi.device_count()
+    if ranks.world > 1:
+        bound = bind_to_gpu_local_cpus(dev)
+        if bound:
+            log(f"[bench] rank {ranks.rank}: bound to the {len(bound)} CPUs local to GPU {dev}")
     w, sc, sec = build_workload(args.workload, args.lines)
     line0, nlines = shard(sc.length, ranks.rank, ranks.world)
     npix_local = nlines * sc.width
@@ -406,7 +429,7 @@ def run_b200(args, ranks):
         return r
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         e2e_step()
     ranks.barrier()
     e2e_times = []
