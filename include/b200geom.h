@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200GEOM_ABI_VERSION 1
+#define B200GEOM_ABI_VERSION 2
 
 enum {
     B200_OK = 0,

@@ -355,7 +355,7 @@ static int topo_plan_build(b200_topo_plan *pl, const void *dem, int dem_dtype, c
     CK(dmalloc(&d_bbox, sizeof h_bbox));
     {
         TopoConst Cb = C;
-        Cb.dem = DemView{nullptr, 0, 0, nullptr};
+        Cb.dem = DemView{nullptr, 0, 0, nullptr, nullptr, 0};
         Cb.rho_image = pl->d_rho0; // row 1 of the image, or NULL -> polynomial
         launch_topo_bbox(Cb, pl->orb.view, d_bbox, s);
         pl->launches++;

@@ -642,22 +642,6 @@ __device__ bool block_stable_ranks(const double *v, int n, const double *pm, con
     return sorted;
 }
 
-// block-wide "is non-decreasing" test of a[0..n) (adjacent compares; NaNs count as ordered, like the reference's
-// insertion sort, which never moves across a false comparison)
-__device__ bool block_is_sorted(const double *a, int n, int *s_flag)
-{
-    if (threadIdx.x == 0) *s_flag = 1;
-    __syncthreads();
-    int bad = 0;
-    for (int i = threadIdx.x + 1; i < n; i += blockDim.x)
-        if (a[i - 1] > a[i]) bad = 1;
-    if (bad) *s_flag = 0; // benign race: everybody writes the same value
-    __syncthreads();
-    const int r = *s_flag;
-    __syncthreads();
-    return r != 0;
-}
-
 // Forward scan of the reference (:791-799, :834-842):  aa = v(1); for i = 2..nflag: if v(i) <= aa flag else aa = v(i).
 // Flagged samples never exceed aa, so aa is the plain prefix maximum: flag[i] |= bit if v[i] <= max(v[0..i-1]).
 template <typename T, typename S, typename Op>

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/b200geom.h but not exported by libb200geom.so"
     assert sorted(_capi.EXPORTS) == declared
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2  # 2: geozero + resamp_slc entry points
 
 
 def test_struct_layouts_match_header():
@@ -48,7 +48,9 @@ def test_struct_layouts_match_header():
     for cname, ctype in (("b200_topo_params", _capi.TopoParams), ("b200_topo_result", _capi.TopoResult),
                          ("b200_geo_params", _capi.GeoParams), ("b200_geo_result", _capi.GeoResult),
                          ("b200_topo_outputs", _capi.TopoOutputs), ("b200_geo_outputs", _capi.GeoOutputs),
-                         ("b200_orbit", _capi.Orbit), ("b200_poly2d", _capi.Poly2d), ("b200_poly1d", _capi.Poly1d)):
+                         ("b200_orbit", _capi.Orbit), ("b200_poly2d", _capi.Poly2d), ("b200_poly1d", _capi.Poly1d),
+                         ("b200_geozero_params", _capi.GeozeroParams), ("b200_geozero_result", _capi.GeozeroResult),
+                         ("b200_resamp_params", _capi.ResampParams), ("b200_resamp_result", _capi.ResampResult)):
         assert fields(cname) == [f[0] for f in ctype._fields_], cname
 
 
@@ -65,6 +67,17 @@ def test_no_cpu_fallback():
     z = np.zeros((4, 64))
     with pytest.raises(_capi.B200Error) as ei:
         _capi.geo2rdr_run(gp, z, z, z, sc.orbit_t, sc.orbit_pos, sc.orbit_vel)
+    assert ei.value.code == -2
+    zp = _capi.geozero_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                              delta_lon=sc.delta_lon, snwe=(sc.first_lat - 0.05, sc.first_lat - 0.01, sc.first_lon + 0.01,
+                                                            sc.first_lon + 0.05),
+                              length=4, width=64, r0=sc.r0, dr=sc.dr, prf=sc.prf, t0=sc.t0, wvl=sc.wvl)
+    assert min(_capi.geozero_grid(zp)) > 0  # sizing the output grid needs no device
+    with pytest.raises(_capi.B200Error) as ei:
+        _capi.geozero_run(zp, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, np.zeros((4, 64), np.float32))
+    assert ei.value.code == -2
+    with pytest.raises(_capi.B200Error) as ei:
+        _capi.resamp_slc_run(np.zeros((16, 16), np.complex64), (16, 16))
     assert ei.value.code == -2
 
 
