@@ -135,3 +135,35 @@ def test_bad_dem_samples_wrong_look_side_and_rows_outside_the_dem():
     n = orc.geozero(dem=dem, image=img, method="NEAREST", side=sc.side, **kw2)
     assert n["grid"]["max_lat_idx"] == -5
     assert n["num_outside_dem"] == 5 * dem.shape[1] and not n["geo"][:5].any() and not n["dem_crop"][:5].any()
+
+
+def test_geozero_solve_against_the_reference_pythons_own_geo2rdr(golden):
+    """tests/golden/ref_python_vectors.json holds single-point solutions computed by importing the reference's Python
+    (isceobj.Orbit.Orbit.rdr2geo / geo2rdr on its 15-vector orbit fixture): geozero's fixed-point iteration solves the
+    same zero-Doppler equation, so the image coordinates it assigns to that ground point must be the golden azimuth
+    time and range (to geozero's own stopping tolerance of 5e-7 s and the 1 us resolution of Python datetimes)."""
+    rows = np.array(golden["orbit_rsc"])
+    n_checked = 0
+    for e in golden["rdr2geo"]:
+        lat, lon, h = e["llh"][0], e["llh"][1], e["height"]
+        spacing, half = 1.0 / 1200, 40
+        dem = np.full((2 * half + 1, 2 * half + 1), h, np.float32)
+        first_lat, first_lon = lat + half * spacing, lon - half * spacing
+        prf, dr = 1000.0, 1.0
+        t0, r0 = e["t"] - 0.5, e["rng"] - 2000.0
+        L, W = 1001, 4001
+        snwe = (lat - 2.2 * spacing, lat + 2.2 * spacing, lon - 2.2 * spacing, lon + 2.2 * spacing)
+        p = orc.geozero_params(dem_shape=dem.shape, first_lat=first_lat, first_lon=first_lon, delta_lat=-spacing,
+                               delta_lon=spacing, snwe=snwe, length=L, width=W, r0=r0, dr=dr, prf=prf, t0=t0, wvl=0.056)
+        g = orc.geozero_grid(p)
+        r = orc.geozero(dem=dem, image=np.zeros((L, W), np.float32), orbit_t=rows[:, 0], orbit_pos=rows[:, 1:4],
+                        orbit_vel=rows[:, 4:7], method="NEAREST", side=e["side"], first_lat=first_lat, first_lon=first_lon,
+                        delta_lat=-spacing, delta_lon=spacing, snwe=snwe, r0=r0, dr=dr, prf=prf, t0=t0, wvl=0.056)
+        i, j = half - g["max_lat_idx"], half - g["min_lon_idx"]  # the grid node that is the golden point
+        assert 0 <= i < g["geo_len"] and 0 <= j < g["geo_wid"]
+        t_geo = t0 + (r["az_idx"][i, j] - 1.0) / prf
+        rng_geo = r0 + (r["rng_idx"][i, j] - 1.0) * dr
+        assert abs(t_geo - e["t"]) < 6e-7 and abs(t_geo - e["geo2rdr_t"]) < 2e-6, (t_geo, e["t"], e["geo2rdr_t"])
+        assert abs(rng_geo - e["rng"]) < 2e-4 and abs(rng_geo - e["geo2rdr_rng"]) < 2e-4, (rng_geo, e["rng"])
+        n_checked += 1
+    assert n_checked >= 4
