@@ -12,8 +12,10 @@ pixel counts once when it has been through both.
 
   value : device-resident throughput (DEM, orbit and the previous layers already in HBM; CUDA events on the launch
           stream, summed over the kernels of the step; max over ranks).
-  e2e   : the same step through the reference-facing C-ABI calls b200_topo_run / b200_geo2rdr_run with HOST
-          buffers (pinned), host<->device copies inside the timed region.
+  e2e   : the same step through the C ABI with HOST buffers (pinned), host<->device copies inside the timed region:
+          one b200_topo_geo2rdr_run call (host DEM and orbits in; every topo layer and the offsets out to the host;
+          geo2rdr runs on the layers while they are resident in HBM).  `e2e_two_calls` is the reference's own call
+          sequence b200_topo_run -> host lat/lon/hgt -> b200_geo2rdr_run, which sends the 24 B/pixel back up.
   N > 1 : one process per GPU (torchrun); the swath is sharded by contiguous azimuth line blocks, no collective on
           the data path (torch.distributed/gloo is used only for the timing barrier and the max over ranks).
 """
@@ -421,30 +423,52 @@ def run_b200(args, ranks):
                                   dr=gk["dr"], prf=gk["prf"], t0=gk["t0"] + line0 / sc.prf, wvl=gk["wvl"], side=gk["side"],
                                   orbit_method=w["orbit_method"], device=dev, out_f32=True)
 
-    def e2e_step():
+    def e2e_step_two_calls():
+        # the reference's own call sequence: topo verb -> host lat / lon / hgt -> geo2rdr verb
         capi.topo_run(tparams, dem_host, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, slr,
                       want_los=True, want_inc=w["inc"], want_mask=w["mask"], out=outs)
         r = capi.geo2rdr_run(gparams_e2e, outs["lat"], outs["lon"], outs["hgt"], gk["orbit_t"], gk["orbit_pos"], gk["orbit_vel"],
                              want=("azoff", "rgoff"), out=gouts)
         return r
 
+    fused_job = dict(params=gparams, orbit=(gk["orbit_t"], gk["orbit_pos"], gk["orbit_vel"]), want=("azoff", "rgoff"), out=gouts)
+
+    def e2e_step_fused():
+        # one call: same host inputs, same host outputs; geo2rdr runs on the layers while they are resident in HBM
+        _, geos = capi.topo_geo2rdr_run(tparams, dem_host, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [fused_job],
+                                        slr, want_los=True, want_inc=w["inc"], want_mask=w["mask"], out=outs)
+        return geos[0]
+
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(args.warmup):
-        e2e_step()
-    ranks.barrier()
-    e2e_times = []
-    for _ in range(e2e_steps):
-        w0 = time.perf_counter()
-        r = e2e_step()
-        e2e_times.append(time.perf_counter() - w0)
-    log(f"[bench] rank {ranks.rank} e2e step times (ms): {[round(1e3 * t, 1) for t in e2e_times]}")
-    wall_e2e = sum(e2e_times) / e2e_steps
-    wall_e2e = ranks.reduce_max(wall_e2e)
-    ranks.barrier()
+
+    def time_e2e(step, tag):
+        for _ in range(args.warmup):
+            step()
+        ranks.barrier()
+        times = []
+        for _ in range(e2e_steps):
+            w0 = time.perf_counter()
+            r = step()
+            times.append(time.perf_counter() - w0)
+        log(f"[bench] rank {ranks.rank} e2e ({tag}) step times (ms): {[round(1e3 * t, 1) for t in times]}")
+        wall = ranks.reduce_max(sum(times) / e2e_steps)
+        ranks.barrier()
+        return wall, r
+
+    wall_two, r = time_e2e(e2e_step_two_calls, "b200_topo_run + b200_geo2rdr_run")
+    check = {k: v.copy() for k, v in gouts.items() if v is not None} if npix_local <= 64_000_000 else None
+    wall_e2e, r_fused = time_e2e(e2e_step_fused, "b200_topo_geo2rdr_run")
+    if check is not None:  # the fused call must leave the very same offsets in the host buffers
+        for k, v in check.items():
+            if not np.array_equal(v, gouts[k]):
+                raise SystemExit(f"bench.py: fused and two-call {k} differ")
+    if r_fused["num_valid"] != r["num_valid"]:
+        raise SystemExit("bench.py: fused and two-call geo2rdr disagree on the valid pixel count")
     e2e_value = npix_total / wall_e2e / 1e6
-    h2d = sc.dem.nbytes * 0 + res.dem_nx * res.dem_ny * 4 + 3 * 8 * npix_local + 2 * 7 * 8 * len(sc.orbit_t)
+    small = res.dem_nx * res.dem_ny * 4 + 2 * 7 * 8 * len(sc.orbit_t)
     d2h = sum(v.nbytes for v in outs.values() if v is not None) + sum(v.nbytes for v in gouts.values() if v is not None)
-    h2d = ranks.reduce_sum(h2d)
+    h2d_two = ranks.reduce_sum(small + 3 * 8 * npix_local)
+    h2d = ranks.reduce_sum(small)
     d2h = ranks.reduce_sum(d2h)
     valid_frac = r["num_valid"] / float(npix_local)
 
@@ -514,7 +538,12 @@ def run_b200(args, ranks):
                            "dem_crop": [res.dem_ny, res.dem_nx]},
                 "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": wall_e2e * 1e3, "steps": e2e_steps, "pinned_host_buffers": bool(pinned),
-                        "api": "b200_topo_run + b200_geo2rdr_run (host buffers in, host buffers out)"},
+                        "api": "b200_topo_geo2rdr_run (host DEM + orbits in; host lat/lon/hgt/los/inc/mask + range/azimuth "
+                               "offsets out; geo2rdr consumes the layers in HBM)"},
+                "e2e_two_calls": {"value": npix_total / wall_two / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d_two),
+                                  "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_two * 1e3, "steps": e2e_steps,
+                                  "api": "b200_topo_run + b200_geo2rdr_run (the reference's call sequence: lat/lon/hgt go "
+                                         "back up through the host)"},
                 "gpu_launches": int(args.steps * ((2 if split else 1) + (1 if w["mask"] else 0) + 2)),
                 "clocks": clocks,
                 "roofline": roofline,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200GEOM_ABI_VERSION 2
+#define B200GEOM_ABI_VERSION 3
 
 enum {
     B200_OK = 0,
@@ -212,6 +212,28 @@ int b200_geo_plan_execute(b200_geo_plan *plan, const b200_geo_params *p, const b
 int b200_geo_plan_fetch(b200_geo_plan *plan, const b200_geo_outputs *out, b200_geo_result *res, char *err,
                         size_t errlen);
 void b200_geo_plan_destroy(b200_geo_plan *plan);
+
+/* Fused form of the two verbs: topo_Py followed by geo2rdr_Py on the layers it just wrote, the sequence of
+ * stripmapApp (runTopo -> runGeo2rdr, components/isceobj/StripmapProc/runGeo2rdr.py:46-110), topsApp (runTopo ->
+ * runCoarseOffsets / runFineOffsets' runGeo2rdrCPU, components/isceobj/TopsProc/runFineOffsets.py:16-67) and topsStack (reference geometry -> one
+ * geo2rdr per secondary date, contrib/stack/topsStack/geo2rdr.py:233-302).  The reference hands lat / lon / hgt from
+ * one to the other through the .rdr files; here every block of lines goes topo kernels -> geo2rdr kernel(s) on the
+ * layers still resident in HBM -> one device-to-host stream carrying the topo layers and the offsets, so the 24 B/pixel
+ * host-to-device trip of the standalone geo2rdr verb disappears.  Outputs are bit-identical to b200_topo_run followed
+ * by b200_geo2rdr_run on its lat / lon / hgt (tests/test_gpu_fused.py).  In each job p->dem_width / dem_length must equal
+ * the topo grid; p->line0 / nlines / device are taken from the topo params. */
+typedef struct {
+    const b200_geo_params *p;
+    const b200_orbit *orbit;      /* secondary (or the same) orbit */
+    const b200_poly1d *dop;
+    const b200_geo_outputs *out;  /* host buffers holding the block's rows, as in b200_geo2rdr_run */
+    b200_geo_result *res;         /* may be NULL */
+} b200_geo_job;
+
+int b200_topo_geo2rdr_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                          const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                          const b200_topo_outputs *out, b200_topo_result *res, int njobs, const b200_geo_job *jobs,
+                          char *err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------ */
 /* geozero (geocoding on the zero-Doppler geometry) -- SURVEY 8(f) row N3                      */

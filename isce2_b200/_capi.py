@@ -87,6 +87,11 @@ class GeoResult(C.Structure):
                 ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
 
 
+class GeoJob(C.Structure):
+    _fields_ = [("p", C.POINTER(GeoParams)), ("orbit", C.POINTER(Orbit)), ("dop", C.POINTER(Poly1d)),
+                ("out", C.POINTER(GeoOutputs)), ("res", C.POINTER(GeoResult))]
+
+
 class GeozeroParams(C.Structure):
     _fields_ = [("major", C.c_double), ("e2", C.c_double), ("min_lat", C.c_double), ("max_lat", C.c_double),
                 ("min_lon", C.c_double), ("max_lon", C.c_double), ("drho", C.c_double), ("rho0", C.c_double),
@@ -123,7 +128,7 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
-           "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan"]
+           "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run"]
 
 _lib = None
 
@@ -140,6 +145,9 @@ def lib():
     err = [C.c_char_p, C.c_size_t]
     L.b200_topo_run.argtypes = [C.POINTER(TopoParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly2d),
                                 C.POINTER(Poly2d), _dp, C.POINTER(TopoOutputs), C.POINTER(TopoResult)] + err
+    L.b200_topo_geo2rdr_run.argtypes = [C.POINTER(TopoParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly2d),
+                                        C.POINTER(Poly2d), _dp, C.POINTER(TopoOutputs), C.POINTER(TopoResult), C.c_int,
+                                        C.POINTER(GeoJob)] + err
     L.b200_topo_plan_create.argtypes = [C.POINTER(TopoParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly2d),
                                         C.POINTER(Poly2d), _dp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + err
     L.b200_topo_plan_execute.argtypes = [C.c_void_p, _fp] + err
@@ -408,6 +416,61 @@ def geo2rdr_run(params, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, doppler_co
     out = dict(out)
     out.update(_result_dict(res))
     return out
+
+
+def topo_geo2rdr_run(params, dem, orbit_t, orbit_pos, orbit_vel, doppler_coeffs, geo_jobs, slrng_coeffs=None, rho_image=None,
+                     want_los=True, want_inc=False, want_mask=False, out=None, doppler_poly=None, slrng_poly=None):
+    """Fused b200_topo_geo2rdr_run: topo over the block of `params`, then every job of `geo_jobs` on the lat / lon / hgt still
+    resident in HBM.  Each job is a dict(params=GeoParams, orbit=(t, pos, vel), doppler=(coeffs, mean, norm),
+    want=(...keys of azt/rgm/azoff/rgoff), out=None | dict of host arrays holding the block's rows).
+    Returns (topo dict, [geo dicts])."""
+    L = lib()
+    keep = _Keep()
+    dem, code = _dem_arg(dem)
+    orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
+    dop = doppler_poly if doppler_poly is not None else make_poly2d(keep, doppler_coeffs)
+    slr = slrng_poly if slrng_poly is not None else (make_poly2d(keep, slrng_coeffs) if slrng_coeffs is not None else None)
+    rimg = keep.d(rho_image) if rho_image is not None else None
+    n = params.length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+    w = params.width
+    if out is None:
+        out = dict(lat=np.empty((n, w)), lon=np.empty((n, w)), hgt=np.empty((n, w)),
+                   los=np.empty((n, 2, w), np.float32) if want_los else None,
+                   inc=np.empty((n, 2, w), np.float32) if want_inc else None,
+                   mask=np.empty((n, w), np.int8) if want_mask else None)
+    o = TopoOutputs(out["lat"].ctypes.data_as(_dp), out["lon"].ctypes.data_as(_dp), out["hgt"].ctypes.data_as(_dp),
+                    out["los"].ctypes.data_as(_fp) if out.get("los") is not None else None,
+                    out["inc"].ctypes.data_as(_fp) if out.get("inc") is not None else None,
+                    out["mask"].ctypes.data_as(C.POINTER(C.c_int8)) if out.get("mask") is not None else None)
+    jobs = (GeoJob * max(len(geo_jobs), 1))()
+    gouts, gres = [], []
+    for j, jb in enumerate(geo_jobs):
+        gp = jb["params"]
+        # the block is the topo block: the output buffers are sized from it
+        gp_blk = GeoParams.from_buffer_copy(gp)
+        gp_blk.line0, gp_blk.nlines = max(params.line0, 0), n
+        jo, jos = _geo_out(gp_blk, tuple(jb.get("want", _GEO_KEYS)), jb.get("out"))
+        jorb = make_orbit(keep, *jb["orbit"])
+        dc = jb.get("doppler", ((0.0,), 0.0, 1.0))
+        jdop = make_poly1d(keep, *dc)
+        r = GeoResult()
+        keep.refs += [gp_blk, jos, jorb, jdop, r]
+        jobs[j] = GeoJob(C.pointer(gp_blk), C.pointer(jorb), C.pointer(jdop), C.pointer(jos), C.pointer(r))
+        gouts.append(jo)
+        gres.append(r)
+    res = TopoResult()
+    e = _errbuf()
+    _check(L.b200_topo_geo2rdr_run(C.byref(params), dem.ctypes.data_as(C.c_void_p), code, C.byref(orb), C.byref(dop),
+                                   C.byref(slr) if slr is not None else None, rimg, C.byref(o), C.byref(res), len(geo_jobs), jobs,
+                                   e, 512), e)
+    out = dict(out)
+    out.update(_result_dict(res))
+    geos = []
+    for jo, r in zip(gouts, gres):
+        d = dict(jo)
+        d.update(_result_dict(r))
+        geos.append(d)
+    return out, geos
 
 
 class GeoPlan:

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <memory>
 #include <vector>
 
 #include "geo2rdr_kernels.cuh"
@@ -608,100 +609,6 @@ extern "C" int b200_topo_plan_device_layers(b200_topo_plan *pl, const double **l
 
 extern "C" void b200_topo_plan_destroy(b200_topo_plan *pl) { delete pl; }
 
-extern "C" int b200_topo_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
-                             const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
-                             const b200_topo_outputs *out, b200_topo_result *res, char *err, size_t errlen)
-{
-    if (!out || !out->lat || !out->lon || !out->hgt)
-        return fail(err, errlen, B200_EINVAL, "lat/lon/hgt output buffers are mandatory (Topozero.py:274-302)");
-    const double t0 = now_ms();
-    b200_topo_plan *pl = nullptr;
-    int rc = b200_topo_plan_create(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out->los != nullptr, out->inc != nullptr,
-                                   out->mask != nullptr, &pl, err, errlen);
-    if (rc != B200_OK) return rc;
-    struct PlanGuard {
-        b200_topo_plan *p;
-        ~PlanGuard() { delete p; }
-    } pg{pl};
-    // ---- two-stage pipeline over blocks of lines: kernels(c+1) | D2H(c) ----
-    struct Streams {
-        cudaStream_t d = nullptr;
-        std::vector<cudaEvent_t> ev;
-        ~Streams()
-        {
-            for (cudaEvent_t e : ev) cudaEventDestroy(e);
-            if (d) cudaStreamDestroy(d);
-        }
-    } st;
-    CK(cudaStreamCreateWithFlags(&st.d, cudaStreamNonBlocking));
-    cudaStream_t s = pl->stream;
-    TopoStats init;
-    init.min_lat = init.min_lon = 0x7fffffffffffffffLL;
-    init.max_lat = init.max_lon = (long long)0x8000000000000000ULL;
-    init.converged = init.iterations = 0;
-    CK(cudaMemcpyAsync(pl->d_stats, &init, sizeof init, cudaMemcpyHostToDevice, s));
-    CK(cudaEventRecord(pl->ev0, s));
-    const size_t w = (size_t)pl->p.width;
-    const int cl = chunk_lines(pl->p.width, pl->nlines);
-    int launches = 0;
-    auto launch_chunk = [&](int c0, int n, cudaEvent_t done) -> int {
-        const size_t o = (size_t)c0 * w;
-        TopoLayers L = pl->layers;
-        L.lat += o; L.lon += o; L.hgt += o; L.ctrack += o;
-        if (L.los) L.los += 2 * o;
-        if (L.inc) L.inc += 2 * o;
-        if (L.mask) L.mask += o;
-        if (L.elev) L.elev += o;
-        if (launch_topo_pixels(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->d_stats, s) != 0) return -1;
-        launches += topo_pixel_launches(pl->C.method);
-        if (L.mask) {
-            const int g = pl->mask_grid < n ? pl->mask_grid : n;
-            if (launch_topo_mask(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->dem_max, pl->scr, g, s) != 0) return -1;
-            launches++;
-        }
-        return cudaEventRecord(done, s) == cudaSuccess ? 0 : -1;
-    };
-    auto copy_chunk = [&](int c0, int n, cudaEvent_t done) -> cudaError_t {
-        const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
-        cudaError_t e = cudaStreamWaitEvent(st.d, done, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lat + o, pl->layers.lat + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lon + o, pl->layers.lon + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->hgt + o, pl->layers.hgt + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->los && pl->layers.los)
-            e = cudaMemcpyAsync(out->los + 2 * o, pl->layers.los + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->inc && pl->layers.inc)
-            e = cudaMemcpyAsync(out->inc + 2 * o, pl->layers.inc + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->mask && pl->layers.mask)
-            e = cudaMemcpyAsync(out->mask + o, pl->layers.mask + o, cnt, cudaMemcpyDeviceToHost, st.d);
-        return e;
-    };
-    const int nchunks = (pl->nlines + cl - 1) / cl;
-    st.ev.resize(nchunks, nullptr);
-    for (int c = 0; c < nchunks; c++) CK(cudaEventCreateWithFlags(&st.ev[c], cudaEventDisableTiming));
-    // kernels of chunk c+1 are queued before the (possibly host-blocking, pageable) copies of chunk c
-    if (launch_chunk(0, cl < pl->nlines ? cl : pl->nlines, st.ev[0]) != 0)
-        return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
-    for (int c = 0; c < nchunks; c++) {
-        const int c0 = c * cl, n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
-        if (c + 1 < nchunks) {
-            const int d0 = (c + 1) * cl, dn = (d0 + cl <= pl->nlines) ? cl : pl->nlines - d0;
-            if (launch_chunk(d0, dn, st.ev[c + 1]) != 0) return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
-        }
-        CK(copy_chunk(c0, n, st.ev[c]));
-    }
-    CK(cudaEventRecord(pl->ev1, s));
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s));
-    CK(cudaStreamSynchronize(st.d));
-    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
-    pl->ms_pixels = pl->ms_solve = pl->ms_mask = 0.f; // not separable in the pipelined form
-    pl->launches += launches;
-    pl->executed = true;
-    rc = b200_topo_plan_fetch(pl, nullptr, res, err, errlen);
-    if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
-    return rc;
-}
-
 // =================================================================================================
 // geo2rdr
 // =================================================================================================
@@ -1074,6 +981,178 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
     rc = b200_geo_plan_fetch(pl, nullptr, res, err, errlen);
     if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
     return rc;
+}
+
+// =================================================================================================
+// the topo verb (host buffers), optionally with geo2rdr jobs fused behind every block of lines
+// =================================================================================================
+static int topo_run_impl(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                         const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                         const b200_topo_outputs *out, b200_topo_result *res, int njobs, const b200_geo_job *jobs, char *err,
+                         size_t errlen)
+{
+    if (!out || !out->lat || !out->lon || !out->hgt)
+        return fail(err, errlen, B200_EINVAL, "lat/lon/hgt output buffers are mandatory (Topozero.py:274-302)");
+    const double t0 = now_ms();
+    b200_topo_plan *pl = nullptr;
+    int rc = b200_topo_plan_create(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out->los != nullptr, out->inc != nullptr,
+                                   out->mask != nullptr, &pl, err, errlen);
+    if (rc != B200_OK) return rc;
+    struct PlanGuard {
+        b200_topo_plan *p;
+        ~PlanGuard() { delete p; }
+    } pg{pl};
+    // ---- two-stage pipeline over blocks of lines: kernels(c+1) | D2H(c) ----
+    struct Streams {
+        cudaStream_t d = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Streams()
+        {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            if (d) cudaStreamDestroy(d);
+        }
+    } st;
+    CK(cudaStreamCreateWithFlags(&st.d, cudaStreamNonBlocking));
+    cudaStream_t s = pl->stream;
+    // ---- fused geo2rdr jobs: each borrows the resident lat / lon / hgt of this block (no trip through the host) ----
+    struct Job {
+        std::unique_ptr<b200_geo_plan> gp;
+        std::unique_ptr<GeoRun> R;
+        b200_geo_params p{};
+        void *hout[4] = {nullptr, nullptr, nullptr, nullptr};
+        size_t esz = 4;
+    };
+    std::vector<Job> fused((size_t)(njobs > 0 ? njobs : 0));
+    for (int j = 0; j < njobs; j++) {
+        const b200_geo_job &jb = jobs[j];
+        Job &J = fused[j];
+        if (!jb.p || !jb.out || (!jb.out->azt && !jb.out->rgm && !jb.out->azoff && !jb.out->rgoff))
+            return fail(err, errlen, B200_EINVAL, "No outputs requested from geo2rdr. Check again. (job %d)", j);
+        if (jb.p->dem_width != pl->p.width || jb.p->dem_length != pl->p.length)
+            return fail(err, errlen, B200_EINVAL, "fused geo2rdr job %d: lat/lon/hgt grid %d x %d is not the topo grid %d x %d", j,
+                        jb.p->dem_length, jb.p->dem_width, pl->p.length, pl->p.width);
+        J.p = *jb.p;
+        J.p.line0 = pl->line0;
+        J.p.nlines = pl->nlines;
+        J.p.device = pl->p.device;
+        J.gp.reset(new (std::nothrow) b200_geo_plan);
+        J.R.reset(new (std::nothrow) GeoRun);
+        if (!J.gp || !J.R) return fail(err, errlen, B200_ENOMEM, "out of host memory");
+        J.gp->p = J.p;
+        J.gp->owns_inputs = false;
+        if ((rc = geo_plan_common(J.gp.get(), err, errlen)) != B200_OK) return rc;
+        J.gp->d_lat = pl->layers.lat;
+        J.gp->d_lon = pl->layers.lon;
+        J.gp->d_hgt = pl->layers.hgt;
+        if ((rc = geo_prepare(J.gp.get(), J.p, jb.orbit, jb.dop, *J.R, err, errlen)) != B200_OK) return rc;
+        const int want[4] = {jb.out->azt != nullptr, jb.out->rgm != nullptr, jb.out->azoff != nullptr, jb.out->rgoff != nullptr};
+        if ((rc = geo_alloc_outputs(J.gp.get(), J.p, want, err, errlen)) != B200_OK) return rc;
+        CK(cudaMemsetAsync(J.gp->d_stats, 0, sizeof(GeoStats), J.gp->stream));
+        CK(cudaStreamSynchronize(J.gp->stream));
+        J.hout[0] = jb.out->azt; J.hout[1] = jb.out->rgm; J.hout[2] = jb.out->azoff; J.hout[3] = jb.out->rgoff;
+        J.esz = J.p.out_f32 ? 4 : 8;
+        J.gp->launches = 1;
+    }
+    TopoStats init;
+    init.min_lat = init.min_lon = 0x7fffffffffffffffLL;
+    init.max_lat = init.max_lon = (long long)0x8000000000000000ULL;
+    init.converged = init.iterations = 0;
+    CK(cudaMemcpyAsync(pl->d_stats, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(pl->ev0, s));
+    const size_t w = (size_t)pl->p.width;
+    const int cl = chunk_lines(pl->p.width, pl->nlines);
+    int launches = 0;
+    auto launch_chunk = [&](int c0, int n, cudaEvent_t done) -> int {
+        const size_t o = (size_t)c0 * w;
+        TopoLayers L = pl->layers;
+        L.lat += o; L.lon += o; L.hgt += o; L.ctrack += o;
+        if (L.los) L.los += 2 * o;
+        if (L.inc) L.inc += 2 * o;
+        if (L.mask) L.mask += o;
+        if (L.elev) L.elev += o;
+        if (launch_topo_pixels(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->d_stats, s) != 0) return -1;
+        launches += topo_pixel_launches(pl->C.method);
+        if (L.mask) {
+            const int g = pl->mask_grid < n ? pl->mask_grid : n;
+            if (launch_topo_mask(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->dem_max, pl->scr, g, s) != 0) return -1;
+            launches++;
+        }
+        for (Job &J : fused) { // same stream: the block's lat / lon / hgt are complete
+            GeoLayers G{pl->layers.lat + o, pl->layers.lon + o, pl->layers.hgt + o, nullptr, nullptr, nullptr, nullptr};
+            void **lo[4] = {&G.azt, &G.rgm, &G.azoff, &G.rgoff};
+            for (int i = 0; i < 4; i++)
+                if (J.gp->d_out[i]) *lo[i] = (char *)J.gp->d_out[i] + o * J.esz;
+            if (geo_launch(*J.R, pl->line0 + c0, n, G, J.p.out_f32, J.gp->d_stats, s) != 0) return -1;
+            J.gp->launches++;
+        }
+        return cudaEventRecord(done, s) == cudaSuccess ? 0 : -1;
+    };
+    auto copy_chunk = [&](int c0, int n, cudaEvent_t done) -> cudaError_t {
+        const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
+        cudaError_t e = cudaStreamWaitEvent(st.d, done, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lat + o, pl->layers.lat + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lon + o, pl->layers.lon + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->hgt + o, pl->layers.hgt + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->los && pl->layers.los)
+            e = cudaMemcpyAsync(out->los + 2 * o, pl->layers.los + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->inc && pl->layers.inc)
+            e = cudaMemcpyAsync(out->inc + 2 * o, pl->layers.inc + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess && out->mask && pl->layers.mask)
+            e = cudaMemcpyAsync(out->mask + o, pl->layers.mask + o, cnt, cudaMemcpyDeviceToHost, st.d);
+        for (Job &J : fused)
+            for (int i = 0; i < 4; i++)
+                if (e == cudaSuccess && J.hout[i] && J.gp->d_out[i])
+                    e = cudaMemcpyAsync((char *)J.hout[i] + o * J.esz, (char *)J.gp->d_out[i] + o * J.esz, cnt * J.esz,
+                                        cudaMemcpyDeviceToHost, st.d);
+        return e;
+    };
+    const int nchunks = (pl->nlines + cl - 1) / cl;
+    st.ev.resize(nchunks, nullptr);
+    for (int c = 0; c < nchunks; c++) CK(cudaEventCreateWithFlags(&st.ev[c], cudaEventDisableTiming));
+    // kernels of chunk c+1 are queued before the (possibly host-blocking, pageable) copies of chunk c
+    if (launch_chunk(0, cl < pl->nlines ? cl : pl->nlines, st.ev[0]) != 0)
+        return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
+    for (int c = 0; c < nchunks; c++) {
+        const int c0 = c * cl, n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
+        if (c + 1 < nchunks) {
+            const int d0 = (c + 1) * cl, dn = (d0 + cl <= pl->nlines) ? cl : pl->nlines - d0;
+            if (launch_chunk(d0, dn, st.ev[c + 1]) != 0) return fail(err, errlen, B200_EINVAL, "cannot launch the topo kernels");
+        }
+        CK(copy_chunk(c0, n, st.ev[c]));
+    }
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(st.d));
+    CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
+    pl->ms_pixels = pl->ms_solve = pl->ms_mask = 0.f; // not separable in the pipelined form
+    pl->launches += launches;
+    pl->executed = true;
+    rc = b200_topo_plan_fetch(pl, nullptr, res, err, errlen);
+    if (rc == B200_OK && res) res->ms_total = (float)(now_ms() - t0);
+    for (int j = 0; j < njobs && rc == B200_OK; j++) {
+        fused[j].gp->executed = true;
+        fused[j].gp->ms_kernels = 0.f; // not separable from the topo kernels of the same stream (see the topo result)
+        rc = b200_geo_plan_fetch(fused[j].gp.get(), nullptr, jobs[j].res, err, errlen);
+        if (rc == B200_OK && jobs[j].res) jobs[j].res->ms_total = (float)(now_ms() - t0);
+    }
+    return rc;
+}
+
+extern "C" int b200_topo_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                             const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                             const b200_topo_outputs *out, b200_topo_result *res, char *err, size_t errlen)
+{
+    return topo_run_impl(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out, res, 0, nullptr, err, errlen);
+}
+
+extern "C" int b200_topo_geo2rdr_run(const b200_topo_params *p, const void *dem, int dem_dtype, const b200_orbit *orbit,
+                                     const b200_poly2d *dop, const b200_poly2d *slrng, const double *rho_image,
+                                     const b200_topo_outputs *out, b200_topo_result *res, int njobs, const b200_geo_job *jobs,
+                                     char *err, size_t errlen)
+{
+    if (njobs < 0 || (njobs > 0 && !jobs)) return fail(err, errlen, B200_EINVAL, "bad geo2rdr job list");
+    return topo_run_impl(p, dem, dem_dtype, orbit, dop, slrng, rho_image, out, res, njobs, jobs, err, errlen);
 }
 
 // =================================================================================================

@@ -151,6 +151,47 @@ class Geo2rdr(Component):
         self.gpuTimings = [{k: r[k] for k in ("ms_setup", "ms_kernels", "ms_total", "gpu_launches")} for r in res]
         self.logger.info("Number of pixels outside the image: %d; with valid data: %d", self.numOutsideImage, self.numValid)
 
+    # ---- B200 extension: this component as a job fused behind Topo.topo() (Topo.chainGeo2rdr) ----
+    def _chain_prepare(self, topo):
+        """Everything geo2rdr() does before the verb, with the Topo component's output images as lat / lon / hgt."""
+        self.activateInputPorts()
+        self.latImage, self.lonImage, self.demImage = topo.latImage, topo.lonImage, topo.heightImage
+        if self.orbit is None:
+            raise Exception('No orbit provided for geocoding')
+        self.setDefaults()
+        self.createImages()
+        rows, cols = int(self.demLength), int(self.demWidth)
+        t, pos, vel = export_rows(self.orbit, self.sensingStart)
+        single = self.outputPrecision.upper() == 'SINGLE'
+        imgs = dict(azt=self.azimuthImage, rgm=self.rangeImage, azoff=self.azimuthOffsetImage, rgoff=self.rangeOffsetImage)
+        outs = {k: (v.memMap() if v is not None else None) for k, v in imgs.items()}
+
+        def params(line0, nlines, device):
+            return _capi.geo_params(length=int(self.length), width=int(self.width), dem_shape=(rows, cols),
+                                    r0=float(self.rangeFirstSample), dr=float(self.slantRangePixelSpacing), prf=float(self.prf),
+                                    t0=seconds_since_midnight(self.sensingStart), wvl=float(self.radarWavelength),
+                                    side=int(self.lookSide), a=float(self.ellipsoidMajorSemiAxis),
+                                    e2=float(self.ellipsoidEccentricitySquared), orbit_method=self.orbitInterpolationMethod,
+                                    bistatic=bool(self.bistaticDelayCorrectionFlag), nrnglooks=int(self.numberRangeLooks),
+                                    nazlooks=int(self.numberAzimuthLooks), line0=line0, nlines=nlines, device=device,
+                                    out_f32=single)
+
+        return dict(params=params, orbit=(t, pos, vel), doppler=poly1d_fields(self.polyDoppler), outs=outs,
+                    want=tuple(k for k, v in outs.items() if v is not None))
+
+    def _chain_finish(self, res):
+        self.numOutsideImage = sum(r["num_outside"] for r in res)
+        self.numValid = sum(r["num_valid"] for r in res)
+        self.numConverged = sum(r["num_converged"] for r in res)
+        self.gpuTimings = [{k: r[k] for k in ("ms_setup", "ms_kernels", "ms_total", "gpu_launches")} for r in res]
+        self.logger.info("Number of pixels outside the image: %d; with valid data: %d", self.numOutsideImage, self.numValid)
+        # the lat / lon / hgt images belong to the Topo component, which finalizes them itself
+        for outfile in [self.rangeImage, self.azimuthImage, self.rangeOffsetImage, self.azimuthOffsetImage]:
+            if outfile is not None:
+                outfile.finalizeImage()
+                outfile.renderHdr()
+        self.polyDopplerAccessor = None
+
     # ---- Geo2rdr.py:264-297 ----
     def setDefaults(self):
         if self.polyDoppler is None:

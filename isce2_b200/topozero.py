@@ -92,6 +92,8 @@ class Topo(Component):
                     inc=self.incImage.memMap() if self.incImage else None,
                     mask=self.maskImage.memMap() if self.maskImage else None)
         results, errors = [None] * n, [None] * n
+        chained = [g._chain_prepare(self) for g in self.chainedGeo2rdr]
+        chained_results = [[None] * n for _ in chained]
 
         def work(i):
             a = (length * i) // n
@@ -109,9 +111,20 @@ class Topo(Component):
                                   nazlooks=int(self.numberAzimuthLooks), line0=a, nlines=b - a, device=devices[i])
             blk = {k: (v[a:b] if v is not None else None) for k, v in outs.items()}
             try:
-                results[i] = _capi.topo_run(p, dem, t, pos, vel, None, None, rho_image=rho_image, want_los=blk["los"] is not None,
-                                            want_inc=blk["inc"] is not None, want_mask=blk["mask"] is not None, out=blk,
-                                            doppler_poly=dop, slrng_poly=slr)
+                if chained:
+                    # fused verb: geo2rdr of every chained component on the block's layers while they are resident
+                    jobs = [dict(params=c["params"](a, b - a, devices[i]), orbit=c["orbit"], doppler=c["doppler"], want=c["want"],
+                                 out={k: (v[a:b] if v is not None else None) for k, v in c["outs"].items()}) for c in chained]
+                    results[i], geos = _capi.topo_geo2rdr_run(p, dem, t, pos, vel, None, jobs, rho_image=rho_image,
+                                                              want_los=blk["los"] is not None, want_inc=blk["inc"] is not None,
+                                                              want_mask=blk["mask"] is not None, out=blk, doppler_poly=dop,
+                                                              slrng_poly=slr)
+                    for j, gres in enumerate(geos):
+                        chained_results[j][i] = gres
+                else:
+                    results[i] = _capi.topo_run(p, dem, t, pos, vel, None, None, rho_image=rho_image,
+                                                want_los=blk["los"] is not None, want_inc=blk["inc"] is not None,
+                                                want_mask=blk["mask"] is not None, out=blk, doppler_poly=dop, slrng_poly=slr)
             except Exception as e:  # surfaced below, in the caller's thread
                 errors[i] = e
 
@@ -136,6 +149,17 @@ class Topo(Component):
         self.gpuTimings = [{k: r[k] for k in ("ms_setup", "ms_kernels", "ms_pixels", "ms_mask", "ms_total", "gpu_launches")}
                            for r in res]
         self.logger.info("Total convergence: %d out of %d", self.totalConverged, length * width)
+        for g, rs in zip(self.chainedGeo2rdr, chained_results):
+            g._chain_finish([r for r in rs if r is not None])
+
+    def chainGeo2rdr(self, grdr):
+        """B200 extension (not in the reference): run `grdr` (a configured Geo2rdr component: orbit, sensingStart, output
+        file names ...) inside this component's topo() call, on the lat / lon / hgt layers of every block of lines while
+        they are still in GPU memory (b200_topo_geo2rdr_run).  Equivalent to calling
+        ``grdr.geo2rdr(latImage=, lonImage=, demImage=)`` on this component's output files afterwards -- same .off / .rdr
+        rasters, same XML -- without reading them back from disk and uploading them again."""
+        self.chainedGeo2rdr.append(grdr)
+        return grdr
 
     # ---- Topozero.py:133-205 ----
     def setDefaults(self):
@@ -481,6 +505,7 @@ class Topo(Component):
         self.gpuDevices = None  # B200 extension: list of CUDA device ordinals to shard the azimuth lines over
         self.gpuTimings = None
         self.totalConverged = None
+        self.chainedGeo2rdr = []  # B200 extension: see chainGeo2rdr()
         self.dictionaryOfVariables = {
             'NUMBER_ITERATIONS': ['numberIterations', 'int', 'optional'],
             'DEM_WIDTH': ['demWidth', 'int', 'mandatory'],

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/b200geom.h but not exported by libb200geom.so"
     assert sorted(_capi.EXPORTS) == declared
-    assert lib.b200_abi_version() == 2  # 2: geozero + resamp_slc entry points
+    assert lib.b200_abi_version() == 3  # 2: geozero + resamp_slc entry points; 3: fused b200_topo_geo2rdr_run
 
 
 def test_struct_layouts_match_header():
@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(unsigned\s+)?(long long|double|float|int8_t|int|void)\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(unsigned\s+)?(long long|double|float|int8_t|int|void|b200_[a-z0-9_]+)\s*", "", decl)
             names += [n.strip().lstrip("*") for n in decl.split(",")]
         return names
 
@@ -50,7 +50,8 @@ def test_struct_layouts_match_header():
                          ("b200_topo_outputs", _capi.TopoOutputs), ("b200_geo_outputs", _capi.GeoOutputs),
                          ("b200_orbit", _capi.Orbit), ("b200_poly2d", _capi.Poly2d), ("b200_poly1d", _capi.Poly1d),
                          ("b200_geozero_params", _capi.GeozeroParams), ("b200_geozero_result", _capi.GeozeroResult),
-                         ("b200_resamp_params", _capi.ResampParams), ("b200_resamp_result", _capi.ResampResult)):
+                         ("b200_resamp_params", _capi.ResampParams), ("b200_resamp_result", _capi.ResampResult),
+                         ("b200_geo_job", _capi.GeoJob)):
         assert fields(cname) == [f[0] for f in ctype._fields_], cname
 
 
@@ -67,6 +68,10 @@ def test_no_cpu_fallback():
     z = np.zeros((4, 64))
     with pytest.raises(_capi.B200Error) as ei:
         _capi.geo2rdr_run(gp, z, z, z, sc.orbit_t, sc.orbit_pos, sc.orbit_vel)
+    assert ei.value.code == -2
+    with pytest.raises(_capi.B200Error) as ei:  # the fused verb has no host route either
+        _capi.topo_geo2rdr_run(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs,
+                               [dict(params=gp, orbit=(sc.orbit_t, sc.orbit_pos, sc.orbit_vel))], [[sc.r0, sc.dr]])
     assert ei.value.code == -2
     zp = _capi.geozero_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
                               delta_lon=sc.delta_lon, snwe=(sc.first_lat - 0.05, sc.first_lat - 0.01, sc.first_lon + 0.01,
