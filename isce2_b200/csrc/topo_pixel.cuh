@@ -251,8 +251,12 @@ B2_HD void topo_final(const TopoConst &C, const LineState &L, double rng, double
         dem_index(C, lat, lon, 2.0f, idemlat, idemlon, fraclat, fraclon);
         // slope probes (:680-688): same fractions at ix-1, ix+1, iy-1, iy+1
         double pr0 = 0.0, pr1 = 0.0, pr2 = 0.0, pr3 = 0.0;
+        bool probed = false;
+#ifdef __CUDA_ARCH__
+        if (METHOD == 5) probed = biquintic_probes4(C.dem, C.spl, idemlon, idemlat, fraclon, fraclat, pr0, pr1, pr2, pr3);
+#endif
 #pragma unroll 1
-        for (int j = 0; j < 4; j++) { // one copy of the interpolator in the instruction stream
+        for (int j = probed ? 4 : 0; j < 4; j++) { // one copy of the interpolator in the instruction stream
             int dx = (j == 0) ? -1 : (j == 1 ? 1 : 0);
             int dy = (j == 2) ? -1 : (j == 3 ? 1 : 0);
             double v = interp_dem<METHOD>(C, idemlon + dx, idemlat + dy, fraclon, fraclat);
