@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200GEOM_ABI_VERSION 3
+#define B200GEOM_ABI_VERSION 4
 
 enum {
     B200_OK = 0,
@@ -344,6 +344,43 @@ int b200_resamp_slc_from_geo_plan(const b200_resamp_params *p, b200_geo_plan *ge
                                   const b200_poly2d *az_carrier, const b200_poly2d *rg_offsets, const b200_poly2d *az_offsets,
                                   const b200_poly2d *doppler, const float *slc_in, float *slc_out, b200_resamp_result *res,
                                   char *err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------ */
+/* multilooking of the geometry layers, mask projection -- SURVEY 8(f) row N4, other consumers */
+/* ------------------------------------------------------------------------------------------ */
+/* element types == the cases of looks_C (components/mroipac/looks/bindings/looksmodule.cpp:80-127) */
+enum { B200_T_BYTE = 0, B200_T_SHORT = 1, B200_T_INT = 2, B200_T_LONG = 3, B200_T_FLOAT = 4, B200_T_DOUBLE = 5,
+       B200_T_CFLOAT = 6 };
+#define B200_LOOKS_AVERAGE 0 /* mroipac.looks: box mean accumulated in double (runMultilook method='isce') */
+#define B200_LOOKS_NEAREST 1 /* gdal.Translate -outsize: nearest-neighbour decimation (runMultilook method='gdal') */
+
+typedef struct {
+    int out_length, out_width; /* length / down_looks, width / across_looks (integer division, Looks.py:44-45) */
+    float ms_kernels;
+    float ms_total;
+    int gpu_launches;
+} b200_looks_result;
+
+/* Replaces looks_Py(inPtr, outPtr, downLooks, acrossLooks, dataType) of mroipac.looks (Looks.py:79) as runMultilook
+ * drives it for hgt / lat / lon / los / incLocal / shadowMask / waterMask (contrib/stack/stripmapStack/topo.py:365-441).
+ * in: [length][width] x bands of dtype in the given interleaving scheme (B200_SCHEME_*), host memory; out: the same
+ * scheme on the [out_length][out_width] grid.  Trailing lines / samples that do not fill a look are dropped. */
+int b200_looks_run(const void *in, void *out, int dtype, int length, int width, int bands, int scheme, int down_looks,
+                   int across_looks, int method, int device, b200_looks_result *res, char *err, size_t errlen);
+
+typedef struct {
+    float ms_kernels;
+    float ms_total;
+    int gpu_launches;
+} b200_mask_result;
+
+/* Replaces SWBDStitcher.toRadar (contrib/demUtils/swbdstitcher/SWBDStitcher.py:107-131), the geo2radar step of
+ * stripmapStack/createWaterMask.py:66-71: out[p] = mask[clip(int((lat[p] - start_lat) / delta_lat), 0, mask_length - 1)]
+ * [clip(int((lon[p] - start_lon) / delta_lon), 0, mask_width - 1)] + 1 for the npix pixels of lat.rdr / lon.rdr.
+ * mask / out: dtype B200_T_BYTE, SHORT, INT or FLOAT; lat / lon: double (coord_f32 = 0) or float32 (1). */
+int b200_mask_to_radar_run(const void *mask, int dtype, int mask_length, int mask_width, double start_lat, double delta_lat,
+                           double start_lon, double delta_lon, const void *lat, const void *lon, int coord_f32, size_t npix,
+                           void *out, int device, b200_mask_result *res, char *err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------ */
 /* utilities                                                                                   */

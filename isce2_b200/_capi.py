@@ -122,13 +122,23 @@ class ResampResult(C.Structure):
 GEOZERO_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3}
 SCHEMES = {"BIL": 0, "BIP": 1, "BSQ": 2}
 
+class LooksResult(C.Structure):
+    _fields_ = [("out_length", C.c_int), ("out_width", C.c_int), ("ms_kernels", C.c_float), ("ms_total", C.c_float),
+                ("gpu_launches", C.c_int)]
+
+
+class MaskResult(C.Structure):
+    _fields_ = [("ms_kernels", C.c_float), ("ms_total", C.c_float), ("gpu_launches", C.c_int)]
+
+
 EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "b200_topo_plan_fetch",
            "b200_topo_plan_device_layers", "b200_topo_plan_destroy", "b200_geo2rdr_run", "b200_geo_plan_create",
            "b200_geo_plan_create_from_topo", "b200_geo_plan_execute", "b200_geo_plan_fetch", "b200_geo_plan_destroy",
            "b200_abi_version", "b200_release_cached_memory", "b200_device_count", "b200_device_name", "b200_alloc_pinned", "b200_free_pinned",
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
-           "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run"]
+           "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
+           "b200_looks_run", "b200_mask_to_radar_run"]
 
 _lib = None
 
@@ -186,6 +196,10 @@ def lib():
                                       C.c_int, C.c_void_p, C.POINTER(ResampResult)] + err
     L.b200_resamp_slc_from_geo_plan.argtypes = [C.POINTER(ResampParams), C.c_void_p] + [C.POINTER(Poly2d)] * 5 + [
         C.c_void_p, C.c_void_p, C.POINTER(ResampResult)] + err
+    L.b200_looks_run.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.POINTER(LooksResult)] + err
+    L.b200_mask_to_radar_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                                         C.POINTER(MaskResult)] + err
     _lib = L
     return L
 
@@ -733,3 +747,71 @@ def resamp_slc_from_geo_plan(geo_plan, slc, *, wvl=0.056, slr=2.3, r0=0.0, ref_w
     r = dict(slc=out)
     r.update(_result_dict(res))
     return r
+
+
+# ---- multilooking of the geometry layers, mask projection (other consumers) ----
+# numpy dtype -> element type of looks_C (looksmodule.cpp:80-127)
+LOOKS_TYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
+               np.dtype(np.float32): 4, np.dtype(np.float64): 5, np.dtype(np.complex64): 6}
+SCHEMES = {"BIL": 0, "BIP": 1, "BSQ": 2}
+LOOKS_METHODS = {"AVERAGE": 0, "ISCE": 0, "NEAREST": 1, "GDAL": 1}
+
+
+def _band_axes(scheme):
+    # position of (line, band, sample) in an array stored in the given interleaving
+    return {"BIL": (0, 1, 2), "BIP": (0, 2, 1), "BSQ": (1, 0, 2)}[scheme]
+
+
+def looks_run(image, down_looks, across_looks, *, scheme="BIL", method="AVERAGE", out=None, device=0):
+    """b200_looks_run.  `image`: 2-D [length][width] or 3-D in the storage order of `scheme` (BIL [line][band][sample],
+    BIP [line][sample][band], BSQ [band][line][sample]).  Returns (out array in the same layout, result dict)."""
+    a = np.ascontiguousarray(image)
+    if a.dtype == np.uint8:
+        a = a.view(np.int8)  # BYTE is 'i1' in ISCE (Image.py:62)
+    if a.dtype not in LOOKS_TYPES:
+        raise TypeError(f"Error. Unrecognized data type {a.dtype}")
+    scheme = scheme.upper()
+    if a.ndim == 2:
+        length, width, bands = a.shape[0], a.shape[1], 1
+        oshape = (length // down_looks if down_looks > 0 else 0, width // across_looks if across_looks > 0 else 0)
+    else:
+        ax = _band_axes(scheme)
+        length, bands, width = a.shape[ax.index(0)], a.shape[ax.index(1)], a.shape[ax.index(2)]
+        dims = {0: length // down_looks if down_looks > 0 else 0, 1: bands, 2: width // across_looks if across_looks > 0 else 0}
+        oshape = tuple(dims[k] for k in ax)
+    if out is None:
+        out = np.zeros(oshape, a.dtype)
+    elif out.shape != oshape or out.dtype != a.dtype or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"out must be a C-contiguous {a.dtype} array of shape {oshape}")
+    res = LooksResult()
+    e = _errbuf()
+    _check(lib().b200_looks_run(a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), LOOKS_TYPES[a.dtype], length, width,
+                                bands, SCHEMES[scheme], int(down_looks), int(across_looks), LOOKS_METHODS[method.upper()],
+                                int(device), C.byref(res), e, 512), e)
+    return out, _result_dict(res)
+
+
+def mask_to_radar_run(mask, start_lat, delta_lat, start_lon, delta_lon, lat, lon, *, out=None, device=0):
+    """b200_mask_to_radar_run: `mask` [mask_length][mask_width] (int8 / int16 / int32 / float32) sampled at the radar pixels
+    whose latitude / longitude are `lat` / `lon` (float64 or float32, any shape)."""
+    m = np.ascontiguousarray(mask)
+    if m.dtype == np.uint8:
+        m = m.view(np.int8)
+    codes = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.float32): 4}
+    if m.dtype not in codes or m.ndim != 2:
+        raise TypeError("mask must be a 2-D int8 / int16 / int32 / float32 array")
+    lat = np.ascontiguousarray(lat)
+    lon = np.ascontiguousarray(lon)
+    if lat.dtype != lon.dtype or lat.dtype not in (np.float32, np.float64) or lat.shape != lon.shape:
+        raise TypeError("lat / lon must be float32 or float64 arrays of one shape")
+    if out is None:
+        out = np.zeros(lat.shape, m.dtype)
+    elif out.shape != lat.shape or out.dtype != m.dtype or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("out must be a C-contiguous array of the mask's dtype and lat's shape")
+    res = MaskResult()
+    e = _errbuf()
+    _check(lib().b200_mask_to_radar_run(m.ctypes.data_as(C.c_void_p), codes[m.dtype], m.shape[0], m.shape[1], float(start_lat),
+                                        float(delta_lat), float(start_lon), float(delta_lon), lat.ctypes.data_as(C.c_void_p),
+                                        lon.ctypes.data_as(C.c_void_p), int(lat.dtype == np.float32), lat.size,
+                                        out.ctypes.data_as(C.c_void_p), int(device), C.byref(res), e, 512), e)
+    return out, _result_dict(res)

@@ -21,6 +21,7 @@
 #include "geo2rdr_kernels.cuh"
 #include "geozero_kernels.cuh"
 #include "orbit_poly.h"
+#include "post_kernels.cuh"
 #include "resamp_kernels.cuh"
 #include "topo_kernels.cuh"
 
@@ -1703,6 +1704,184 @@ extern "C" int b200_resamp_slc_from_geo_plan(const b200_resamp_params *p, b200_g
     CK(cudaStreamSynchronize(geo->stream));
     return resamp_core(p, rg_carrier, az_carrier, rg_offsets, az_offsets, doppler, slc_in, geo->d_out[2], geo->d_out[3],
                        geo->out_f32 ? B200_RESID_F32 : B200_RESID_F64, true, slc_out, res, err, errlen);
+}
+
+// =================================================================================================
+// multilooking of the geometry layers, mask projection (the other consumers)
+// =================================================================================================
+namespace {
+struct PostStreams { // H2D | kernels | D2H
+    cudaStream_t h = nullptr, k = nullptr, d = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<void *> bufs;
+    int init()
+    {
+        if (cudaStreamCreateWithFlags(&h, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        if (cudaStreamCreateWithFlags(&k, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        if (cudaStreamCreateWithFlags(&d, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess) return -1;
+        return 0;
+    }
+    cudaEvent_t event()
+    {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ev.push_back(e);
+        return e;
+    }
+    ~PostStreams()
+    {
+        for (cudaStream_t s : {h, k, d})
+            if (s) cudaStreamSynchronize(s);
+        for (void *b : bufs) dfree(b);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (cudaStream_t s : {h, k, d})
+            if (s) cudaStreamDestroy(s);
+    }
+};
+} // namespace
+
+extern "C" int b200_looks_run(const void *in, void *out, int dtype, int length, int width, int bands, int scheme, int down_looks,
+                              int across_looks, int method, int device, b200_looks_result *res, char *err, size_t errlen)
+{
+    const double t0 = now_ms();
+    const size_t esz = type_size(dtype);
+    if (!in || !out) return fail(err, errlen, B200_EINVAL, "input / output image is NULL");
+    if (esz == 0) return fail(err, errlen, B200_EINVAL, "Error. Unrecognized data type %d", dtype); // looksmodule.cpp:124-127
+    if (length < 1 || width < 1 || bands < 1) return fail(err, errlen, B200_EINVAL, "bad image %d x %d x %d", length, width, bands);
+    if (scheme != B200_SCHEME_BIL && scheme != B200_SCHEME_BIP && scheme != B200_SCHEME_BSQ)
+        return fail(err, errlen, B200_EINVAL, "bad interleaving scheme %d", scheme);
+    if (down_looks < 1 || across_looks < 1) return fail(err, errlen, B200_EINVAL, "looks must be >= 1 (%d down, %d across)", down_looks, across_looks);
+    if (method != B200_LOOKS_AVERAGE && method != B200_LOOKS_NEAREST) return fail(err, errlen, B200_EINVAL, "bad method %d", method);
+    LooksGeom G{length, width, bands, scheme, down_looks, across_looks, length / down_looks, width / across_looks, 0, 0};
+    if (res) {
+        res->out_length = G.out_length;
+        res->out_width = G.out_width;
+        res->ms_kernels = res->ms_total = 0.f;
+        res->gpu_launches = 0;
+    }
+    if (method == B200_LOOKS_AVERAGE) {
+        const long long per_out = (long long)across_looks * (scheme == B200_SCHEME_BIP ? bands : 1) * (dtype == B200_T_CFLOAT ? 2 : 1);
+        if (per_out > kLooksMaxTile)
+            return fail(err, errlen, B200_EINVAL, "across_looks x interleaved bands = %lld exceeds the %d column sums a tile holds", per_out,
+                        kLooksMaxTile);
+    }
+    int rc = select_device(device, err, errlen);
+    if (rc != B200_OK) return rc;
+    if (G.out_length == 0 || G.out_width == 0) return B200_OK; // nothing to write (the reference's loops do not execute)
+    PostStreams st;
+    if (st.init() != 0) return fail(err, errlen, B200_ECUDA, "cannot create streams");
+    const size_t in_bytes = (size_t)length * width * bands * esz, out_bytes = (size_t)G.out_length * G.out_width * bands * esz;
+    void *d_in = nullptr, *d_out = nullptr;
+    CK(dmalloc(&d_in, in_bytes));
+    st.bufs.push_back(d_in);
+    CK(dmalloc(&d_out, out_bytes));
+    st.bufs.push_back(d_out);
+    // blocks of output lines: H2D(c+1) | kernel(c) | D2H(c-1); a block of a band-sequential image is one piece per band
+    long long cl = 16000000LL / ((long long)width * bands * down_looks);
+    if (cl < 1) cl = 1;
+    const int pieces = scheme == B200_SCHEME_BSQ ? bands : 1;
+    int launches = 0;
+    CK(cudaEventRecord(st.ev0, st.k));
+    for (int c0 = 0; c0 < G.out_length; c0 += (int)cl) {
+        const int n = (c0 + cl <= G.out_length) ? (int)cl : G.out_length - c0;
+        for (int b = 0; b < pieces; b++) {
+            const size_t per_line = (size_t)width * (pieces > 1 ? 1 : bands) * esz;
+            const size_t o = ((size_t)b * length + (size_t)c0 * down_looks) * per_line;
+            CK(cudaMemcpyAsync((char *)d_in + o, (const char *)in + o, (size_t)n * down_looks * per_line, cudaMemcpyHostToDevice, st.h));
+        }
+        cudaEvent_t eh = st.event(), ek = st.event();
+        CK(cudaEventRecord(eh, st.h));
+        CK(cudaStreamWaitEvent(st.k, eh, 0));
+        G.line0 = c0;
+        G.nlines = n;
+        const int lr = launch_looks(G, dtype, method, d_in, d_out, st.k);
+        if (lr != 0) return fail(err, errlen, B200_EINVAL, "cannot launch the looks kernel (%d)", lr);
+        launches++;
+        CK(cudaEventRecord(ek, st.k));
+        CK(cudaStreamWaitEvent(st.d, ek, 0));
+        for (int b = 0; b < pieces; b++) {
+            const size_t per_line = (size_t)G.out_width * (pieces > 1 ? 1 : bands) * esz;
+            const size_t o = ((size_t)b * G.out_length + (size_t)c0) * per_line;
+            CK(cudaMemcpyAsync((char *)out + o, (char *)d_out + o, (size_t)n * per_line, cudaMemcpyDeviceToHost, st.d));
+        }
+    }
+    CK(cudaEventRecord(st.ev1, st.k));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st.k));
+    CK(cudaStreamSynchronize(st.d));
+    if (res) {
+        CK(cudaEventElapsedTime(&res->ms_kernels, st.ev0, st.ev1));
+        res->gpu_launches = launches;
+        res->ms_total = (float)(now_ms() - t0);
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_mask_to_radar_run(const void *mask, int dtype, int mask_length, int mask_width, double start_lat,
+                                      double delta_lat, double start_lon, double delta_lon, const void *lat, const void *lon,
+                                      int coord_f32, size_t npix, void *out, int device, b200_mask_result *res, char *err,
+                                      size_t errlen)
+{
+    const double t0 = now_ms();
+    if (!mask || !lat || !lon || !out) return fail(err, errlen, B200_EINVAL, "mask / lat / lon / out is NULL");
+    if (dtype != B200_T_BYTE && dtype != B200_T_SHORT && dtype != B200_T_INT && dtype != B200_T_FLOAT)
+        return fail(err, errlen, B200_EINVAL, "mask data type %d is not one of BYTE, SHORT, INT, FLOAT", dtype);
+    if (mask_length < 1 || mask_width < 1) return fail(err, errlen, B200_EINVAL, "bad mask grid %d x %d", mask_length, mask_width);
+    if (res) {
+        res->ms_kernels = res->ms_total = 0.f;
+        res->gpu_launches = 0;
+    }
+    int rc = select_device(device, err, errlen);
+    if (rc != B200_OK) return rc;
+    if (npix == 0) return B200_OK;
+    PostStreams st;
+    if (st.init() != 0) return fail(err, errlen, B200_ECUDA, "cannot create streams");
+    const size_t esz = type_size(dtype), csz = coord_f32 ? 4 : 8;
+    const size_t mbytes = (size_t)mask_length * mask_width * esz;
+    void *d_mask = nullptr, *d_lat = nullptr, *d_lon = nullptr, *d_out = nullptr;
+    CK(dmalloc(&d_mask, mbytes));
+    st.bufs.push_back(d_mask);
+    CK(dmalloc(&d_lat, npix * csz));
+    st.bufs.push_back(d_lat);
+    CK(dmalloc(&d_lon, npix * csz));
+    st.bufs.push_back(d_lon);
+    CK(dmalloc(&d_out, npix * esz));
+    st.bufs.push_back(d_out);
+    CK(cudaMemcpyAsync(d_mask, mask, mbytes, cudaMemcpyHostToDevice, st.h));
+    const MaskProj M{mask_length, mask_width, start_lat, delta_lat, start_lon, delta_lon};
+    const size_t chunk = 16000000;
+    int launches = 0;
+    CK(cudaEventRecord(st.ev0, st.k));
+    for (size_t p0 = 0; p0 < npix; p0 += chunk) {
+        const size_t n = p0 + chunk <= npix ? chunk : npix - p0;
+        CK(cudaMemcpyAsync((char *)d_lat + p0 * csz, (const char *)lat + p0 * csz, n * csz, cudaMemcpyHostToDevice, st.h));
+        CK(cudaMemcpyAsync((char *)d_lon + p0 * csz, (const char *)lon + p0 * csz, n * csz, cudaMemcpyHostToDevice, st.h));
+        cudaEvent_t eh = st.event(), ek = st.event();
+        CK(cudaEventRecord(eh, st.h));
+        CK(cudaStreamWaitEvent(st.k, eh, 0));
+        if (launch_mask_to_radar(M, dtype, d_mask, (char *)d_lat + p0 * csz, (char *)d_lon + p0 * csz, coord_f32, n,
+                                 (char *)d_out + p0 * esz, st.k) != 0)
+            return fail(err, errlen, B200_EINVAL, "cannot launch the mask projection kernel");
+        launches++;
+        CK(cudaEventRecord(ek, st.k));
+        CK(cudaStreamWaitEvent(st.d, ek, 0));
+        CK(cudaMemcpyAsync((char *)out + p0 * esz, (char *)d_out + p0 * esz, n * esz, cudaMemcpyDeviceToHost, st.d));
+    }
+    CK(cudaEventRecord(st.ev1, st.k));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st.k));
+    CK(cudaStreamSynchronize(st.d));
+    if (res) {
+        CK(cudaEventElapsedTime(&res->ms_kernels, st.ev0, st.ev1));
+        res->gpu_launches = launches;
+        res->ms_total = (float)(now_ms() - t0);
+    }
+    return B200_OK;
 }
 
 // =================================================================================================

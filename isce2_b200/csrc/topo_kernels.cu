@@ -689,14 +689,17 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
     __syncthreads();
 }
 
+constexpr int kMaskKnots = 256;
+
 template <int METHOD, bool REF>
-__global__ void __launch_bounds__(kMaskBlock)
+__global__ void __launch_bounds__(kMaskBlock, 1024 / kMaskBlock)
 k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines, TopoLayers out,
             float demmax, MaskScratch scr)
 {
     extern __shared__ unsigned char s_dyn[]; // [width] mask bytes of the line being built
     __shared__ SR s_warp[32];                // scan scratch (largest scan state)
     __shared__ double s_mm[2];
+    __shared__ double s_knot[kMaskKnots + 1];
     __shared__ int s_flag;
     __shared__ LineState sL;
     const int w = C.width, ow = 2 * w + 1; // :134-135
@@ -766,8 +769,26 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         }
 
         // ---- DEM surface on the regular cross-track grid :745-782 ----
-        const double cs0 = cs[0], csn = cs[w - 1];
-        const double gscale = (csn > cs0) ? (double)(w - 1) / (csn - cs0) : 0.0;
+        // The sorted cross-track positions are smooth but not uniform in the sample index (ground spacing changes across
+        // the swath), so a straight line through the end points misses the bracket by hundreds of samples and the search
+        // degenerates into ~16 dependent loads.  kMaskKnots + 1 samples of the array in shared memory give a piecewise
+        // linear inverse that lands within a sample or two; the search itself (and therefore the result) is unchanged.
+        for (int k = threadIdx.x; k <= kMaskKnots; k += blockDim.x) s_knot[k] = cs[(int)(((long long)k * (w - 1)) / kMaskKnots)];
+        __syncthreads();
+        const double cs0 = s_knot[0], csn = s_knot[kMaskKnots];
+        const double kscale = (csn > cs0) ? (double)kMaskKnots / (csn - cs0) : 0.0;
+        auto knot_guess = [&](double aa) -> int {
+            if (!(aa > cs0)) return 0;
+            if (!(aa < csn)) return w - 1;
+            int k = (int)((aa - cs0) * kscale);
+            k = k < 0 ? 0 : (k > kMaskKnots - 1 ? kMaskKnots - 1 : k);
+            while (k > 0 && s_knot[k] > aa) k--;
+            while (k < kMaskKnots - 1 && s_knot[k + 1] <= aa) k++;
+            const int i0 = (int)(((long long)k * (w - 1)) / kMaskKnots), i1 = (int)(((long long)(k + 1) * (w - 1)) / kMaskKnots);
+            const double a = s_knot[k], b = s_knot[k + 1];
+            const double f = (b > a) ? (aa - a) / (b - a) : 0.0;
+            return i0 + (int)(f * (double)(i1 - i0));
+        };
         // The slant ranges of consecutive samples are compared as they are produced: a warp owns 32 consecutive samples
         // per sweep, so all but the first one find their predecessor in the neighbouring lane; the warp-boundary pairs
         // (one in 32) are compared afterwards from memory.  Lines without fold-over never read orng back otherwise.
@@ -777,8 +798,7 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             double val = 0.0;
             if (p < ow) {
                 const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
-                const int guess = (int)((aa - cs0) * gscale);
-                int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, guess), w);
+                int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, knot_guess(aa)), w);
                 val = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
                 orng[p] = val;
             }

@@ -141,6 +141,20 @@ class Image:
     def asarray(self):
         return np.asarray(self.memMap())
 
+    def toNumpyDataType(self):
+        """Image.py:255-256"""
+        return TO_NUMPY[self.dataType.upper()]
+
+    def clone(self):
+        """A metadata copy without the open raster (Image.clone as mroipac/looks/Looks.py:38,45 uses it)."""
+        import copy
+        mm, self._mmap = self._mmap, None
+        try:
+            c = copy.deepcopy(self)
+        finally:
+            self._mmap = mm
+        return c
+
     def finalizeImage(self):
         if self._mmap is not None:
             if hasattr(self._mmap, "flush") and not self.accessMode.startswith("r"):

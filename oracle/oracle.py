@@ -360,3 +360,58 @@ def resamp_slc(*, slc, out_shape, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_
     if rc != 0:
         raise RuntimeError(f"orc_resamp_slc failed rc={rc}")
     return out
+
+
+# ---- multilooking / mask projection (other consumers): plain numpy restatements ----
+def _to_line_band_sample(a, scheme):
+    """View of an image stored in `scheme` order as [line][band][sample]."""
+    if a.ndim == 2:
+        return a[:, None, :]
+    return {"BIL": a, "BIP": np.moveaxis(a, 2, 1), "BSQ": np.moveaxis(a, 0, 1)}[scheme.upper()]
+
+
+def _from_line_band_sample(o, scheme, ndim):
+    if ndim == 2:
+        return np.ascontiguousarray(o[:, 0, :])
+    return np.ascontiguousarray({"BIL": o, "BIP": np.moveaxis(o, 1, 2), "BSQ": np.moveaxis(o, 1, 0)}[scheme.upper()])
+
+
+def looks(image, down_looks, across_looks, scheme="BIL", method="AVERAGE"):
+    """takeLooks<T> / takeLookscpx<T> (components/mroipac/looks/bindings/looksmodule.cpp:130-200, :204-275) or, for
+    method 'NEAREST', the gdal.Translate -outsize decimation of runMultilook (contrib/stack/stripmapStack/topo.py:411-424).
+    The accumulation order is the reference's: the `down` lines are added one after the other into a double line
+    buffer (:160-177), then the `across` neighbours one after the other (:179-190), / double(down*across), cast to T."""
+    a = np.asarray(image)
+    v = _to_line_band_sample(a, scheme)
+    nd, _, na = v.shape
+    ld, la = int(down_looks), int(across_looks)
+    ol, ow = nd // ld, na // la
+    if method.upper() in ("NEAREST", "GDAL"):
+        o = v[ld // 2:ol * ld:ld, :, la // 2:ow * la:la][:ol, :, :ow]  # source index floor((i + 0.5) * looks)
+        return _from_line_band_sample(o, scheme, a.ndim)
+    acc_t = np.complex128 if np.iscomplexobj(a) else np.float64
+    o = np.zeros((ol, v.shape[1], ow), a.dtype)
+    norm = float(ld * la)
+    for line in range(ol):
+        bdbl = np.zeros(v.shape[1:], acc_t)
+        for i in range(ld):  # bdbl[j] += ain[j]
+            bdbl = bdbl + v[line * ld + i].astype(acc_t)
+        s = np.zeros((v.shape[1], ow), acc_t)
+        for k in range(la):  # sum += bdbl[(j + k) * bands + b]
+            s = s + bdbl[:, k:ow * la:la][:, :ow]
+        if np.iscomplexobj(a):  # complex<T>(static_cast<T>(sum.real() / norm), static_cast<T>(sum.imag() / norm))
+            o[line] = (s.real / norm).astype(a.real.dtype) + 1j * (s.imag / norm).astype(a.real.dtype)
+            continue
+        q = s / norm
+        if np.issubdtype(a.dtype, np.integer):
+            o[line] = np.trunc(q).astype(a.dtype)  # static_cast<T>(double): toward zero
+        else:
+            o[line] = q.astype(a.dtype)
+    return _from_line_band_sample(o, scheme, a.ndim)
+
+
+def mask_to_radar(mask, start_lat, delta_lat, start_lon, delta_lon, lat, lon):
+    """SWBDStitcher.toRadar (contrib/demUtils/swbdstitcher/SWBDStitcher.py:107-131), the arithmetic only (lines :123-126)."""
+    lati = np.clip(((lat - start_lat) / delta_lat).astype(int), 0, mask.shape[0] - 1)
+    loni = np.clip(((lon - start_lon) / delta_lon).astype(int), 0, mask.shape[1] - 1)
+    return (mask[lati, loni] + 1).astype(mask.dtype)

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/b200geom.h but not exported by libb200geom.so"
     assert sorted(_capi.EXPORTS) == declared
-    assert lib.b200_abi_version() == 3  # 2: geozero + resamp_slc entry points; 3: fused b200_topo_geo2rdr_run
+    assert lib.b200_abi_version() == 4  # 2: geozero + resamp_slc; 3: fused b200_topo_geo2rdr_run; 4: looks + mask projection
 
 
 def test_struct_layouts_match_header():
@@ -51,7 +51,8 @@ def test_struct_layouts_match_header():
                          ("b200_orbit", _capi.Orbit), ("b200_poly2d", _capi.Poly2d), ("b200_poly1d", _capi.Poly1d),
                          ("b200_geozero_params", _capi.GeozeroParams), ("b200_geozero_result", _capi.GeozeroResult),
                          ("b200_resamp_params", _capi.ResampParams), ("b200_resamp_result", _capi.ResampResult),
-                         ("b200_geo_job", _capi.GeoJob)):
+                         ("b200_geo_job", _capi.GeoJob), ("b200_looks_result", _capi.LooksResult),
+                         ("b200_mask_result", _capi.MaskResult)):
         assert fields(cname) == [f[0] for f in ctype._fields_], cname
 
 

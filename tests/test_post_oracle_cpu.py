@@ -1,0 +1,97 @@
+"""CPU pins of the multilooking / mask-projection restatements (other consumers):
+
+* oracle.looks() against the reference's own takeLooks<T> / takeLookscpx<T> templates, compiled unchanged from
+  components/mroipac/looks/bindings/looksmodule.cpp into oracle/_ref/libisce2_looks_ref.so (oracle/Makefile) and driven
+  through an in-memory DataAccessor (oracle/ref_looks_shim.cpp): bit-identical for every element type;
+* oracle.mask_to_radar() against golden output of the reference's own SWBDStitcher.toRadar
+  (tests/golden/make_golden_post.py -> ref_toradar.npz);
+* the host mirrors' file handling that needs no device, and the no-CPU-fallback rule for the new entry points.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from isce2_b200 import _capi
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LOOKS = os.path.join(ROOT, "oracle", "_ref", "libisce2_looks_ref.so")
+DTYPES = [(np.int8, 0), (np.int16, 1), (np.int32, 2), (np.int64, 3), (np.float32, 4), (np.float64, 5), (np.complex64, 6)]
+
+
+def _random(rng, shape, dt):
+    if np.issubdtype(dt, np.integer):
+        info = np.iinfo(dt)
+        lo, hi = max(info.min, -2**40), min(info.max, 2**40)
+        return rng.integers(lo, hi, shape, dtype=np.int64, endpoint=True).astype(dt)
+    if dt == np.complex64:
+        return (rng.normal(size=shape) * 1e3 + 1j * rng.normal(size=shape)).astype(dt)
+    return (rng.normal(size=shape) * 10.0 ** rng.integers(-3, 6, shape)).astype(dt)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LOOKS), reason="oracle/_ref not built (reference tree absent)")
+@pytest.mark.parametrize("dt,code", DTYPES)
+def test_looks_restatement_is_bit_identical_to_reference_templates(dt, code):
+    ref = C.CDLL(REF_LOOKS)
+    rng = np.random.default_rng(code)
+    for (length, width, bands, ld, la) in ((23, 41, 1, 3, 4), (16, 30, 2, 4, 3), (9, 9, 3, 1, 1), (7, 50, 1, 7, 13), (5, 6, 2, 6, 2)):
+        a = _random(rng, (length, width, bands), dt)  # pixel-interleaved lines, as the accessors deliver them
+        out = np.zeros((length // ld, width // la, bands), dt)
+        rc = ref.ref_take_looks(code, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), length, width, bands, ld, la)
+        assert rc == 0
+        mine = orc.looks(a, ld, la, scheme="BIP")
+        assert mine.shape == out.shape and mine.dtype == out.dtype
+        assert np.array_equal(mine.view(np.uint8), out.view(np.uint8)), (dt, length, width, bands, ld, la)
+
+
+def test_looks_restatement_layouts_and_nearest():
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(12, 2, 20)).astype(np.float32)  # BIL
+    bil = orc.looks(a, 3, 4, scheme="BIL")
+    bip = orc.looks(np.ascontiguousarray(np.moveaxis(a, 1, 2)), 3, 4, scheme="BIP")
+    bsq = orc.looks(np.ascontiguousarray(np.moveaxis(a, 1, 0)), 3, 4, scheme="BSQ")
+    assert np.array_equal(bil, np.moveaxis(bip, 2, 1)) and np.array_equal(bil, np.moveaxis(bsq, 0, 1))
+    assert np.array_equal(bil[:, 0], orc.looks(a[:, 0], 3, 4))
+    # exact means of integers, truncation toward zero of static_cast<T>
+    b = np.array([[-3, -4, 5, 6], [-3, -3, 5, 5]], np.int16)
+    assert orc.looks(b, 2, 2).tolist() == [[-3, 5]]  # -13/4 = -3.25 -> -3 ; 21/4 = 5.25 -> 5
+    # nearest: source index floor((i + 0.5) * looks)
+    c = np.arange(7 * 11).reshape(7, 11).astype(np.int32)
+    n = orc.looks(c, 3, 4, method="NEAREST")
+    assert n.tolist() == [[c[1, 2], c[1, 6]], [c[4, 2], c[4, 6]]]
+
+
+def test_mask_projection_restatement_matches_reference_toRadar():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_toradar.npz"))
+    d = float(g["delta"])
+    for tag, dt in (("f64", np.float64), ("f32", np.float32)):
+        out = orc.mask_to_radar(g["mask"], float(g["start_lat"]), -d, float(g["start_lon"]), d, g["lat"].astype(dt), g["lon"].astype(dt))
+        assert out.dtype == np.int8 and np.array_equal(out, g["out_" + tag]), tag
+    assert set(np.unique(g["out_f64"]).tolist()) <= {0, 1, 2}
+
+
+@pytest.mark.skipif(_capi.device_count() > 0, reason="a CUDA device is present")
+def test_post_products_have_no_cpu_fallback():
+    a = np.zeros((8, 8), np.float32)
+    with pytest.raises(_capi.B200Error) as ei:
+        _capi.looks_run(a, 2, 2)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+    with pytest.raises(_capi.B200Error) as ei:
+        _capi.mask_to_radar_run(np.zeros((4, 4), np.int8), 1.0, -0.1, 0.0, 0.1, np.zeros(5), np.zeros(5))
+    assert ei.value.code == -2
+
+
+def test_post_products_argument_validation_precedes_device_use():
+    a = np.zeros((8, 8), np.float32)
+    with pytest.raises(_capi.B200Error) as ei:
+        _capi.looks_run(a, 0, 2)
+    assert ei.value.code == -1 and "looks must be >= 1" in str(ei.value)
+    with pytest.raises(TypeError):  # "Error. Unrecognized data type" (looksmodule.cpp:124-127)
+        _capi.looks_run(a.astype(np.float16), 2, 2)
+    with pytest.raises(_capi.B200Error) as ei:  # more column sums than a tile holds
+        _capi.looks_run(np.zeros((2, 5000, 2), np.float32), 1, 2500, scheme="BIP")
+    assert ei.value.code == -1
+    with pytest.raises(TypeError):
+        _capi.mask_to_radar_run(np.zeros((4, 4), np.float64), 1.0, -0.1, 0.0, 0.1, np.zeros(5), np.zeros(5))
