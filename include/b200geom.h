@@ -368,6 +368,14 @@ typedef struct {
 int b200_looks_run(const void *in, void *out, int dtype, int length, int width, int bands, int scheme, int down_looks,
                    int across_looks, int method, int device, b200_looks_result *res, char *err, size_t errlen);
 
+/* Fused form for the stack shape (topo.py: runTopo then runMultilook of what it wrote): the multilooked copy of one
+ * layer of an executed topo plan, taken from the full-resolution layer still resident in HBM.  layer = B200_LAYER_*;
+ * out: host buffer [nlines / down_looks][width / across_looks] of the layer's type (los / inc: two BIL bands).  The
+ * plan's block of lines is multilooked on its own: shard by multiples of down_looks. */
+enum { B200_LAYER_LAT = 0, B200_LAYER_LON = 1, B200_LAYER_HGT = 2, B200_LAYER_LOS = 3, B200_LAYER_INC = 4, B200_LAYER_MASK = 5 };
+int b200_topo_plan_looks(b200_topo_plan *plan, int layer, int down_looks, int across_looks, int method, void *out,
+                         b200_looks_result *res, char *err, size_t errlen);
+
 typedef struct {
     float ms_kernels;
     float ms_total;

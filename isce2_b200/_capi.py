@@ -138,7 +138,7 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
            "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
-           "b200_looks_run", "b200_mask_to_radar_run"]
+           "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks"]
 
 _lib = None
 
@@ -197,6 +197,7 @@ def lib():
     L.b200_resamp_slc_from_geo_plan.argtypes = [C.POINTER(ResampParams), C.c_void_p] + [C.POINTER(Poly2d)] * 5 + [
         C.c_void_p, C.c_void_p, C.POINTER(ResampResult)] + err
     L.b200_looks_run.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.POINTER(LooksResult)] + err
+    L.b200_topo_plan_looks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(LooksResult)] + err
     L.b200_mask_to_radar_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                          C.POINTER(MaskResult)] + err
@@ -354,6 +355,21 @@ class TopoPlan:
         out = dict(out)
         out.update(_result_dict(res))
         return out
+
+    LAYERS = {"lat": (0, np.float64, 1), "lon": (1, np.float64, 1), "hgt": (2, np.float64, 1), "los": (3, np.float32, 2),
+              "inc": (4, np.float32, 2), "mask": (5, np.int8, 1)}
+
+    def looks(self, layer, down_looks, across_looks, method="AVERAGE"):
+        """Multilooked copy of one resident layer (b200_topo_plan_looks).  Returns (array, result dict)."""
+        code, dt, bands = self.LAYERS[layer]
+        ol = self.nlines // down_looks if down_looks > 0 else 0
+        ow = self.width // across_looks if across_looks > 0 else 0
+        out = np.zeros((ol, ow) if bands == 1 else (ol, bands, ow), dt)
+        res = LooksResult()
+        e = _errbuf()
+        _check(lib().b200_topo_plan_looks(self.handle, code, int(down_looks), int(across_looks), LOOKS_METHODS[method.upper()],
+                                          out.ctypes.data_as(C.c_void_p), C.byref(res), e, 512), e)
+        return out, _result_dict(res)
 
     def close(self):
         if self.handle:

@@ -1822,6 +1822,60 @@ extern "C" int b200_looks_run(const void *in, void *out, int dtype, int length, 
     return B200_OK;
 }
 
+extern "C" int b200_topo_plan_looks(b200_topo_plan *pl, int layer, int down_looks, int across_looks, int method, void *out,
+                                    b200_looks_result *res, char *err, size_t errlen)
+{
+    const double t0 = now_ms();
+    if (!pl || !out) return fail(err, errlen, B200_EINVAL, "plan / out is NULL");
+    if (!pl->executed) return fail(err, errlen, B200_EINVAL, "plan was not executed");
+    if (down_looks < 1 || across_looks < 1) return fail(err, errlen, B200_EINVAL, "looks must be >= 1 (%d down, %d across)", down_looks, across_looks);
+    if (method != B200_LOOKS_AVERAGE && method != B200_LOOKS_NEAREST) return fail(err, errlen, B200_EINVAL, "bad method %d", method);
+    const void *src = nullptr;
+    int dtype = B200_T_DOUBLE, bands = 1;
+    switch (layer) {
+    case B200_LAYER_LAT: src = pl->layers.lat; break;
+    case B200_LAYER_LON: src = pl->layers.lon; break;
+    case B200_LAYER_HGT: src = pl->layers.hgt; break;
+    case B200_LAYER_LOS: src = pl->layers.los; dtype = B200_T_FLOAT; bands = 2; break;
+    case B200_LAYER_INC: src = pl->layers.inc; dtype = B200_T_FLOAT; bands = 2; break;
+    case B200_LAYER_MASK: src = pl->layers.mask; dtype = B200_T_BYTE; break;
+    default: return fail(err, errlen, B200_EINVAL, "bad layer %d", layer);
+    }
+    if (!src) return fail(err, errlen, B200_EINVAL, "layer %d was not requested from this plan", layer);
+    if (method == B200_LOOKS_AVERAGE && across_looks > kLooksMaxTile)
+        return fail(err, errlen, B200_EINVAL, "across_looks = %d exceeds the %d column sums a tile holds", across_looks, kLooksMaxTile);
+    LooksGeom G{pl->nlines, pl->p.width, bands, B200_SCHEME_BIL, down_looks, across_looks, pl->nlines / down_looks,
+                pl->p.width / across_looks, 0, pl->nlines / down_looks};
+    if (res) {
+        res->out_length = G.out_length;
+        res->out_width = G.out_width;
+        res->ms_kernels = res->ms_total = 0.f;
+        res->gpu_launches = 0;
+    }
+    if (G.out_length == 0 || G.out_width == 0) return B200_OK;
+    CK(cudaSetDevice(pl->p.device));
+    cudaStream_t s = pl->stream;
+    const size_t out_bytes = (size_t)G.out_length * G.out_width * bands * type_size(dtype);
+    void *d_out = nullptr;
+    CK(dmalloc(&d_out, out_bytes));
+    struct Guard {
+        void *p;
+        ~Guard() { dfree(p); }
+    } guard{d_out};
+    CK(cudaEventRecord(pl->ev0, s));
+    if (launch_looks(G, dtype, method, src, d_out, s) != 0) return fail(err, errlen, B200_EINVAL, "cannot launch the looks kernel");
+    CK(cudaEventRecord(pl->ev1, s));
+    CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    if (res) {
+        CK(cudaEventElapsedTime(&res->ms_kernels, pl->ev0, pl->ev1));
+        res->gpu_launches = 1;
+        res->ms_total = (float)(now_ms() - t0);
+    }
+    return B200_OK;
+}
+
 extern "C" int b200_mask_to_radar_run(const void *mask, int dtype, int mask_length, int mask_width, double start_lat,
                                       double delta_lat, double start_lon, double delta_lon, const void *lat, const void *lon,
                                       int coord_f32, size_t npix, void *out, int device, b200_mask_result *res, char *err,

@@ -161,7 +161,9 @@ int looks_average(const LooksGeom &G, const void *in, void *out, cudaStream_t s)
     const int inner = (G.scheme == kSchemeBIP) ? G.bands : 1;
     const long long per_out = (long long)G.la * inner * (CPLX ? 2 : 1);
     if (per_out > kLooksMaxTile) return -2;
-    int tile_out = (int)(kLooksMaxTile / per_out);
+    // ~1024 column sums per CTA: enough CTAs (several waves on 148 SMs) to keep HBM busy, four columns per thread
+    int tile_out = (int)((per_out >= 1024 ? kLooksMaxTile : 1024) / per_out);
+    if (tile_out < 1) tile_out = 1;
     if (tile_out > G.out_width) tile_out = G.out_width;
     const int tiles = (G.out_width + tile_out - 1) / tile_out;
     const long long rows = (long long)G.nlines * (G.scheme == kSchemeBIP ? 1 : G.bands);

@@ -90,8 +90,8 @@ def test_multilook_and_water_mask_through_the_host_mirrors(tmp_path):
     topo.losFilename, topo.incFilename, topo.maskFilename = (str(geom / f) for f in ("los.rdr", "incLocal.rdr", "shadowMask.rdr"))
     topo.topo()
 
-    # water mask on the DEM grid: "water" below the median height (SWBD convention -1 water / 0 land)
-    wb = np.where(sc.dem < np.median(sc.dem), -1, 0).astype(np.int8)
+    # water mask on the DEM grid: "water" below the scene's median height (SWBD convention -1 water / 0 land)
+    wb = np.where(sc.dem < np.median(np.fromfile(geom / "hgt.rdr")), -1, 0).astype(np.int8)
     wpath = str(tmp_path / "swbd.wbd")
     wb.tofile(wpath)
     wim = IF.createImage()
@@ -122,3 +122,28 @@ def test_multilook_and_water_mask_through_the_host_mirrors(tmp_path):
             h = IF.createImage().load(str(out_dir / (fbase + ".rdr.xml")))
             assert (h.width, h.length, h.bands) == (sc.width // 3, sc.length // 4, bands)
             assert os.path.exists(out_dir / (fbase + ".rdr.full.xml")) and os.path.exists(out_dir / (fbase + ".rdr.full.vrt"))
+
+
+def test_looks_of_resident_topo_layers():
+    """b200_topo_plan_looks: multilooked layers straight from the plan's HBM copy == looks of the fetched layers."""
+    sc = pu.rough_scene(50, 2048)
+    p = _capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                          delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side,
+                          peg_heading=sc.peg_heading, dem_method="BILINEAR", line0=6, nlines=40)
+    plan = _capi.TopoPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]], want_los=True,
+                          want_inc=False, want_mask=True)
+    with pytest.raises(_capi.B200Error):
+        plan.looks("lat", 4, 3)  # not executed yet
+    plan.execute()
+    full = plan.fetch()
+    for layer in ("lat", "lon", "hgt", "los", "mask"):
+        for method in ("AVERAGE", "NEAREST"):
+            g, res = plan.looks(layer, 7, 5, method=method)
+            want = orc.looks(full[layer], 7, 5, scheme="BIL", method=method)
+            assert g.shape == want.shape == ((5, 409) if layer != "los" else (5, 2, 409))
+            assert np.array_equal(g, want), (layer, method)
+            assert res["gpu_launches"] == 1 and res["ms_kernels"] > 0
+    with pytest.raises(_capi.B200Error) as ei:
+        plan.looks("inc", 2, 2)  # layer not requested
+    assert ei.value.code == -1
+    plan.close()

@@ -118,7 +118,43 @@ def resamp_perf(lines=1500, width=25000, reps=3):
     return out
 
 
+def post_perf(lines=1500, width=25000, ld=14, la=4):
+    """Multilooking from the resident topo layers (device time of the kernel alone) and through the host-buffer verbs."""
+    sc = synth.make_scene(lines, width)
+    p = _capi.topo_params(dem_shape=sc.dem.shape, first_lat=sc.first_lat, first_lon=sc.first_lon, delta_lat=sc.delta_lat,
+                          delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
+                          side=sc.side, peg_heading=sc.peg_heading, dem_method="BILINEAR")
+    tp = _capi.TopoPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]],
+                        want_los=True, want_inc=False, want_mask=True)
+    tp.execute()
+    out = {"looks": [ld, la]}
+    npx = lines * width
+    for layer, bpp in (("lat", 8), ("los", 8), ("mask", 1)):
+        for method in ("AVERAGE", "NEAREST"):
+            ms = min(tp.looks(layer, ld, la, method=method)[1]["ms_kernels"] for _ in range(5))
+            algo = npx * bpp * (1.0 + 1.0 / (ld * la)) if method == "AVERAGE" else 2.0 * npx * bpp / (ld * la)
+            out[f"{layer}_{method}"] = {"ms_kernel": round(ms, 4), "algorithmic_GBs": round(algo / ms / 1e6, 1)}
+    full = tp.fetch()
+    tp.close()
+    t0 = time.perf_counter()
+    _, r = _capi.looks_run(full["lat"], ld, la)
+    out["host_verb_lat"] = {"wall_ms": round(1e3 * (time.perf_counter() - t0), 1), "ms_total": round(r["ms_total"], 1),
+                            "launches": r["gpu_launches"]}
+    mask = (sc.dem < np.median(sc.dem)).astype(np.int8)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _, r = _capi.mask_to_radar_run(mask, sc.first_lat, sc.delta_lat, sc.first_lon, sc.delta_lon, full["lat"], full["lon"])
+        best = min(best, time.perf_counter() - t0)
+    out["mask_to_radar"] = {"wall_ms": round(1e3 * best, 1), "ms_kernels_incl_h2d_wait": round(r["ms_kernels"], 2),
+                            "launches": r["gpu_launches"]}
+    return out
+
+
 if __name__ == "__main__":
+    if "--post" in sys.argv:
+        print(json.dumps({"post": post_perf()}), flush=True)
+        sys.exit(0)
     if "--resamp" in sys.argv:
         print(json.dumps({"resamp_slc": resamp_perf()}), flush=True)
         sys.exit(0)
