@@ -578,6 +578,9 @@ def run_c4(args, ranks):
     gp = capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0 - 1.7, dr=sc.dr, prf=sc.prf,
                          t0=sc.t0 - 0.013, wvl=sc.wvl, side=sc.side, device=dev, out_f32=True)
     gplan = capi.GeoPlan(gp, topo_plan=tplan)
+    # the reference geometry is fixed for the whole batch: its ECEF coordinates are formed once (outside the timed
+    # region, like the topo run that produced it), not once per secondary date
+    gplan.freeze_geometry()
 
     def step():
         ms = 0.0

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200GEOM_ABI_VERSION 4
+#define B200GEOM_ABI_VERSION 5
 
 enum {
     B200_OK = 0,
@@ -209,6 +209,13 @@ int b200_geo_plan_create_from_topo(const b200_geo_params *p, b200_topo_plan *top
 int b200_geo_plan_execute(b200_geo_plan *plan, const b200_geo_params *p, const b200_orbit *orbit,
                           const b200_poly1d *dop, int want_azt, int want_rgm, int want_azoff, int want_rgoff,
                           float *ms_kernels, char *err, size_t errlen);
+/* Stack shape only (one reference geometry x N secondary dates): declares that the plan's lat / lon / hgt will not change
+ * any more and converts them ONCE to ECEF for the ellipsoid (major, e2); every later b200_geo_plan_execute with that
+ * ellipsoid starts from the stored coordinates instead of redoing LLH -> XYZ per pixel and date (the reference redoes it,
+ * geo2rdr.f90:247-250; the stored values are the ones the per-pixel path forms, so the outputs are bit-identical).
+ * Costs 24 B/pixel of device memory.  Call again after the geometry changed (e.g. the topo plan it borrows from was
+ * re-executed). */
+int b200_geo_plan_freeze_geometry(b200_geo_plan *plan, double major, double e2, char *err, size_t errlen);
 int b200_geo_plan_fetch(b200_geo_plan *plan, const b200_geo_outputs *out, b200_geo_result *res, char *err,
                         size_t errlen);
 void b200_geo_plan_destroy(b200_geo_plan *plan);

@@ -138,7 +138,7 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
            "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
-           "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks"]
+           "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks", "b200_geo_plan_freeze_geometry"]
 
 _lib = None
 
@@ -171,6 +171,7 @@ def lib():
     L.b200_geo_plan_create_from_topo.argtypes = [C.POINTER(GeoParams), C.c_void_p, C.POINTER(C.c_void_p)] + err
     L.b200_geo_plan_execute.argtypes = [C.c_void_p, C.POINTER(GeoParams), C.POINTER(Orbit), C.POINTER(Poly1d),
                                         C.c_int, C.c_int, C.c_int, C.c_int, _fp] + err
+    L.b200_geo_plan_freeze_geometry.argtypes = [C.c_void_p, C.c_double, C.c_double] + err
     L.b200_geo_plan_fetch.argtypes = [C.c_void_p, C.POINTER(GeoOutputs), C.POINTER(GeoResult)] + err
     L.b200_geo_plan_destroy.argtypes = [C.c_void_p]
     L.b200_geo_plan_destroy.restype = None
@@ -533,6 +534,12 @@ class GeoPlan:
         _check(lib().b200_geo_plan_execute(self.handle, C.byref(params), C.byref(orb), C.byref(dop),
                                            *[int(k in want) for k in _GEO_KEYS], C.byref(ms), e, 512), e)
         return ms.value
+
+    def freeze_geometry(self, a=6378137.0, e2=0.0066943799901):
+        """Stack shape: convert the (now fixed) lat / lon / hgt to ECEF once for all secondary dates
+        (b200_geo_plan_freeze_geometry)."""
+        e = _errbuf()
+        _check(lib().b200_geo_plan_freeze_geometry(self.handle, float(a), float(e2), e, 512), e)
 
     def fetch(self, out=None):
         p = self.last_params

@@ -628,10 +628,14 @@ struct b200_geo_plan {
     int launches = 0;
     bool executed = false;
     int want[4] = {0, 0, 0, 0};
+    // frozen geometry (b200_geo_plan_freeze_geometry): ECEF copy of lat / lon / hgt for the given ellipsoid
+    double *d_xyz[3] = {nullptr, nullptr, nullptr};
+    double xyz_major = 0.0, xyz_e2 = 0.0;
 
     ~b200_geo_plan()
     {
         cudaSetDevice(p.device);
+        for (double *q : d_xyz) dfree(q);
         if (owns_inputs) {
             dfree(d_lat);
             dfree(d_lon);
@@ -770,6 +774,7 @@ int geo_prepare(b200_geo_plan *pl, const b200_geo_params &p, const b200_orbit *o
     const double pi = 4.0 * atan(1.0);
     C.deg2rad = pi / 180.0;
     C.sol = 299792458.0; // fortranUtils.f90:43-46
+    C.xyz_in = 0;
     // ---- doppler-vs-range polynomial and its derivative (:161-189) ----
     C.fd.order = dop->order;
     C.fd.mean = p.rho0 + dop->mean * p.drho;
@@ -859,6 +864,12 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
     const int want[4] = {want_azt, want_rgm, want_azoff, want_rgoff};
     if ((rc = geo_alloc_outputs(pl, p, want, err, errlen)) != B200_OK) return rc;
     GeoLayers L{pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_out[0], pl->d_out[1], pl->d_out[2], pl->d_out[3]};
+    if (pl->d_xyz[0] && pl->xyz_major == p.major && pl->xyz_e2 == p.e2) { // frozen geometry of this ellipsoid
+        R.C.xyz_in = 1;
+        L.lat = pl->d_xyz[0];
+        L.lon = pl->d_xyz[1];
+        L.hgt = pl->d_xyz[2];
+    }
     CK(cudaMemsetAsync(pl->d_stats, 0, sizeof(GeoStats), s));
     if (geo_launch(R, pl->line0, pl->nlines, L, p.out_f32, pl->d_stats, s) != 0)
         return fail(err, errlen, B200_EINVAL, "cannot launch the geo2rdr kernel");
@@ -869,6 +880,25 @@ extern "C" int b200_geo_plan_execute(b200_geo_plan *pl, const b200_geo_params *p
     pl->launches = 2;
     pl->executed = true;
     if (ms_kernels) *ms_kernels = pl->ms_kernels;
+    return B200_OK;
+}
+
+extern "C" int b200_geo_plan_freeze_geometry(b200_geo_plan *pl, double major, double e2, char *err, size_t errlen)
+{
+    if (!pl) return fail(err, errlen, B200_EINVAL, "plan is NULL");
+    if (!(major > 0.0) || !(e2 >= 0.0 && e2 < 1.0)) return fail(err, errlen, B200_EINVAL, "bad ellipsoid (a = %g, e2 = %g)", major, e2);
+    CK(cudaSetDevice(pl->p.device));
+    const size_t npix = (size_t)pl->nlines * (size_t)pl->p.dem_width;
+    for (int i = 0; i < 3; i++)
+        if (!pl->d_xyz[i]) CK(dmalloc(&pl->d_xyz[i], sizeof(double) * npix));
+    GeoConst C{};
+    C.elp = make_ellipsoid(major, e2);
+    C.deg2rad = 4.0 * atan(1.0) / 180.0;
+    launch_llh_to_xyz(C, pl->d_lat, pl->d_lon, pl->d_hgt, pl->d_xyz[0], pl->d_xyz[1], pl->d_xyz[2], npix, pl->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(pl->stream));
+    pl->xyz_major = major;
+    pl->xyz_e2 = e2;
     return B200_OK;
 }
 

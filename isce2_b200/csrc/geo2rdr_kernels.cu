@@ -67,7 +67,7 @@ k_geo2rdr(const __grid_constant__ GeoConst C, OrbitView orb_g, int line0, int nl
         const int line = line0 + row;                   // 0-based line of the lat/lon/hgt images
         const size_t o = (size_t)row * (size_t)C.demwidth + (size_t)pix;
         double azt = BAD_VALUE, rgm = BAD_VALUE, rgoff = BAD_VALUE, azoff = BAD_VALUE;
-        Vec3 xyz = llh_to_xyz(C.elp, L.lat[o] * C.deg2rad, L.lon[o] * C.deg2rad, L.hgt[o]);
+        Vec3 xyz = C.xyz_in ? Vec3{L.lat[o], L.lon[o], L.hgt[o]} : llh_to_xyz(C.elp, L.lat[o] * C.deg2rad, L.lon[o] * C.deg2rad, L.hgt[o]);
         double tline = C.tmid, tprev = 0.0, rngpix = 0.0;
         Vec3 satx = C.xyz_mid, satv = C.vel_mid;
         const Vec3 sata = C.acc_mid;
@@ -198,7 +198,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
         }
         const size_t o = rowoff + (size_t)pix;
         double azt = BAD_VALUE, rgm = BAD_VALUE, rgoff = BAD_VALUE, azoff = BAD_VALUE;
-        const Vec3 xyz = llh_to_xyz(C.elp, lat * C.deg2rad, lon * C.deg2rad, hgt);
+        const Vec3 xyz = C.xyz_in ? Vec3{lat, lon, hgt} : llh_to_xyz(C.elp, lat * C.deg2rad, lon * C.deg2rad, hgt);
         double tline = C.tmid, rngpix = 0.0;
         OrbState S;
         S.x = C.xyz_mid;
@@ -289,6 +289,27 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
         for (int q = 0; q < 4; q++)
             if (v[q]) atomicAdd(dst[q], (unsigned long long)v[q]);
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_llh_to_xyz(const __grid_constant__ GeoConst C, const double *__restrict__ lat, const double *__restrict__ lon,
+             const double *__restrict__ hgt, double *__restrict__ x, double *__restrict__ y, double *__restrict__ z, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const Vec3 v = llh_to_xyz(C.elp, lat[i] * C.deg2rad, lon[i] * C.deg2rad, hgt[i]);
+        x[i] = v.x;
+        y[i] = v.y;
+        z[i] = v.z;
+    }
+}
+
+void launch_llh_to_xyz(const GeoConst &C, const double *lat, const double *lon, const double *hgt, double *x, double *y, double *z,
+                       size_t n, cudaStream_t s)
+{
+    if (n == 0) return;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    k_llh_to_xyz<<<(unsigned)blocks, 256, 0, s>>>(C, lat, lon, hgt, x, y, z, n);
 }
 
 void launch_geo_setup(int orbit_method, const OrbitView &orb, double tmid, GeoMid *d_out, cudaStream_t s)

@@ -21,12 +21,17 @@ struct GeoConst {
     int orbit_method, bistatic;
     int demwidth;
     double deg2rad, sol;
+    int xyz_in; // 1: the lat / lon / hgt layers hold ECEF x / y / z (frozen stack geometry, launch_llh_to_xyz)
 };
 
 struct GeoLayers {
     const double *lat, *lon, *hgt; // [nlines][demwidth] rows of the block, degrees / metres
     void *azt, *rgm, *azoff, *rgoff; // [nlines][demwidth] float or double, may be null
 };
+
+// ECEF coordinates of a lat / lon / hgt geometry, exactly as the solve kernels form them per pixel (geo2rdr.f90:247-250)
+void launch_llh_to_xyz(const GeoConst &C, const double *lat, const double *lon, const double *hgt, double *x, double *y, double *z,
+                       size_t n, cudaStream_t s);
 
 struct GeoStats {
     unsigned long long outside, valid, converged, iterations;

@@ -316,6 +316,9 @@ class Geo2rdrStack:
                     p, start = self._params(job, shape, dev)
                     if job["key"] not in plans:  # upload once, reuse for every date
                         plans[job["key"]] = _capi.GeoPlan(p, lat=gm["lat"], lon=gm["lon"], hgt=gm["hgt"])
+                        if sum(1 for j in by_slot[s] if j["key"] == job["key"]) > 1:
+                            # several dates on this geometry: LLH -> ECEF once instead of once per date
+                            plans[job["key"]].freeze_geometry(self.a, self.e2)
                     plan = plans[job["key"]]
                     t, pos, vel = export_rows(job["info"].orbit, start)
                     ms = plan.execute(p, t, pos, vel, doppler_coeffs=job["doppler"], want=("azoff", "rgoff"))

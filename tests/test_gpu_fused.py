@@ -184,3 +184,32 @@ def test_chained_components_write_the_same_files(tmp_path, devices):
     assert (grdr2.numValid, grdr2.numOutsideImage, grdr2.numConverged) == (grdr.numValid, grdr.numOutsideImage, grdr.numConverged)
     assert topo2.snwe == topo.snwe and topo2.totalConverged == topo.totalConverged
     assert grdr2.numValid > 0.5 * sc.length * sc.width
+
+
+def test_frozen_stack_geometry_is_bit_identical():
+    """b200_geo_plan_freeze_geometry: the ECEF copy of a fixed reference geometry serves every secondary date; outputs
+    equal the per-pixel LLH -> XYZ path bit for bit; another ellipsoid falls back to that path."""
+    sc = pu.rough_scene(40, 2048)
+    c = pu.cpu_topo(sc, dem_method="BILINEAR", want_inc=False, want_mask=False)
+    outs = {}
+    for frozen in (False, True):
+        kw0 = _secondaries(sc)[0][0]
+        plan = _capi.GeoPlan(_geo_params(sc, kw0, False), lat=c["lat"], lon=c["lon"], hgt=c["hgt"])
+        if frozen:
+            plan.freeze_geometry()
+        for i, (kw, f32, want) in enumerate(_secondaries(sc)):
+            p = _geo_params(sc, kw, f32)
+            plan.execute(p, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"], want=GEO_KEYS)
+            outs[(frozen, i)] = plan.fetch()
+        # a sphere of the same radius: not the frozen ellipsoid
+        p2 = _capi.geo_params(length=kw0["length"], width=kw0["width"], dem_shape=(sc.length, sc.width), r0=kw0["r0"], dr=kw0["dr"],
+                              prf=kw0["prf"], t0=kw0["t0"], wvl=kw0["wvl"], side=kw0["side"], e2=0.0)
+        plan.execute(p2, kw0["orbit_t"], kw0["orbit_pos"], kw0["orbit_vel"], want=("rgm",))
+        outs[(frozen, "sphere")] = plan.fetch()
+        plan.close()
+    for i in (0, 1):
+        for k in GEO_KEYS:
+            assert np.array_equal(outs[(False, i)][k], outs[(True, i)][k]), (i, k)
+        assert outs[(False, i)]["num_valid"] == outs[(True, i)]["num_valid"] > 0
+    assert np.array_equal(outs[(False, "sphere")]["rgm"], outs[(True, "sphere")]["rgm"])
+    assert not np.array_equal(outs[(True, "sphere")]["rgm"], outs[(True, 0)]["rgm"])
