@@ -1093,6 +1093,22 @@ static int topo_run_impl(const b200_topo_params *p, const void *dem, int dem_dty
     const size_t w = (size_t)pl->p.width;
     const int cl = chunk_lines(pl->p.width, pl->nlines);
     int launches = 0;
+    // several jobs on one ellipsoid (the stack shape): the ECEF coordinates of a block are formed once for all of them
+    struct XyzScratch {
+        double *p[3] = {nullptr, nullptr, nullptr};
+        ~XyzScratch()
+        {
+            for (double *q : p) dfree(q);
+        }
+    } xs;
+    bool share_xyz = fused.size() >= 2;
+    for (size_t j = 1; j < fused.size() && share_xyz; j++)
+        share_xyz = fused[j].R->use_poly && fused[0].R->use_poly && fused[j].p.major == fused[0].p.major && fused[j].p.e2 == fused[0].p.e2;
+    if (share_xyz) {
+        const size_t cpx = (size_t)(cl < pl->nlines ? cl : pl->nlines) * w;
+        for (int i = 0; i < 3; i++) CK(dmalloc(&xs.p[i], sizeof(double) * cpx));
+        for (Job &J : fused) J.R->C.xyz_in = 1;
+    }
     auto launch_chunk = [&](int c0, int n, cudaEvent_t done) -> int {
         const size_t o = (size_t)c0 * w;
         TopoLayers L = pl->layers;
@@ -1108,8 +1124,18 @@ static int topo_run_impl(const b200_topo_params *p, const void *dem, int dem_dty
             if (launch_topo_mask(pl->C, pl->d_states + c0, pl->line0 + c0, n, L, pl->dem_max, pl->scr, g, s) != 0) return -1;
             launches++;
         }
+        if (share_xyz) {
+            launch_llh_to_xyz(fused[0].R->C, pl->layers.lat + o, pl->layers.lon + o, pl->layers.hgt + o, xs.p[0], xs.p[1], xs.p[2],
+                              (size_t)n * w, s);
+            launches++;
+        }
         for (Job &J : fused) { // same stream: the block's lat / lon / hgt are complete
             GeoLayers G{pl->layers.lat + o, pl->layers.lon + o, pl->layers.hgt + o, nullptr, nullptr, nullptr, nullptr};
+            if (share_xyz) {
+                G.lat = xs.p[0];
+                G.lon = xs.p[1];
+                G.hgt = xs.p[2];
+            }
             void **lo[4] = {&G.azt, &G.rgm, &G.azoff, &G.rgoff};
             for (int i = 0; i < 4; i++)
                 if (J.gp->d_out[i]) *lo[i] = (char *)J.gp->d_out[i] + o * J.esz;

@@ -69,3 +69,40 @@ def test_reference_arm_runs_on_rank0_only_world2():
     d = lines[0]
     assert d["impl"] == "reference" and d["metric"] == "topo+geo2rdr Mpixels/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+BENCH_WORKER = r'''
+import sys
+sys.path.insert(0, {root!r})
+import isce2_b200
+from tests import fake_capi_for_bench as fake
+sys.modules["isce2_b200._capi"] = fake
+isce2_b200._capi = fake
+import bench
+sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--workload", "c0c1", "--lines", "37", "--e2e-steps", "2",
+            "--no-cpu-baseline", "--max-seconds", "200"]
+bench.main()
+'''
+
+
+@pytest.mark.timeout(400)
+def test_bench_control_flow_world2_with_a_stand_in_library(tmp_path):
+    """The whole of bench.run_b200 under torchrun with two ranks (tests/fake_capi_for_bench.py stands in for the CUDA
+    library): every rank reaches every barrier / reduction, also when the two end-to-end arms of a rank that does not
+    start at line 0 differ in the last bits; rank 0 alone prints the JSON line, with the contract's keys."""
+    script = tmp_path / "bench_worker.py"
+    script.write_text(BENCH_WORKER.format(root=ROOT))
+    p = _torchrun([str(script)], timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = lines[0]
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "e2e_two_calls", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 2 and d["config"]["pixels_per_step"] == 37 * 21000 and d["cpu_baseline"] is None
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] < d["e2e_two_calls"]["h2d_bytes_per_step"]
+    v = d["e2e"]["vs_two_calls"]
+    assert v["compared"] and v["validity_equal"] and v["max_abs_offset_diff_px"] < 1e-3
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
