@@ -59,14 +59,16 @@ class Looks(Component):
         outImage.setLength(outLength)
         outImage.setFilename(self.outputFilename)
         outImage.setAccessMode('WRITE')
-        out = outImage.createImage()
-
-        src = np.ascontiguousarray(inImage.memMap())
         if outLength > 0 and outWidth > 0:
+            out = outImage.createImage()
+            src = np.ascontiguousarray(inImage.memMap())
             res_arr, res = _capi.looks_run(src, self.downLooks, self.acrossLooks, scheme=inImage.scheme, method=self.method,
                                            device=self.gpuDevice)
             out[...] = res_arr.view(out.dtype)
             self.gpuTimings = {k: res[k] for k in ("ms_kernels", "ms_total", "gpu_launches")}
+        else:  # fewer lines / samples than looks: the reference's loops do not execute and leave an empty raster
+            os.makedirs(os.path.dirname(os.path.abspath(self.outputFilename)), exist_ok=True)
+            open(self.outputFilename, 'wb').close()
         inImage.finalizeImage()
         outImage.finalizeImage()
         outImage.renderHdr()

@@ -95,3 +95,25 @@ def test_post_products_argument_validation_precedes_device_use():
     assert ei.value.code == -1
     with pytest.raises(TypeError):
         _capi.mask_to_radar_run(np.zeros((4, 4), np.float64), 1.0, -0.1, 0.0, 0.1, np.zeros(5), np.zeros(5))
+
+
+def test_looks_component_with_fewer_lines_than_looks_writes_an_empty_raster(tmp_path):
+    """Looks.py:44-45: outLength = length // downLooks may be 0; the reference's loops then do not execute.  Needs no
+    device (nothing is computed)."""
+    from isce2_b200 import image as IF, looks as LK
+    np.zeros((3, 20), np.float32).tofile(tmp_path / "hgt.rdr")
+    im = IF.createImage()
+    im.initImage(str(tmp_path / "hgt.rdr"), "read", 20, "FLOAT")
+    im.setLength(3)
+    im.coord1.coordStart, im.coord1.coordDelta = 100.0, 2.0
+    im.renderHdr()
+    lk = LK.Looks()
+    lk.setDownLooks(4)
+    lk.setAcrossLooks(2)
+    lk.setInputImage(im)
+    lk.setOutputFilename(str(tmp_path / "ml" / "hgt.rdr"))
+    o = lk.looks()
+    assert (o.width, o.length) == (10, 0) and os.path.getsize(tmp_path / "ml" / "hgt.rdr") == 0
+    assert os.path.exists(tmp_path / "ml" / "hgt.rdr.xml")
+    # geo-referenced images: delta scales with the looks, start moves to the centre of the first look (Looks.py:49-55)
+    assert o.coord1.coordDelta == 4.0 and o.coord1.coordStart == 101.0
