@@ -781,7 +781,7 @@ LOOKS_METHODS = {"AVERAGE": 0, "ISCE": 0, "NEAREST": 1, "GDAL": 1}
 
 
 def _band_axes(scheme):
-    # position of (line, band, sample) in an array stored in the given interleaving
+    # which quantity (0 line, 1 band, 2 sample) runs along each axis of an array stored in the given interleaving
     return {"BIL": (0, 1, 2), "BIP": (0, 2, 1), "BSQ": (1, 0, 2)}[scheme]
 
 

@@ -45,13 +45,6 @@ def test_looks_full_size_properties():
     for r0 in (0, 53, L // ld - 1):
         c = orc.looks(a[r0 * ld:(r0 + 1) * ld], ld, la, scheme="BIL")
         assert np.array_equal(g[r0:r0 + 1], c)
-    # several pipeline blocks of a band-sequential and of a pixel-interleaved image (one H2D / D2H piece per band plane)
-    for shape, scheme in (((2, 3000, 3000), "BSQ"), ((3000, 3000, 2), "BIP")):
-        b = rng.normal(size=shape).astype(np.float32)
-        gb, rb = _capi.looks_run(b, 3, 5, scheme=scheme)
-        assert rb["gpu_launches"] > 1
-        assert np.array_equal(gb, orc.looks(b, 3, 5, scheme=scheme)), scheme
-        assert np.array_equal(_capi.looks_run(b, 3, 5, scheme=scheme, method="NEAREST")[0], orc.looks(b, 3, 5, scheme=scheme, method="NEAREST"))
     k, _ = _capi.looks_run(np.full((L, W), 3.25, np.float64), ld, la)
     assert np.all(k == 3.25)
     m, _ = _capi.looks_run(np.full((L, W), -7, np.int8), ld, la)
