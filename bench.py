@@ -72,9 +72,10 @@ class Ranks:
             import torch.distributed as dist
             import datetime
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            # a finite timeout: ranks that fall out of step raise instead of waiting for each other forever
+            # a finite timeout: ranks that fall out of step raise instead of waiting for each other forever (long enough
+            # for the idle ranks of the --impl reference arm, which wait at the final barrier while rank 0 computes)
             dist.init_process_group(backend="gloo", rank=self.rank, world_size=self.world,
-                                    timeout=datetime.timedelta(seconds=300))
+                                    timeout=datetime.timedelta(seconds=1000))
             self.dist = dist
             self.torch = torch
 
