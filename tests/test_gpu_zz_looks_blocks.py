@@ -1,6 +1,6 @@
 """Multilooking of images that span several pipeline blocks in the band-sequential and pixel-interleaved layouts (one
-host<->device piece per band plane and block).  Kept in a file that sorts last: this case was added after the round's last
-GPU pass, so under `pytest -x` a surprise here cannot hide the tests that were run on hardware."""
+host<->device piece per band plane and block).  Kept in a file that sorts last: the case was added after the round's last
+full GPU pass (it has since been run on a B200 on its own), so under `pytest -x` a surprise here cannot hide the rest."""
 import numpy as np
 import pytest
 

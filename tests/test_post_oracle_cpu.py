@@ -46,6 +46,25 @@ def test_looks_restatement_is_bit_identical_to_reference_templates(dt, code):
         assert np.array_equal(mine.view(np.uint8), out.view(np.uint8)), (dt, length, width, bands, ld, la)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_LOOKS), reason="oracle/_ref not built (reference tree absent)")
+def test_looks_restatement_random_shapes_against_reference_templates():
+    """Forty random (shape, bands, looks, type) draws, including looks that do not divide the image and looks larger
+    than the image (empty output)."""
+    ref = C.CDLL(REF_LOOKS)
+    rng = np.random.default_rng(2026)
+    for _ in range(40):
+        dt, code = DTYPES[int(rng.integers(0, len(DTYPES)))]
+        length, width, bands = int(rng.integers(1, 40)), int(rng.integers(1, 60)), int(rng.integers(1, 4))
+        ld, la = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        a = _random(rng, (length, width, bands), dt)
+        out = np.zeros((length // ld, width // la, bands), dt)
+        if out.size:
+            assert ref.ref_take_looks(code, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), length, width, bands, ld, la) == 0
+        mine = orc.looks(a, ld, la, scheme="BIP")
+        assert mine.shape == out.shape
+        assert np.array_equal(mine.view(np.uint8), out.view(np.uint8)), (dt, length, width, bands, ld, la)
+
+
 def test_looks_restatement_layouts_and_nearest():
     rng = np.random.default_rng(3)
     a = rng.normal(size=(12, 2, 20)).astype(np.float32)  # BIL
