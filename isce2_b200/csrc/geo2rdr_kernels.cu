@@ -164,7 +164,10 @@ k_geo2rdr(const __grid_constant__ GeoConst C, OrbitView orb_g, int line0, int nl
 // coalesced) and loads the next pixel's lat / lon / hgt before it solves the current one: with one pixel per thread
 // the warps of a CTA all sat on the DRAM latency of their three input loads at the same moment (ncu: 43 % of the stall
 // samples on the first use of lat / lon / hgt).
-constexpr int kGeoPixPerThread = 4;
+#ifndef B2_GEO_PPT
+#define B2_GEO_PPT 4 // tunable (tools/build_variant.sh NAME "-DB2_GEO_PPT=8")
+#endif
+constexpr int kGeoPixPerThread = B2_GEO_PPT;
 
 template <int METHOD, typename T>
 __global__ void __launch_bounds__(kGeoBlock)

@@ -200,11 +200,19 @@ __device__ __forceinline__ void load_line_state(LineState &sL, const LineState *
 //   * k_topo_fused: the run is a strip of kStrip pixels staged up front (the final pass needs them again);
 //   * k_topo_solve: the run is a segment of up to kSegMax pixels streamed through a ring of kRing entries, which
 //     makes the idle tail at the end of a run (lanes waiting for the last pixels) 8x rarer than with 128-pixel strips.
+// tunables of experimental builds (tools/build_variant.sh NAME "-DB2_SEG_MAX=2048"); the defaults are the measured best
+#ifndef B2_RING
+#define B2_RING 64
+#endif
+#ifndef B2_SEG_MAX
+#define B2_SEG_MAX 1024
+#endif
 constexpr int kStrip = 128;                                    // pixels per warp (fused kernel)
 constexpr int kSolvePixelsPerCta = (kTopoBlock / 32) * kStrip; // 512
-constexpr int kRing = 64;                                      // staged look-ahead per warp (split solve kernel)
+constexpr int kRing = B2_RING;                                 // staged look-ahead per warp (split solve kernel), power of two
 constexpr int kStage = 32;                                     // pixels staged per refill of the ring
-constexpr int kSegMax = 1024;                                  // longest run of pixels per warp
+constexpr int kSegMax = B2_SEG_MAX;                            // longest run of pixels per warp
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 2 * kStage, "the ring is indexed with a mask and refilled kStage at a time");
 
 // Per-pixel constants of the upcoming pixels, evaluated with all lanes busy (a refill inside the solve loop typically
 // has only a handful of lanes active, so everything hoisted here is paid at 1/6 of the price).
@@ -689,7 +697,10 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
     __syncthreads();
 }
 
-constexpr int kMaskKnots = 256;
+#ifndef B2_MASK_KNOTS
+#define B2_MASK_KNOTS 256
+#endif
+constexpr int kMaskKnots = B2_MASK_KNOTS;
 
 template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kMaskBlock, 1024 / kMaskBlock)
