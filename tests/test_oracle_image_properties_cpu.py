@@ -1,0 +1,82 @@
+"""Whole-image pin of the topozero / geo2rdr restatement (the reference asserts no image output anywhere, so
+"self-consistency becomes the pin").  Every pixel of an oracle run is checked against the DEFINING equations of the
+range-Doppler geometry, evaluated here in plain numpy, independently of the restatement's internals:
+
+  (1) |P - S(t_line)| = slant range of the pixel             (range sphere, topozero.f90:495-516)
+  (2) (P - S) . V = lambda/2 * f_dop * range                  (Doppler cone; zero-Doppler and native-Doppler scenes)
+  (3) the point lies on the side of the track the look direction says
+  (4) its ellipsoidal height is the DEM height at its own (lat, lon) to the iteration threshold
+  (5) geo2rdr of the layers with the same orbit returns the pixel's own line / sample (offsets ~ 0, 1e-3 px)
+  (6) los channel 1 is the angle between the line of sight and the local vertical
+
+with S, V from the reference-identical Hermite / Legendre interpolators (bit-identical to the reference C, see
+test_oracle_pins.py) and P = WGS-84 LLH -> ECEF in numpy."""
+import numpy as np
+import pytest
+
+from isce2_b200 import synth
+from oracle import oracle as orc
+from tests import parity_util as pu
+
+
+def _ecef(lat_deg, lon_deg, h, a, e2):
+    la, lo = np.radians(lat_deg), np.radians(lon_deg)
+    n = a / np.sqrt(1.0 - e2 * np.sin(la) ** 2)
+    return np.stack([(n + h) * np.cos(la) * np.cos(lo), (n + h) * np.cos(la) * np.sin(lo), (n * (1.0 - e2) + h) * np.sin(la)], -1)
+
+
+def _bilinear(dem, y, x):
+    iy, ix = np.floor(y).astype(int), np.floor(x).astype(int)
+    fy, fx = y - iy, x - ix
+    d = dem.astype(np.float64)
+    return ((1 - fy) * (1 - fx) * d[iy, ix] + (1 - fy) * fx * d[iy, ix + 1] + fy * (1 - fx) * d[iy + 1, ix] + fy * fx * d[iy + 1, ix + 1])
+
+
+@pytest.mark.parametrize("sensor,orbit_method,dem_method", [("s1", "HERMITE", "BILINEAR"), ("s1", "HERMITE", "BIQUINTIC"),
+                                                            ("nisar", "LEGENDRE", "BICUBIC")])
+def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method, dem_method):
+    sc = synth.make_scene(20, 1536, sensor=sensor)  # ordinary terrain: (nearly) every pixel converges
+    o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method=dem_method, orbit_method=orbit_method, want_mask=False))
+    # (1)-(3), (5), (6) hold for every pixel whether or not its iteration met the threshold: the final pass always puts
+    # the point on the pixel's range sphere and Doppler cone (topozero.f90:618-644); (4) is a statement about converged ones
+    assert o["totalconv"] >= 0.999 * sc.pixels
+    orb = orc.Orbit(sc.orbit_t, sc.orbit_pos, sc.orbit_vel)
+    P = _ecef(o["lat"], o["lon"], o["hgt"], sc.a, sc.e2)
+    rng = sc.r0 + sc.dr * np.arange(sc.width)
+    dop = np.array([[orc.Poly2D(sc.doppler_coeffs)(line, pix) for pix in (0, sc.width // 2, sc.width - 1)] for line in (0, sc.length - 1)])
+    cols = [0, sc.width // 2, sc.width - 1]
+    for line in range(sc.length):
+        stat, S, V = orb.interp(sc.t0 + line / sc.prf, orbit_method)
+        assert stat == 0
+        d = P[line] - S
+        r = np.linalg.norm(d, axis=1)
+        assert np.abs(r - rng).max() < 2e-6, (line, np.abs(r - rng).max())                       # (1), metres
+        # (2): checked on the columns where the Doppler polynomial was evaluated through the reference-identical evaluator
+        if line in (0, sc.length - 1):
+            fd = dop[0 if line == 0 else 1]
+            lhs = (d[cols] @ V)
+            rhs = 0.5 * sc.wvl * fd * rng[cols]
+            assert np.abs(lhs - rhs).max() < 2e-5 * np.linalg.norm(V), (line, lhs - rhs)          # metres x speed
+        # (3): sign of the cross-track component, c = unit(n x v) with n the inward vertical at the satellite
+        nhat = -S / np.linalg.norm(S)
+        chat = np.cross(nhat, V)
+        assert np.all(np.sign(d @ chat) == -sc.side)
+        # (6)
+        up = _ecef(o["lat"][line], o["lon"][line], o["hgt"][line] + 1.0, sc.a, sc.e2) - P[line]
+        cosi = np.abs(np.sum(-d * up, axis=1)) / r
+        assert np.abs(np.degrees(np.arccos(np.clip(cosi, -1, 1))) - o["los"][line, 0]).max() < 2e-5
+    # (4): plain bilinear DEM at the pixel's own position against its height; the iteration stops at 0.05 m in slant range
+    y = (o["lat"] - sc.first_lat) / sc.delta_lat
+    x = (o["lon"] - sc.first_lon) / sc.delta_lon
+    dh = np.abs(_bilinear(sc.dem, y, x) - o["hgt"])
+    tol = 0.2 if dem_method == "BILINEAR" else 1.5  # the other interpolators differ from bilinear by their own overshoot
+    assert np.quantile(dh, 0.999) < tol, np.quantile(dh, 0.999)
+    # (5)
+    g = orc.geo2rdr(lat=o["lat"], lon=o["lon"], hgt=o["hgt"], orbit_t=sc.orbit_t, orbit_pos=sc.orbit_pos, orbit_vel=sc.orbit_vel,
+                    length=sc.length, width=sc.width, r0=sc.r0, dr=sc.dr, prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side,
+                    orbit_method=orbit_method,
+                    # geo2rdr takes the centroid in cycles / PRF against the range pixel (StripmapProc/runGeo2rdr.py:77-80)
+                    doppler_coeffs=tuple(c / sc.prf for c in sc.doppler_coeffs[0]))
+    inner = np.s_[1:-1, 1:-1]  # the first / last line and sample sit on the acquisition bounds geo2rdr tests against
+    assert (g["azoff"][inner] != -999999.0).all()
+    assert np.abs(g["azoff"][inner]).max() < pu.TOL_OFFSET_PX and np.abs(g["rgoff"][inner]).max() < pu.TOL_OFFSET_PX
