@@ -80,3 +80,49 @@ def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method,
     inner = np.s_[1:-1, 1:-1]  # the first / last line and sample sit on the acquisition bounds geo2rdr tests against
     assert (g["azoff"][inner] != -999999.0).all()
     assert np.abs(g["azoff"][inner]).max() < pu.TOL_OFFSET_PX and np.abs(g["rgoff"][inner]).max() < pu.TOL_OFFSET_PX
+
+
+def test_shadow_bit_against_its_geometric_definition_and_mask_on_simple_terrain():
+    """Shadow (mask bit 1, topozero.f90:791-809): the look angle at the satellite -- the angle between the direction to the
+    centre of the local approximating sphere and the direction to the target -- must grow with range; where it does not
+    (forward scan against the running maximum, backward scan against the running minimum) the pixel is shadowed.  The
+    angle is rebuilt here from the output layers alone (law of cosines replaced by the actual vectors)."""
+    sc = pu.rough_scene(16, 4096)
+    o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method="BILINEAR", want_mask=True))
+    m = o["mask"]
+    assert set(np.unique(m).tolist()) <= {0, 1, 2, 3} and (m == 1).any() and (m >= 2).any()
+    orb = orc.Orbit(sc.orbit_t, sc.orbit_pos, sc.orbit_vel)
+    P = _ecef(o["lat"], o["lon"], o["hgt"], sc.a, sc.e2)
+    mism = 0
+    for line in range(sc.length):
+        _, S, V = orb.interp(sc.t0 + line / sc.prf, "HERMITE")
+        llh = orc.xyz_to_latlon(S, sc.a, sc.e2)  # radians, metres
+        slat = np.sin(llh[0])
+        re = sc.a / np.sqrt(1.0 - sc.e2 * slat ** 2)
+        rn = sc.a * (1.0 - sc.e2) / (1.0 - sc.e2 * slat ** 2) ** 1.5
+        rcurv = re * rn / (re * np.cos(sc.peg_heading) ** 2 + rn * np.sin(sc.peg_heading) ** 2)  # curvature.F:26-64
+        up = np.array([np.cos(llh[0]) * np.cos(llh[1]), np.cos(llh[0]) * np.sin(llh[1]), np.sin(llh[0])])
+        centre = _ecef(np.degrees(llh[0]), np.degrees(llh[1]), 0.0, sc.a, sc.e2) - rcurv * up
+        d = P[line] - S
+        c = centre - S
+        ang = np.degrees(np.arccos(np.clip((d @ c) / (np.linalg.norm(d, axis=1) * np.linalg.norm(c)), -1, 1))).astype(np.float32)
+        sh = np.zeros(sc.width, bool)
+        run = ang[0]
+        for i in range(1, sc.width):
+            if ang[i] <= run:
+                sh[i] = True
+            else:
+                run = ang[i]
+        run = ang[-1]
+        for i in range(sc.width - 2, -1, -1):
+            if ang[i] >= run:
+                sh[i] = True
+            else:
+                run = ang[i]
+        mism += int((sh != ((m[line] & 1) == 1)).sum())
+    # measured: 0 of 65536 (995 shadowed); a last-bit difference of the two float32 angle sequences could move an edge
+    assert mism <= 8, mism
+    # no relief, no fold-over, no shadow
+    flat = synth.make_scene(6, 1024)
+    flat.dem = np.full_like(flat.dem, 250.0)
+    assert not orc.topo(**orc.scene_topo_kwargs(flat, dem_method="BILINEAR", want_mask=True))["mask"].any()
