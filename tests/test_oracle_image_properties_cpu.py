@@ -65,6 +65,13 @@ def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method,
         up = _ecef(o["lat"][line], o["lon"][line], o["hgt"][line] + 1.0, sc.a, sc.e2) - P[line]
         cosi = np.abs(np.sum(-d * up, axis=1)) / r
         assert np.abs(np.degrees(np.arccos(np.clip(cosi, -1, 1))) - o["los"][line, 0]).max() < 2e-5
+        # los channel 2: direction of the target -> platform vector in the local horizontal plane, from North, anticlockwise
+        la, lo = np.radians(o["lat"][line]), np.radians(o["lon"][line])
+        east = np.stack([-np.sin(lo), np.cos(lo), 0 * lo], -1)
+        north = np.stack([-np.sin(la) * np.cos(lo), -np.sin(la) * np.sin(lo), np.cos(la)], -1)
+        az = np.degrees(np.arctan2(-np.sum(d * north, 1), -np.sum(d * east, 1)) - 0.5 * np.pi)
+        dz = np.abs(az - o["los"][line, 1])
+        assert np.minimum(dz, np.abs(dz - 360.0)).max() < 2e-5
     # (4): plain bilinear DEM at the pixel's own position against its height; the iteration stops at 0.05 m in slant range
     y = (o["lat"] - sc.first_lat) / sc.delta_lat
     x = (o["lon"] - sc.first_lon) / sc.delta_lon
