@@ -189,3 +189,44 @@ def test_layover_bit_against_an_independent_reconstruction():
         union += int((lay[inner] | ref[inner]).sum())
         n_ref += int(ref[inner].sum())
     assert n_ref > 1000 and inter / union > 0.9, (n_ref, inter / union)
+
+
+def test_geo2rdr_on_a_secondary_orbit_against_an_independent_root_finder():
+    """configs[1]: offsets against a perturbed secondary orbit.  For sampled pixels the zero-Doppler time is found again by
+    bracketing + bisection on (P - S(t)) . V(t) = 0 (no Newton step, no derivative), the range from the interpolated state
+    at that time; the oracle's azimuth time must agree to 1e-8 s and its range to 1e-5 m (1e-3 px = 2e-6 s / 2.3e-3 m)."""
+    sc = synth.make_scene(40, 2048)
+    o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method="BILINEAR", want_mask=False))
+    sec = synth.config_c1_secondary(length=sc.length, width=sc.width)
+    kw = pu.secondary_kwargs(sc, sec, recenter=0.37)
+    g = orc.geo2rdr(lat=o["lat"], lon=o["lon"], hgt=o["hgt"], **kw)
+    orb = orc.Orbit(sec.orbit_t, sec.orbit_pos, sec.orbit_vel)
+    P = _ecef(o["lat"], o["lon"], o["hgt"], sc.a, sc.e2)
+
+    def f(t, p):
+        _, S, V = orb.interp(t, "HERMITE")
+        return float((p - S) @ V)
+
+    rng = np.random.default_rng(11)
+    checked = 0
+    for line, pix in zip(rng.integers(0, sc.length, 120), rng.integers(0, sc.width, 120)):
+        if g["azt"][line, pix] == -999999.0:
+            continue
+        p = P[line, pix]
+        lo, hi = g["azt"][line, pix] - 0.5, g["azt"][line, pix] + 0.5
+        assert f(lo, p) > 0 > f(hi, p)  # the satellite approaches, then recedes
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if f(mid, p) > 0:
+                lo = mid
+            else:
+                hi = mid
+        t = 0.5 * (lo + hi)
+        _, S, _ = orb.interp(t, "HERMITE")
+        assert abs(t - g["azt"][line, pix]) < 1e-8, (line, pix, t - g["azt"][line, pix])
+        assert abs(np.linalg.norm(p - S) - g["rgm"][line, pix]) < 1e-5
+        # offsets are relative to the 0-based line / sample (geo2rdr.f90:374-375)
+        assert abs((t - kw["t0"]) * kw["prf"] - line - g["azoff"][line, pix]) < 1e-4
+        assert abs((np.linalg.norm(p - S) - kw["r0"]) / kw["dr"] - pix - g["rgoff"][line, pix]) < 1e-4
+        checked += 1
+    assert checked > 80
