@@ -230,3 +230,26 @@ def test_geo2rdr_on_a_secondary_orbit_against_an_independent_root_finder():
         assert abs((np.linalg.norm(p - S) - kw["r0"]) / kw["dr"] - pix - g["rgoff"][line, pix]) < 1e-4
         checked += 1
     assert checked > 80
+
+
+def test_dem_interpolators_against_independent_implementations():
+    """BIQUINTIC (spline.f:15-117 as called at topozeroMethods.f:196) is a separable natural cubic spline over the 6 x 6
+    window floor-1 .. floor+4 evaluated between its 2nd and 3rd node: scipy's CubicSpline(bc_type='natural') gives the
+    same float32 value on every draw.  BILINEAR against the textbook formula, NEAREST against rounding; outside their
+    windows all return -1000 (topozeroMethods.f:112)."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(0)
+    dem = (rng.normal(size=(40, 50)) * 100).astype(np.float32)
+    for _ in range(1500):
+        ix, iy = int(rng.integers(3, 47)), int(rng.integers(3, 37))  # 1-based cell indices
+        fx, fy = rng.random(2)
+        rows = [CubicSpline(np.arange(6), dem[r, ix - 2:ix + 4].astype(np.float64), bc_type="natural")(1.0 + fx)
+                for r in range(iy - 2, iy + 4)]
+        want = np.float32(CubicSpline(np.arange(6), np.array(rows), bc_type="natural")(1.0 + fy))
+        assert orc.interp_dem("BIQUINTIC", dem, ix, iy, fx, fy) == want
+        d = dem.astype(np.float64)
+        bl = ((1 - fy) * ((1 - fx) * d[iy - 1, ix - 1] + fx * d[iy - 1, ix]) + fy * ((1 - fx) * d[iy, ix - 1] + fx * d[iy, ix]))
+        assert abs(orc.interp_dem("BILINEAR", dem, ix, iy, fx, fy) - bl) <= 2e-5 * max(1.0, abs(bl))
+        assert orc.interp_dem("NEAREST", dem, ix, iy, fx, fy) == dem[iy - 1 + int(round(fy)), ix - 1 + int(round(fx))]
+    for method, bad in (("BIQUINTIC", (2, 10)), ("BIQUINTIC", (48, 10)), ("BILINEAR", (50, 10)), ("BILINEAR", (0, 10))):
+        assert orc.interp_dem(method, dem, bad[0], bad[1], 0.5, 0.5) == -1000.0
