@@ -32,10 +32,15 @@ def _bilinear(dem, y, x):
     return ((1 - fy) * (1 - fx) * d[iy, ix] + (1 - fy) * fx * d[iy, ix + 1] + fy * (1 - fx) * d[iy + 1, ix] + fy * fx * d[iy + 1, ix + 1])
 
 
-@pytest.mark.parametrize("sensor,orbit_method,dem_method", [("s1", "HERMITE", "BILINEAR"), ("s1", "HERMITE", "BIQUINTIC"),
-                                                            ("nisar", "LEGENDRE", "BICUBIC")])
-def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method, dem_method):
+@pytest.mark.parametrize("sensor,orbit_method,dem_method,dop2d", [
+    ("s1", "HERMITE", "BILINEAR", None), ("s1", "HERMITE", "BIQUINTIC", None), ("nisar", "LEGENDRE", "BICUBIC", None),
+    ("s1", "SCH", "BILINEAR", None),
+    # azimuth-varying (2-D) Doppler, Hz against (line, range pixel): Topozero.py:305-334
+    ("s1", "HERMITE", "BILINEAR", [[40.0, 1.0e-2, -2.0e-7], [0.8, 1.0e-5, 0.0]])])
+def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method, dem_method, dop2d):
     sc = synth.make_scene(20, 1536, sensor=sensor)  # ordinary terrain: (nearly) every pixel converges
+    if dop2d is not None:
+        sc.doppler_coeffs = dop2d
     o = orc.topo(**orc.scene_topo_kwargs(sc, dem_method=dem_method, orbit_method=orbit_method, want_mask=False))
     # (1)-(3), (5), (6) hold for every pixel whether or not its iteration met the threshold: the final pass always puts
     # the point on the pixel's range sphere and Doppler cone (topozero.f90:618-644); (4) is a statement about converged ones
@@ -78,7 +83,9 @@ def test_every_pixel_satisfies_the_range_doppler_equations(sensor, orbit_method,
     dh = np.abs(_bilinear(sc.dem, y, x) - o["hgt"])
     tol = 0.2 if dem_method == "BILINEAR" else 1.5  # the other interpolators differ from bilinear by their own overshoot
     assert np.quantile(dh, 0.999) < tol, np.quantile(dh, 0.999)
-    # (5)
+    # (5) -- geo2rdr knows the Doppler as a function of range only (Geo2rdr.py:264-270)
+    if dop2d is not None:
+        return
     g = orc.geo2rdr(lat=o["lat"], lon=o["lon"], hgt=o["hgt"], orbit_t=sc.orbit_t, orbit_pos=sc.orbit_pos, orbit_vel=sc.orbit_vel,
                     length=sc.length, width=sc.width, r0=sc.r0, dr=sc.dr, prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side,
                     orbit_method=orbit_method,
@@ -200,6 +207,7 @@ def test_geo2rdr_on_a_secondary_orbit_against_an_independent_root_finder():
     sec = synth.config_c1_secondary(length=sc.length, width=sc.width)
     kw = pu.secondary_kwargs(sc, sec, recenter=0.37)
     g = orc.geo2rdr(lat=o["lat"], lon=o["lon"], hgt=o["hgt"], **kw)
+    gb = orc.geo2rdr(lat=o["lat"], lon=o["lon"], hgt=o["hgt"], bistatic=True, **kw)
     orb = orc.Orbit(sec.orbit_t, sec.orbit_pos, sec.orbit_vel)
     P = _ecef(o["lat"], o["lon"], o["hgt"], sc.a, sc.e2)
 
@@ -228,6 +236,12 @@ def test_geo2rdr_on_a_secondary_orbit_against_an_independent_root_finder():
         # offsets are relative to the 0-based line / sample (geo2rdr.f90:374-375)
         assert abs((t - kw["t0"]) * kw["prf"] - line - g["azoff"][line, pix]) < 1e-4
         assert abs((np.linalg.norm(p - S) - kw["r0"]) / kw["dr"] - pix - g["rgoff"][line, pix]) < 1e-4
+        # bistatic delay correction (geo2rdr.f90:331-368): the echo is attributed to the time shifted by the two-way
+        # travel time, the range is that of the state interpolated there
+        if gb["azt"][line, pix] != -999999.0:
+            tb = t + 2.0 * np.linalg.norm(p - S) / 299792458.0
+            _, Sb, _ = orb.interp(tb, "HERMITE")
+            assert abs(tb - gb["azt"][line, pix]) < 1e-8 and abs(np.linalg.norm(p - Sb) - gb["rgm"][line, pix]) < 1e-5
         checked += 1
     assert checked > 80
 
