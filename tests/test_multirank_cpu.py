@@ -79,7 +79,7 @@ from tests import fake_capi_for_bench as fake
 sys.modules["isce2_b200._capi"] = fake
 isce2_b200._capi = fake
 import bench
-sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--workload", "c0c1", "--lines", "37", "--e2e-steps", "2",
+sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--workload", {workload!r}, "--lines", "37", "--e2e-steps", "2",
             "--no-cpu-baseline", "--max-seconds", "200"]
 bench.main()
 '''
@@ -91,7 +91,7 @@ def test_bench_control_flow_world2_with_a_stand_in_library(tmp_path):
     library): every rank reaches every barrier / reduction, also when the two end-to-end arms of a rank that does not
     start at line 0 differ in the last bits; rank 0 alone prints the JSON line, with the contract's keys."""
     script = tmp_path / "bench_worker.py"
-    script.write_text(BENCH_WORKER.format(root=ROOT))
+    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c0c1"))
     p = _torchrun([str(script)], timeout=300)
     assert p.returncode == 0, p.stderr[-3000:]
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
@@ -106,3 +106,15 @@ def test_bench_control_flow_world2_with_a_stand_in_library(tmp_path):
     assert v["compared"] and v["validity_equal"] and v["max_abs_offset_diff_px"] < 1e-3
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in d["roofline"], k
+
+
+@pytest.mark.timeout(400)
+def test_stack_batch_control_flow_world2_with_a_stand_in_library(tmp_path):
+    """configs[4] (29 secondary orbits dealt round-robin to the ranks) through the same stand-in: one JSON line, from rank 0."""
+    script = tmp_path / "bench_worker_c4.py"
+    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c4"))
+    p = _torchrun([str(script)], timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and lines[0]["config"]["jobs_on_rank0"] == 15
+    assert lines[0]["metric"].startswith("geo2rdr Mpixels/s") and lines[0]["value"] > 0
