@@ -3,8 +3,6 @@
 world_size 2 on a machine without GPUs.  It computes nothing real: layers and offsets are cheap closed-form functions of
 the pixel index, written so that -- like on the device -- a block described with a re-based sensing start differs from
 the absolute description in the last bits only.  Never imported by the product or by bench.py."""
-import ctypes as C
-
 import numpy as np
 
 from isce2_b200 import _capi as real
@@ -98,7 +96,6 @@ class GeoPlan:
 
     def execute(self, params, t, pos, vel, want=("azoff", "rgoff"), **kw):
         n, w = self.topo.layers["lat"].shape
-        p = C.pointer(params).contents
         out = dict(azoff=np.empty((n, w), np.float32), rgoff=np.empty((n, w), np.float32))
         q = real.GeoParams.from_buffer_copy(params)
         q.line0, q.nlines = max(self.topo.params.line0, 0), n
