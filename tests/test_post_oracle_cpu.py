@@ -136,3 +136,64 @@ def test_looks_component_with_fewer_lines_than_looks_writes_an_empty_raster(tmp_
     assert os.path.exists(tmp_path / "ml" / "hgt.rdr.xml")
     # geo-referenced images: delta scales with the looks, start moves to the centre of the first look (Looks.py:49-55)
     assert o.coord1.coordDelta == 4.0 and o.coord1.coordStart == 101.0
+
+
+def test_multilook_and_water_mask_host_logic_with_the_oracle_standing_in(tmp_path, monkeypatch):
+    """File handling of the host mirrors (names, XML / VRT, .full copies, layouts, data types) without a device: for this
+    test only, the two library calls are replaced by the oracle restatements."""
+    from isce2_b200 import image as IF, looks as LK, watermask as WM
+
+    def fake_looks(image, ld, la, *, scheme="BIL", method="AVERAGE", out=None, device=0):
+        return orc.looks(np.asarray(image), ld, la, scheme=scheme, method=method), dict(ms_kernels=0.0, ms_total=0.0, gpu_launches=1)
+
+    def fake_mask(mask, lat0, dlat, lon0, dlon, lat, lon, *, out=None, device=0):
+        return orc.mask_to_radar(np.asarray(mask), lat0, dlat, lon0, dlon, lat, lon), dict(ms_kernels=0.0, ms_total=0.0, gpu_launches=1)
+
+    monkeypatch.setattr(_capi, "looks_run", fake_looks)
+    monkeypatch.setattr(_capi, "mask_to_radar_run", fake_mask)
+    rng = np.random.default_rng(4)
+    L, W = 23, 31
+    geom = tmp_path / "geom_full"
+    geom.mkdir()
+    layers = {"hgt": (rng.normal(size=(L, W)) * 100, "DOUBLE", 1), "lat": (35.0 - 1e-3 * rng.random((L, W)), "DOUBLE", 1),
+              "lon": (-118.0 + 1e-3 * rng.random((L, W)), "DOUBLE", 1), "los": (rng.normal(size=(L, 2, W)).astype(np.float32), "FLOAT", 2),
+              "shadowMask": (rng.integers(0, 4, (L, W)).astype(np.int8), "BYTE", 1)}
+    for name, (arr, dt, bands) in layers.items():
+        arr.tofile(geom / (name + ".rdr"))
+        im = IF.createImage()
+        im.initImage(str(geom / (name + ".rdr")), "read", W, dt, bands=bands, scheme="BIL")
+        im.setLength(L)
+        im.renderHdr()
+        im.renderVRT()
+    # water mask: geocoded BYTE raster + header with its geographic coordinates
+    wb = rng.integers(-1, 1, (40, 50)).astype(np.int8)
+    wb.tofile(tmp_path / "swbd.wbd")
+    wim = IF.createImage()
+    wim.initImage(str(tmp_path / "swbd.wbd"), "read", 50, "BYTE")
+    wim.setLength(40)
+    wim.coord1.coordStart, wim.coord1.coordDelta, wim.coord1.coordSize = -118.0, 2.5e-5, 50
+    wim.coord2.coordStart, wim.coord2.coordDelta, wim.coord2.coordSize = 35.0, -2.5e-5, 40
+    wim.renderHdr()
+    rdr = WM.geo2radar(str(tmp_path / "swbd.wbd"), str(geom / "waterMask.rdr"), str(geom / "lat.rdr"), str(geom / "lon.rdr"))
+    assert rdr == str(geom / "waterMask.rdr")
+    wm = np.fromfile(geom / "waterMask.rdr", np.int8).reshape(L, W)
+    assert np.array_equal(wm, orc.mask_to_radar(wb, 35.0, -2.5e-5, -118.0, 2.5e-5, layers["lat"][0], layers["lon"][0]))
+    h = IF.createImage().load(str(geom / "waterMask.rdr.xml"))
+    assert (h.dataType, h.width, h.length) == ("BYTE", W, L)
+    IF.createImage().load(str(geom / "waterMask.rdr.xml")).renderVRT()  # runMultilook only takes layers that have all three files
+
+    for method, omethod in (("isce", "AVERAGE"), ("gdal", "NEAREST")):
+        out_dir = tmp_path / ("geom_" + method)
+        assert LK.runMultilook(str(geom), str(out_dir), 4, 3, method=method) == str(out_dir)
+        for name, (arr, dt, bands) in list(layers.items()) + [("waterMask", (wm, "BYTE", 1))]:
+            want = orc.looks(arr, 4, 3, scheme="BIL", method=omethod)
+            got = np.fromfile(out_dir / (name + ".rdr"), arr.dtype).reshape(want.shape)
+            assert np.array_equal(got, want), (method, name)
+            hh = IF.createImage().load(str(out_dir / (name + ".rdr.xml")))
+            src_scheme = IF.createImage().load(str(geom / (name + ".rdr.xml"))).scheme  # the output keeps the input's interleaving
+            assert (hh.width, hh.length, hh.bands, hh.dataType, hh.scheme) == (W // 3, L // 4, bands, dt, src_scheme)
+            for ext in (".rdr.vrt", ".rdr.full.xml", ".rdr.full.vrt"):
+                assert (out_dir / (name + ext)).exists(), (name, ext)
+        assert not (out_dir / "incLocal.rdr").exists()  # absent inputs are skipped (topo.py:381)
+    with pytest.raises(ValueError):
+        LK.runMultilook(str(geom), str(tmp_path / "x"), 2, 2, method="bogus")
