@@ -267,3 +267,30 @@ def test_dem_interpolators_against_independent_implementations():
         assert orc.interp_dem("NEAREST", dem, ix, iy, fx, fy) == dem[iy - 1 + int(round(fy)), ix - 1 + int(round(fx))]
     for method, bad in (("BIQUINTIC", (2, 10)), ("BIQUINTIC", (48, 10)), ("BILINEAR", (50, 10)), ("BILINEAR", (0, 10))):
         assert orc.interp_dem(method, dem, bad[0], bad[1], 0.5, 0.5) == -1000.0
+
+
+def test_polynomial_reproduction_of_the_six_dem_interpolators_as_written():
+    """What each interpolator of the reference does to constants and planes (the restatement keeps every quirk, DESIGN
+    section 8): constants come back exactly from all but SINC (its eight-tap table is not renormalised per phase: ~0.6 %
+    ripple); planes come back to float32 rounding from BILINEAR, AKIMA and BIQUINTIC and, along x only, from BICUBIC, whose
+    dzdy column typo (uniform_interp.f90:152-154) shows as an error proportional to the y slope; NEAREST and the
+    one-cell-shifted SINC do not reproduce planes."""
+    ny, nx = 40, 50
+    yy, xx = np.mgrid[0:ny, 0:nx].astype(np.float64)
+    rng = np.random.default_rng(1)
+    pts = [(int(rng.integers(6, nx - 6)), int(rng.integers(6, ny - 6)), rng.random(), rng.random()) for _ in range(200)]
+
+    def worst(method, field, truth):
+        dem = field.astype(np.float32)
+        return max(abs(orc.interp_dem(method, dem, ix, iy, fx, fy) - truth(ix - 1 + fx, iy - 1 + fy)) for ix, iy, fx, fy in pts)
+
+    const = (np.full((ny, nx), 123.5), lambda x, y: 123.5)
+    lin_x = (10 + 2.0 * xx, lambda x, y: 10 + 2 * x)
+    lin_y = (10 - 3.0 * yy, lambda x, y: 10 - 3 * y)
+    for m in ("BILINEAR", "BICUBIC", "NEAREST", "AKIMA", "BIQUINTIC"):
+        assert worst(m, *const) == 0.0, m
+    assert 0.1 < worst("SINC", *const) < 1.5
+    for m in ("BILINEAR", "AKIMA", "BIQUINTIC"):
+        assert worst(m, *lin_x) < 1e-5 and worst(m, *lin_y) < 1e-5, m
+    assert worst("BICUBIC", *lin_x) < 1e-5 and 0.05 < worst("BICUBIC", *lin_y) < 0.5
+    assert worst("NEAREST", *lin_x) > 0.5 and worst("SINC", *lin_x) > 0.5
