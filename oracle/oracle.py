@@ -14,6 +14,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libzerodop_oracle.so")
 REF_LIB_PATH = os.path.join(HERE, "_ref", "libisce2_c_ref.so")
+# the reference's C++ restatements of the path, compiled unchanged (oracle/Makefile target ref; doors in ref_cpp.py)
+REF_CPP_LIBS = {k: os.path.join(HERE, "_ref", f"libisce2_cpp{k}_ref.so") for k in ("topo", "geo", "resamp")}
 
 DEM_METHODS = {"SINC": 0, "BILINEAR": 1, "BICUBIC": 2, "NEAREST": 3, "AKIMA": 4, "BIQUINTIC": 5}
 ORBIT_METHODS = {"HERMITE": 0, "SCH": 1, "LEGENDRE": 2}
@@ -92,7 +94,8 @@ def build(force=False):
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src)
     if force or stale:
         subprocess.check_call(["make", "-C", HERE, "libzerodop_oracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_LIB_PATH)):
+    ref_libs = [REF_LIB_PATH] + list(REF_CPP_LIBS.values())
+    if os.path.isdir("/root/reference") and (force or not all(os.path.exists(q) for q in ref_libs)):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -126,6 +129,10 @@ def lib():
         L.orc_eval_poly1d.argtypes = [C.POINTER(OrcPoly1d), C.c_double]
         L.orc_interp_dem.restype = C.c_float
         L.orc_interp_dem.argtypes = [C.c_int, _fp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        _ip = C.POINTER(C.c_int)
+        L.orc_interp_dem_batch.argtypes = [C.c_int, _fp, C.c_int, C.c_int, C.c_long, _ip, _ip, _dp, _dp, _fp]
+        L.orc_test_set_cpp_quirks.argtypes = [C.c_int]
+        L.orc_sinc_table.argtypes = [_fp]
         L.orc_insertion_sort.argtypes = [_dp, _dp, _dp, C.c_int]
         L.orc_binarysearch.restype = C.c_int
         L.orc_binarysearch.argtypes = [_dp, C.c_int, C.c_double]
@@ -213,6 +220,31 @@ def interp_dem(method, dem, ix, iy, fx, fy):
     dem = np.ascontiguousarray(dem, np.float32)
     ny, nx = dem.shape
     return float(lib().orc_interp_dem(DEM_METHODS[method.upper()], _f(dem), int(ix), int(iy), float(fx), float(fy), nx, ny))
+
+
+def interp_dem_batch(method, dem, ix, iy, fx, fy, cpp_quirks=0):
+    """orc_interp_dem over arrays.  cpp_quirks: test hook of tests/test_oracle_cpp_pins.py (see zerodop_oracle.c)."""
+    dem = np.ascontiguousarray(dem, np.float32)
+    ny, nx = dem.shape
+    ix = np.ascontiguousarray(ix, np.int32)
+    iy = np.ascontiguousarray(iy, np.int32)
+    fx = np.ascontiguousarray(fx, np.float64)
+    fy = np.ascontiguousarray(fy, np.float64)
+    out = np.empty(ix.size, np.float32)
+    ip = C.POINTER(C.c_int)
+    lib().orc_test_set_cpp_quirks(int(cpp_quirks))
+    try:
+        lib().orc_interp_dem_batch(DEM_METHODS[method.upper()], _f(dem), nx, ny, ix.size, ix.ctypes.data_as(ip),
+                                   iy.ctypes.data_as(ip), _d(fx), _d(fy), _f(out))
+    finally:
+        lib().orc_test_set_cpp_quirks(0)
+    return out
+
+
+def sinc_table():
+    out = np.empty(8192 * 8, np.float32)
+    lib().orc_sinc_table(_f(out))
+    return out
 
 
 def topo(*, dem, first_lat, first_lon, delta_lat, delta_lon, orbit_t, orbit_pos, orbit_vel, length, width,

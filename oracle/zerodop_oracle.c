@@ -507,6 +507,7 @@ static float interp2dspline(int order, const float *dem, int nx /*lon count*/, i
 #define SINC_SUB 8192
 #define SINC_LEN 8
 static float *g_fintp = NULL;
+static int g_sinc_cpp_arith;
 static const float *sinc_table(void)
 {
 #pragma omp critical(orc_sinc_table)
@@ -549,6 +550,10 @@ static float sinc_eval_2d_f(const float *dem, const float *intarr, int idec, int
             for (int m = 0; m < ilen; m++) {
                 /* arrin(intpx-k, intpy-m) is 0-based: dem element (intpx-k+1, intpy-m+1) in 1-based terms */
                 float a = DEM(intpx - k + 1, intpy - m + 1);
+                if (g_sinc_cpp_arith) { /* test hook, see g_akima_cpp_quirks */
+                    acc = (float)(acc + (a * (double)intarr[k + ifracx * ilen] * (double)intarr[m + ifracy * ilen]));
+                    continue;
+                }
                 float t = a * intarr[k + ifracx * ilen];
                 t = t * intarr[m + ifracy * ilen];
                 acc = acc + t;
@@ -563,7 +568,17 @@ static float sinc_eval_2d_f(const float *dem, const float *intarr, int idec, int
  * (ix..ix+1, iy..iy+1) (getParDer :70-73 vs polyfitAkima :166-169) and (b) wx2/wx3/wy2/wy3 keeping their value from
  * the previous grid point when the "equal slopes" branch is taken (:81-86, :95-100; the Fortran leaves them
  * unassigned there -- they are initialised to 0 here, which the subsequent guard turns into 1). */
-static int aki_almost_equal(double x, double y) { return fabs(x - y) <= 2.220446049250313e-16; }
+/* TEST HOOK (tests/test_oracle_cpp_pins.py only): when set, the two places where the reference's C++ restatement
+ * (components/zerodop/GPUtopozero/src/AkimaLib.cpp) departs from akima_reg.F are reproduced, so that every OTHER line of
+ * this function can be held bit for bit against that reference-authored code: (1) AkimaLib.cpp:70-76 stores the Y slope
+ * into slpx and leaves slpy zero (akima_reg.F:95-100 stores slpy); (2) Constants.h:13 declares AKI_EPS as an int, i.e. 0
+ * (akima_reg.F:12 epsilon(1.0d0)). */
+static int g_akima_cpp_quirks = 0;
+/* (3) UniformInterp.cpp:186 forms each sinc term in double and rounds the running sum to float once per tap
+ * (uniform_interp.f90:424-425 multiplies and adds in real*4). */
+static int g_sinc_cpp_arith = 0;
+void orc_test_set_cpp_quirks(int on) { g_akima_cpp_quirks = on & 1; g_sinc_cpp_arith = (on >> 1) & 1; }
+static int aki_almost_equal(double x, double y) { return fabs(x - y) <= (g_akima_cpp_quirks ? 0.0 : 2.220446049250313e-16); }
 static double akima_eval(const float *dem, int nx, int ny, int ix, int iy, double fx, double fy)
 {
     double sx[2][2], sy[2][2], sxy[2][2]; /* [jj][ii] */
@@ -594,6 +609,7 @@ static double akima_eval(const float *dem, int nx, int ny, int ix, int iy, doubl
                 wy3 = fabs(m2 - m1);
                 sy[jj - 1][ii - 1] = (wy2 * m2 + wy3 * m3) / (wy2 + wy3);
             }
+            if (g_akima_cpp_quirks) { sx[jj - 1][ii - 1] = sy[jj - 1][ii - 1]; sy[jj - 1][ii - 1] = 0.0; }
             /* cross derivative: m2, m3 below are the Y slopes just computed (the Fortran reuses the variables) */
             double d22, d23, d42, d43;
             f = DEM(xx - 1, yy) - DEM(xx - 1, yy - 1); d22 = f;
@@ -665,6 +681,13 @@ float orc_interp_dem(int method, const float *dem, int i_x, int i_y, double f_x,
     default:
         return NAN;
     }
+}
+
+/* many points at once (the pins against the reference's C++ run over > 1e6 draws) */
+void orc_interp_dem_batch(int method, const float *dem, int nx, int ny, long n, const int *ix, const int *iy,
+                          const double *fx, const double *fy, float *out)
+{
+    for (long k = 0; k < n; k++) out[k] = orc_interp_dem(method, dem, ix[k], iy[k], fx[k], fy[k], nx, ny);
 }
 
 /* ------------------------------------------------------------------ */
