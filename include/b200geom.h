@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B200GEOM_ABI_VERSION 5
+#define B200GEOM_ABI_VERSION 6
 
 enum {
     B200_OK = 0,
@@ -407,6 +407,15 @@ int b200_device_name(int device, char *buf, size_t len); /* e.g. "NVIDIA B200" *
 void b200_release_cached_memory(void);
 void *b200_alloc_pinned(size_t bytes);                   /* page-locked host memory (fast H2D/D2H); NULL on failure */
 void b200_free_pinned(void *p);
+/* Host buffers handed to any entry point may be page-locked (b200_alloc_pinned, cudaHostRegister: copied by DMA at PCIe
+ * speed) or ordinary pageable memory such as a numpy.memmap over the raster being written -- what the reference's
+ * callers have (Topozero.py:274-302, Geo2rdr.py:321-384).  Results bound for pageable memory are bounced through a
+ * page-locked ring and copied out by a pool of B200_COPY_THREADS host threads (environment; default half the host
+ * threads, at most 8; 0 = plain cudaMemcpy), so that the page faults of a file that does not exist yet are paid in
+ * parallel with the DMA instead of by one thread. */
+/* device -> page-locked host copy of `bytes` (chunks of chunk_bytes, one stream), timed with CUDA events: the floor of
+ * an end-to-end call that has to deliver that many bytes of results.  host must hold `bytes`. */
+int b200_d2h_floor(int device, void *host, size_t bytes, size_t chunk_bytes, float *ms, char *err, size_t errlen);
 /* DFMA-saturating microbenchmark: measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per FMA) */
 int b200_fp64_peak(int device, double *tflops, char *err, size_t errlen);
 /* single-point primitives evaluated ON THE DEVICE (one thread), for known-answer tests of the device math:

@@ -138,7 +138,8 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_fp64_peak", "b200_device_primitive", "b200_geozero_grid", "b200_geozero_plan_create",
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
            "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
-           "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks", "b200_geo_plan_freeze_geometry"]
+           "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks", "b200_geo_plan_freeze_geometry",
+           "b200_d2h_floor"]
 
 _lib = None
 
@@ -182,6 +183,7 @@ def lib():
     L.b200_free_pinned.argtypes = [C.c_void_p]
     L.b200_free_pinned.restype = None
     L.b200_fp64_peak.argtypes = [C.c_int, _dp] + err
+    L.b200_d2h_floor.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, _fp] + err
     L.b200_device_primitive.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Orbit), _dp, _dp] + err
     L.b200_geozero_grid.argtypes = [C.POINTER(GeozeroParams), C.POINTER(C.c_int), C.POINTER(C.c_int)] + err
     L.b200_geozero_plan_create.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d),
@@ -230,6 +232,19 @@ def fp64_peak(device=0):
     e = _errbuf()
     _check(lib().b200_fp64_peak(device, C.byref(v), e, 512), e)
     return v.value
+
+
+def d2h_floor(host, nbytes=None, chunk_bytes=0, device=0):
+    """Milliseconds (CUDA events) of a device -> host copy of nbytes into the page-locked array `host`: the floor of
+    any call that has to deliver that many bytes of results over PCIe."""
+    host = np.asarray(host)
+    nbytes = host.nbytes if nbytes is None else int(nbytes)
+    if nbytes > host.nbytes:
+        raise ValueError("host buffer is smaller than the requested copy")
+    ms = C.c_float()
+    e = _errbuf()
+    _check(lib().b200_d2h_floor(device, host.ctypes.data_as(C.c_void_p), nbytes, int(chunk_bytes), C.byref(ms), e, 512), e)
+    return float(ms.value)
 
 
 def pinned_empty(shape, dtype):
@@ -434,7 +449,10 @@ def _geo_out(params, want, out):
 
 
 def geo2rdr_run(params, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, doppler_coeffs=(0.0,), doppler_mean=0.0,
-                doppler_norm=1.0, want=_GEO_KEYS, out=None):
+                doppler_norm=1.0, want=_GEO_KEYS, out=None, block_rows=False):
+    """b200_geo2rdr_run.  lat / lon / hgt are the whole [dem_length][dem_width] images; with block_rows=True they hold
+    only the rows [line0, line0 + nlines) of the block (a rank of a sharded run that owns nothing else): the library
+    reads no other row, so the image base it is given is the block's address moved back by line0 rows."""
     L = lib()
     keep = _Keep()
     orb = make_orbit(keep, orbit_t, orbit_pos, orbit_vel)
@@ -442,7 +460,15 @@ def geo2rdr_run(params, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, doppler_co
     out, o = _geo_out(params, want, out)
     res = GeoResult()
     e = _errbuf()
-    _check(L.b200_geo2rdr_run(C.byref(params), keep.d(lat), keep.d(lon), keep.d(hgt), C.byref(orb), C.byref(dop),
+    ptrs = [keep.d(lat), keep.d(lon), keep.d(hgt)]
+    if block_rows:
+        n = params.dem_length - max(params.line0, 0) if params.nlines < 0 else params.nlines
+        for a in (lat, lon, hgt):
+            if a.shape != (n, params.dem_width):
+                raise ValueError(f"block_rows: expected the block's {n} x {params.dem_width} rows, got {a.shape}")
+        back = max(params.line0, 0) * params.dem_width * 8
+        ptrs = [C.cast(C.c_void_p(C.cast(q, C.c_void_p).value - back), _dp) for q in ptrs]
+    _check(L.b200_geo2rdr_run(C.byref(params), ptrs[0], ptrs[1], ptrs[2], C.byref(orb), C.byref(dop),
                               C.byref(o), C.byref(res), e, 512), e)
     out = dict(out)
     out.update(_result_dict(res))

@@ -7,15 +7,19 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "geo2rdr_kernels.cuh"
@@ -146,6 +150,225 @@ cudaError_t dmalloc(T **p, size_t bytes)
 {
     return dmalloc(reinterpret_cast<void **>(p), bytes);
 }
+
+
+// -------------------------------------------------------------------------------------------------
+// HostSink: device -> host copies of the output layers, whatever kind of host memory the caller handed over.
+//
+// Page-locked destinations (b200_alloc_pinned, cudaHostRegister) take the plain cudaMemcpyAsync path: the DMA engine
+// writes them directly, asynchronously, at PCIe speed.  PAGEABLE destinations -- what the reference's callers have: a
+// numpy.memmap over the .rdr / .off file being written (Topozero.py:274-302) -- would make cudaMemcpyAsync synchronous and
+// single threaded: the driver bounces every 64 KB through its own small staging buffer and one CPU thread pays all the
+// page faults of a file that does not exist yet.  For those the sink bounces through its own ring of page-locked slots
+// and a pool of copier threads that memcpy finished slots into the destination in parallel (page faults of a fresh
+// mapping included), while the DMA engine fills the next slots.  B200_COPY_THREADS (default: half the host threads, at
+// most 8) sizes the pool; B200_COPY_THREADS=0 disables the bounce path (plain cudaMemcpyAsync for everything).
+// -------------------------------------------------------------------------------------------------
+constexpr size_t kSinkSlotBytes = 32u << 20; // one bounce slot
+constexpr int kSinkSlots = 6;                // ring per sink: 192 MB page-locked, cached between calls
+
+struct SinkRing {
+    char *buf[kSinkSlots] = {};
+    cudaEvent_t ev[kSinkSlots] = {};
+    bool ok = false;
+};
+std::mutex g_ring_mu;
+std::vector<SinkRing *> g_free_rings; // rings of finished calls, handed to the next one (pinning 192 MB costs ~50 ms)
+
+SinkRing *ring_acquire()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        if (!g_free_rings.empty()) {
+            SinkRing *r = g_free_rings.back();
+            g_free_rings.pop_back();
+            return r;
+        }
+    }
+    SinkRing *r = new (std::nothrow) SinkRing;
+    if (!r) return nullptr;
+    r->ok = true;
+    for (int i = 0; i < kSinkSlots && r->ok; i++) {
+        r->ok = cudaHostAlloc((void **)&r->buf[i], kSinkSlotBytes, cudaHostAllocPortable) == cudaSuccess &&
+                cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!r->ok) {
+        cudaGetLastError();
+        for (int i = 0; i < kSinkSlots; i++) {
+            if (r->buf[i]) cudaFreeHost(r->buf[i]);
+            if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+        }
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+void ring_release(SinkRing *r)
+{
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    g_free_rings.push_back(r);
+}
+
+int sink_threads()
+{
+    static const int n = [] {
+        if (const char *e = getenv("B200_COPY_THREADS")) return atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
+        unsigned hc = std::thread::hardware_concurrency();
+        int t = (int)(hc / 2);
+        return t < 2 ? 2 : (t > 8 ? 8 : t);
+    }();
+    return n;
+}
+
+// process-wide pool of copier threads: a task is one memcpy of a part of a finished slot
+class CopyPool {
+  public:
+    struct Task {
+        cudaEvent_t ready;         // the slot's D2H has landed once this event completed
+        int device;
+        void *dst;
+        const void *src;
+        size_t bytes;
+        std::atomic<int> *pending; // per slot: parts still to copy; 0 == slot reusable
+        std::mutex *mu;            // owner's mutex / cv, signalled when pending reaches 0
+        std::condition_variable *cv;
+    };
+    static CopyPool &get()
+    {
+        static CopyPool *p = new CopyPool(sink_threads()); // leaked on purpose: threads may outlive static destructors
+        return *p;
+    }
+    void push(const Task &t)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(t);
+        }
+        cv_.notify_one();
+    }
+    int size() const { return n_; }
+
+  private:
+    explicit CopyPool(int n) : n_(n)
+    {
+        for (int i = 0; i < n; i++) std::thread([this] { run(); }).detach();
+    }
+    void run()
+    {
+        int cur = -1;
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return !q_.empty(); });
+                t = q_.front();
+                q_.pop_front();
+            }
+            if (cur != t.device) {
+                cudaSetDevice(t.device);
+                cur = t.device;
+            }
+            cudaEventSynchronize(t.ready);
+            memcpy(t.dst, t.src, t.bytes);
+            if (t.pending->fetch_sub(1) == 1) {
+                std::lock_guard<std::mutex> lk(*t.mu);
+                t.cv->notify_all();
+            }
+        }
+    }
+    int n_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Task> q_;
+};
+
+class HostSink {
+  public:
+    HostSink(cudaStream_t s, int device) : s_(s), device_(device) {}
+    ~HostSink()
+    {
+        finish();
+        if (ring_) ring_release(ring_);
+    }
+    // enqueue `bytes` from device memory `src` to host memory `dst` behind everything already on the stream
+    cudaError_t copy(void *dst, const void *src, size_t bytes)
+    {
+        if (!bytes) return cudaSuccess;
+        if (!pageable(dst)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_);
+        if (!ring_) {
+            ring_ = ring_acquire();
+            if (!ring_) { // no page-locked memory to bounce through: the driver's own path still works
+                bounce_failed_ = true;
+                return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_);
+            }
+            for (int i = 0; i < kSinkSlots; i++) pending_[i].store(0);
+        }
+        const int nt = CopyPool::get().size();
+        for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
+            const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
+            const int k = next_;
+            next_ = (next_ + 1) % kSinkSlots;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return pending_[k].load() == 0; });
+            }
+            cudaError_t e = cudaMemcpyAsync(ring_->buf[k], (const char *)src + o, n, cudaMemcpyDeviceToHost, s_);
+            if (e == cudaSuccess) e = cudaEventRecord(ring_->ev[k], s_);
+            if (e != cudaSuccess) return e;
+            // parts of >= 1 MB, page aligned within the slot, one per copier thread
+            size_t part = (n + nt - 1) / nt;
+            part = (part + 4095) & ~(size_t)4095;
+            if (part < (1u << 20)) part = 1u << 20;
+            const int nparts = (int)((n + part - 1) / part);
+            pending_[k].store(nparts);
+            for (int q = 0; q < nparts; q++) {
+                const size_t po = (size_t)q * part, pn = n - po < part ? n - po : part;
+                CopyPool::get().push(CopyPool::Task{ring_->ev[k], device_, (char *)dst + o + po, ring_->buf[k] + po, pn, &pending_[k],
+                                                    &mu_, &cv_});
+            }
+            bounced_ += n;
+        }
+        return cudaSuccess;
+    }
+    // all bounced bytes are in their destination (plain copies still need the caller's stream synchronize)
+    void finish()
+    {
+        if (!ring_) return;
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+            for (int i = 0; i < kSinkSlots; i++)
+                if (pending_[i].load() != 0) return false;
+            return true;
+        });
+    }
+    size_t bounced_bytes() const { return bounced_; }
+
+  private:
+    bool pageable(const void *p)
+    {
+        if (sink_threads() == 0 || bounce_failed_) return false;
+        if (p == last_ptr_) return last_pageable_; // the layers are asked about chunk after chunk
+        // same allocation as a pointer seen before?  cudaPointerGetAttributes costs ~1 us; there are <= 10 distinct buffers
+        cudaPointerAttributes a;
+        bool pg = false;
+        if (cudaPointerGetAttributes(&a, p) == cudaSuccess) pg = (a.type == cudaMemoryTypeUnregistered);
+        else cudaGetLastError();
+        last_ptr_ = p;
+        last_pageable_ = pg;
+        return pg;
+    }
+    cudaStream_t s_;
+    int device_;
+    SinkRing *ring_ = nullptr;
+    std::atomic<int> pending_[kSinkSlots];
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int next_ = 0;
+    size_t bounced_ = 0;
+    bool bounce_failed_ = false;
+    const void *last_ptr_ = nullptr;
+    bool last_pageable_ = false;
+};
 
 // lines per pipeline chunk: ~8 Mpixel, so that copies of one chunk overlap the kernels of the next
 int chunk_lines(int width, int nlines)
@@ -566,12 +789,14 @@ extern "C" int b200_topo_plan_fetch(b200_topo_plan *pl, const b200_topo_outputs 
     cudaStream_t s = pl->stream;
     const size_t npix = (size_t)pl->nlines * (size_t)pl->p.width;
     if (out) {
-        if (out->lat) CK(cudaMemcpyAsync(out->lat, pl->layers.lat, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
-        if (out->lon) CK(cudaMemcpyAsync(out->lon, pl->layers.lon, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
-        if (out->hgt) CK(cudaMemcpyAsync(out->hgt, pl->layers.hgt, sizeof(double) * npix, cudaMemcpyDeviceToHost, s));
-        if (out->los && pl->layers.los) CK(cudaMemcpyAsync(out->los, pl->layers.los, sizeof(float) * 2 * npix, cudaMemcpyDeviceToHost, s));
-        if (out->inc && pl->layers.inc) CK(cudaMemcpyAsync(out->inc, pl->layers.inc, sizeof(float) * 2 * npix, cudaMemcpyDeviceToHost, s));
-        if (out->mask && pl->layers.mask) CK(cudaMemcpyAsync(out->mask, pl->layers.mask, npix, cudaMemcpyDeviceToHost, s));
+        HostSink sink(s, pl->p.device);
+        if (out->lat) CK(sink.copy(out->lat, pl->layers.lat, sizeof(double) * npix));
+        if (out->lon) CK(sink.copy(out->lon, pl->layers.lon, sizeof(double) * npix));
+        if (out->hgt) CK(sink.copy(out->hgt, pl->layers.hgt, sizeof(double) * npix));
+        if (out->los && pl->layers.los) CK(sink.copy(out->los, pl->layers.los, sizeof(float) * 2 * npix));
+        if (out->inc && pl->layers.inc) CK(sink.copy(out->inc, pl->layers.inc, sizeof(float) * 2 * npix));
+        if (out->mask && pl->layers.mask) CK(sink.copy(out->mask, pl->layers.mask, npix));
+        sink.finish();
     }
     TopoStats st;
     CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
@@ -911,9 +1136,11 @@ extern "C" int b200_geo_plan_fetch(b200_geo_plan *pl, const b200_geo_outputs *ou
     cudaStream_t s = pl->stream;
     const size_t bytes = (size_t)pl->nlines * (size_t)pl->p.dem_width * (pl->out_f32 ? 4 : 8);
     if (out) {
+        HostSink sink(s, pl->p.device);
         void *h[4] = {out->azt, out->rgm, out->azoff, out->rgoff};
         for (int i = 0; i < 4; i++)
-            if (h[i] && pl->d_out[i]) CK(cudaMemcpyAsync(h[i], pl->d_out[i], bytes, cudaMemcpyDeviceToHost, s));
+            if (h[i] && pl->d_out[i]) CK(sink.copy(h[i], pl->d_out[i], bytes));
+        sink.finish();
     }
     GeoStats st;
     CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
@@ -976,6 +1203,7 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
     const size_t esz = p->out_f32 ? 4 : 8;
     void *hout[4] = {out->azt, out->rgm, out->azoff, out->rgoff};
     int launches = 1;
+    HostSink sink(st.d, p->device);
     for (int c0 = 0; c0 < pl->nlines; c0 += cl) {
         const int n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
         const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
@@ -1000,12 +1228,13 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
         CK(cudaStreamWaitEvent(st.d, ek, 0));
         for (int i = 0; i < 4; i++)
             if (hout[i] && pl->d_out[i])
-                CK(cudaMemcpyAsync((char *)hout[i] + o * esz, (char *)pl->d_out[i] + o * esz, cnt * esz, cudaMemcpyDeviceToHost, st.d));
+                CK(sink.copy((char *)hout[i] + o * esz, (char *)pl->d_out[i] + o * esz, cnt * esz));
     }
     CK(cudaEventRecord(pl->ev1, s));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     CK(cudaStreamSynchronize(st.d));
+    sink.finish();
     CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
     pl->launches = launches;
     pl->executed = true;
@@ -1144,23 +1373,20 @@ static int topo_run_impl(const b200_topo_params *p, const void *dem, int dem_dty
         }
         return cudaEventRecord(done, s) == cudaSuccess ? 0 : -1;
     };
+    HostSink sink(st.d, pl->p.device); // pageable destinations (numpy.memmap over the output files) are bounced in parallel
     auto copy_chunk = [&](int c0, int n, cudaEvent_t done) -> cudaError_t {
         const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
         cudaError_t e = cudaStreamWaitEvent(st.d, done, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lat + o, pl->layers.lat + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->lon + o, pl->layers.lon + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->hgt + o, pl->layers.hgt + o, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->los && pl->layers.los)
-            e = cudaMemcpyAsync(out->los + 2 * o, pl->layers.los + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->inc && pl->layers.inc)
-            e = cudaMemcpyAsync(out->inc + 2 * o, pl->layers.inc + 2 * o, sizeof(float) * 2 * cnt, cudaMemcpyDeviceToHost, st.d);
-        if (e == cudaSuccess && out->mask && pl->layers.mask)
-            e = cudaMemcpyAsync(out->mask + o, pl->layers.mask + o, cnt, cudaMemcpyDeviceToHost, st.d);
+        if (e == cudaSuccess) e = sink.copy(out->lat + o, pl->layers.lat + o, sizeof(double) * cnt);
+        if (e == cudaSuccess) e = sink.copy(out->lon + o, pl->layers.lon + o, sizeof(double) * cnt);
+        if (e == cudaSuccess) e = sink.copy(out->hgt + o, pl->layers.hgt + o, sizeof(double) * cnt);
+        if (e == cudaSuccess && out->los && pl->layers.los) e = sink.copy(out->los + 2 * o, pl->layers.los + 2 * o, sizeof(float) * 2 * cnt);
+        if (e == cudaSuccess && out->inc && pl->layers.inc) e = sink.copy(out->inc + 2 * o, pl->layers.inc + 2 * o, sizeof(float) * 2 * cnt);
+        if (e == cudaSuccess && out->mask && pl->layers.mask) e = sink.copy(out->mask + o, pl->layers.mask + o, cnt);
         for (Job &J : fused)
             for (int i = 0; i < 4; i++)
                 if (e == cudaSuccess && J.hout[i] && J.gp->d_out[i])
-                    e = cudaMemcpyAsync((char *)J.hout[i] + o * J.esz, (char *)J.gp->d_out[i] + o * J.esz, cnt * J.esz,
-                                        cudaMemcpyDeviceToHost, st.d);
+                    e = sink.copy((char *)J.hout[i] + o * J.esz, (char *)J.gp->d_out[i] + o * J.esz, cnt * J.esz);
         return e;
     };
     const int nchunks = (pl->nlines + cl - 1) / cl;
@@ -1181,6 +1407,7 @@ static int topo_run_impl(const b200_topo_params *p, const void *dem, int dem_dty
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
     CK(cudaStreamSynchronize(st.d));
+    sink.finish();
     CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
     pl->ms_pixels = pl->ms_solve = pl->ms_mask = 0.f; // not separable in the pipelined form
     pl->launches += launches;
@@ -2041,6 +2268,37 @@ extern "C" void *b200_alloc_pinned(size_t bytes)
 extern "C" void b200_free_pinned(void *p)
 {
     if (p) cudaFreeHost(p);
+}
+
+// Device -> page-locked host copy of `bytes` from a scratch device buffer, in chunks of chunk_bytes on one stream: the
+// floor of any end-to-end call that has to deliver that many bytes of results (bench.py runs it on all ranks at once)
+extern "C" int b200_d2h_floor(int device, void *host, size_t bytes, size_t chunk_bytes, float *ms, char *err, size_t errlen)
+{
+    int rc = select_device(device, err, errlen);
+    if (rc != B200_OK) return rc;
+    if (!host || !bytes || !ms) return fail(err, errlen, B200_EINVAL, "host buffer, size and result pointer are mandatory");
+    if (chunk_bytes == 0 || chunk_bytes > bytes) chunk_bytes = bytes;
+    if (chunk_bytes > ((size_t)1 << 30)) chunk_bytes = (size_t)1 << 30;
+    void *d = nullptr;
+    CK(dmalloc(&d, chunk_bytes));
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d, 0, chunk_bytes, s);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e0, s);
+    for (size_t o = 0; o < bytes && ce == cudaSuccess; o += chunk_bytes)
+        ce = cudaMemcpyAsync((char *)host + o, d, bytes - o < chunk_bytes ? bytes - o : chunk_bytes, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e1, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (s) cudaStreamDestroy(s);
+    dfree(d);
+    if (ce != cudaSuccess) return fail(err, errlen, B200_ECUDA, "device-to-host copy failed: %s", cudaGetErrorString(ce));
+    return B200_OK;
 }
 
 // DFMA-saturating microbenchmark: 8 independent FMA chains per thread

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/b200geom.h but not exported by libb200geom.so"
     assert sorted(_capi.EXPORTS) == declared
-    assert lib.b200_abi_version() == 5  # 2: geozero + resamp_slc; 3: fused topo+geo2rdr; 4: looks + mask projection; 5: frozen stack geometry
+    assert lib.b200_abi_version() == 6  # 2: geozero + resamp_slc; 3: fused topo+geo2rdr; 4: looks + mask projection; 5: frozen stack geometry; 6: d2h floor, pageable sinks
 
 
 def test_struct_layouts_match_header():

@@ -83,14 +83,53 @@ def test_c2_full_swath_round_trip_and_line_block_identity():
         assert [blk[k] for k in ("dem_x0", "dem_y0", "dem_nx", "dem_ny")] == [full[k] for k in ("dem_x0", "dem_y0", "dem_nx", "dem_ny")]
     assert conv == full["converged"] and iters == full["iterations"]
     assert bbox == [full["min_lat"], full["max_lat"], full["min_lon"], full["max_lon"]]
-    # ---- a strip of the full run against the oracle ----
-    a, nl = 9000, 6
-    c = pu.cpu_topo(sc, dem_method="BIQUINTIC", line0=a, nlines=nl)
-    strip = {k: (full[k][a:a + nl] if isinstance(full[k], np.ndarray) else full[k]) for k in full}
-    assert np.array_equal(strip["mask"], c["mask"])
-    assert np.abs(strip["hgt"] - c["hgt"]).max() < pu.TOL_HGT_M
-    assert (np.abs(strip["lat"] - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2 and np.abs(strip["lat"] - c["lat"]).max() < 2e-7
-    assert (np.abs(strip["lon"] - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= 2 and np.abs(strip["lon"] - c["lon"]).max() < 2e-7
+    # ---- strips of the full run against the oracle: first burst, across a burst boundary, last burst (258 lines) ----
+    tot = {}
+    for a, nl in ((0, 86), (1457, 86), (sc.length - 86, 86)):
+        c = pu.cpu_topo(sc, dem_method="BIQUINTIC", line0=a, nlines=nl)
+        strip = {k: (full[k][a:a + nl] if isinstance(full[k], np.ndarray) else full[k]) for k in full}
+        assert np.array_equal(strip["mask"], c["mask"])
+        _accumulate(tot, strip, c)
+    _report("c2_full_size_3_strips", tot)
+    _assert_strip_totals(tot)
+
+
+def _accumulate(tot, g, c):
+    """Differences of one strip, added to the running totals (pixels, pixels over tolerance, largest difference)."""
+    for k, tol in (("lat", pu.TOL_LATLON_DEG), ("lon", pu.TOL_LATLON_DEG), ("hgt", pu.TOL_HGT_M), ("los", pu.TOL_ANGLE_DEG),
+                   ("inc", pu.TOL_ANGLE_DEG)):
+        d = np.abs(g[k].astype(np.float64) - c[k].astype(np.float64))
+        if k == "los":
+            d = np.minimum(d, np.abs(d - 360.0))
+        t = tot.setdefault(k, dict(n=0, n_over=0, max=0.0, n_exact=0, tol=tol))
+        t["n"] += int(d.size)
+        t["n_over"] += int((d > tol).sum())
+        t["n_exact"] += int((d == 0).sum())
+        t["max"] = max(t["max"], float(d.max()))
+
+
+def _report(name, tot):
+    """Outliers per 1e9 values, printed and left in gpurun_out/ for the profile summary."""
+    import json
+    import os
+    rep = {k: dict(v, over_per_1e9=1e9 * v["n_over"] / v["n"], exact_fraction=v["n_exact"] / v["n"]) for k, v in tot.items()}
+    print(name, json.dumps(rep))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", f"parity_{name}.json"), "w") as f:
+            json.dump(rep, f, indent=1)
+    except OSError:
+        pass
+
+
+def _assert_strip_totals(tot):
+    # hgt within 1 cm everywhere; lat / lon / angles within tolerance except for the float32 DEM-index flips described in
+    # tests/test_gpu_parity.py, bounded by 5x the tolerance in lat / lon and counted per 1e9 values in the report
+    assert tot["hgt"]["n_over"] == 0, tot["hgt"]
+    for k in ("lat", "lon"):
+        assert tot[k]["n_over"] <= max(2, int(2e-5 * tot[k]["n"])) and tot[k]["max"] < 2e-7, (k, tot[k])
+    for k in ("los", "inc"):
+        assert tot[k]["n_over"] <= max(4, int(4e-5 * tot[k]["n"])) and tot[k]["max"] < 2e-2, (k, tot[k])
 
 
 def test_c3_nisar_frame_round_trip_at_full_size():
@@ -123,3 +162,29 @@ def test_c3_nisar_frame_round_trip_at_full_size():
     tp.close()
     assert res.converged > 0.999 * n and 3.0 < res.iterations / n < 12.0
     print("c3 topo device ms", ms)
+    # ---- a 64-line block from the middle of the full-size frame (global DEM crop, full-size geometry) against the oracle ----
+    a, nl = 30000, 64
+    p.line0, p.nlines = a, nl
+    blk = _capi.topo_run(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]], want_los=True,
+                         want_inc=True, want_mask=True)
+    c = pu.cpu_topo(sc, dem_method="BIQUINTIC", orbit_method="LEGENDRE", line0=a, nlines=nl)
+    assert np.array_equal(blk["mask"], c["mask"]) and blk["iterations"] == c["total_iters"]
+    assert [blk[k] for k in ("dem_x0", "dem_y0", "dem_nx", "dem_ny")] == [c[k] for k in ("ustartx", "ustarty", "udemwidth", "udemlength")]
+    tot = {}
+    _accumulate(tot, blk, c)
+    _report("c3_full_size_strip", tot)
+    _assert_strip_totals(tot)
+    kw = dict(orbit_t=sc.orbit_t, orbit_pos=sc.orbit_pos, orbit_vel=sc.orbit_vel, length=sc.length, width=sc.width, r0=sc.r0,
+              dr=sc.dr, prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side)
+    from oracle import oracle as orc
+    gblk = _capi.geo2rdr_run(_capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0, dr=sc.dr,
+                                              prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side, orbit_method="LEGENDRE", line0=a,
+                                              nlines=nl), c["lat"], c["lon"], c["hgt"], sc.orbit_t, sc.orbit_pos, sc.orbit_vel,
+                             doppler_coeffs=dop, block_rows=True)
+    # the oracle sees the block as an image whose first row is radar line a (offsets are relative to the row index)
+    o = orc.geo2rdr(lat=c["lat"], lon=c["lon"], hgt=c["hgt"], orbit_method="LEGENDRE", doppler_coeffs=dop,
+                    **dict(kw, t0=sc.t0 + a / sc.prf, length=sc.length - a))
+    v = o["azoff"] != -999999.0
+    assert np.array_equal(gblk["azoff"] != -999999.0, v) and v.mean() > 0.99
+    assert np.abs(gblk["rgoff"][v] - o["rgoff"][v]).max() < pu.TOL_OFFSET_PX
+    assert np.abs(gblk["azt"][v] - o["azt"][v]).max() < pu.TOL_OFFSET_PX / sc.prf

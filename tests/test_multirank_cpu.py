@@ -79,8 +79,9 @@ from tests import fake_capi_for_bench as fake
 sys.modules["isce2_b200._capi"] = fake
 isce2_b200._capi = fake
 import bench
+{patch}
 sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "1", "--workload", {workload!r}, "--lines", "37", "--e2e-steps", "2",
-            "--no-cpu-baseline", "--max-seconds", "200"]
+            "--other-lines", "29", "--component", "0", "--no-cpu-baseline", "--max-seconds", "300"]
 bench.main()
 '''
 
@@ -91,7 +92,7 @@ def test_bench_control_flow_world2_with_a_stand_in_library(tmp_path):
     library): every rank reaches every barrier / reduction, also when the two end-to-end arms of a rank that does not
     start at line 0 differ in the last bits; rank 0 alone prints the JSON line, with the contract's keys."""
     script = tmp_path / "bench_worker.py"
-    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c0c1"))
+    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c0c1", patch=""))
     p = _torchrun([str(script)], timeout=300)
     assert p.returncode == 0, p.stderr[-3000:]
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
@@ -106,15 +107,40 @@ def test_bench_control_flow_world2_with_a_stand_in_library(tmp_path):
     assert v["compared"] and v["validity_equal"] and v["max_abs_offset_diff_px"] < 1e-3
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in d["roofline"], k
+    assert d["e2e"]["statistic"].startswith("median") and d["e2e"]["d2h_floor"]["ms"] > 0 and 0 < d["e2e"]["frac_of_d2h_floor"]
+    assert v["rows_compared_per_rank"] > 0
+    # the other BASELINE configs ride in the same line: C3 (NISAR, Legendre, native Doppler) and the 29-orbit stack batch
+    oc = d["other_configs"]
+    assert set(oc) == {"c3", "c4"} and all("error" not in oc[k] for k in oc), oc
+    assert oc["c3"]["config"]["pixels_per_step"] == 29 * 25000 and oc["c3"]["config"]["orbit_method"] == "LEGENDRE"
+    assert oc["c3"]["value"] > 0 and oc["c3"]["e2e"]["value"] > 0 and "e2e_two_calls" not in oc["c3"]
+    assert oc["c4"]["config"]["jobs_on_rank0"] == 15 and oc["c4"]["value"] > 0
 
 
 @pytest.mark.timeout(400)
 def test_stack_batch_control_flow_world2_with_a_stand_in_library(tmp_path):
     """configs[4] (29 secondary orbits dealt round-robin to the ranks) through the same stand-in: one JSON line, from rank 0."""
     script = tmp_path / "bench_worker_c4.py"
-    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c4"))
+    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c4", patch=""))
     p = _torchrun([str(script)], timeout=300)
     assert p.returncode == 0, p.stderr[-3000:]
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and lines[0]["config"]["jobs_on_rank0"] == 15
     assert lines[0]["metric"].startswith("geo2rdr Mpixels/s") and lines[0]["value"] > 0
+
+
+@pytest.mark.timeout(400)
+def test_a_failing_secondary_config_is_reported_not_fatal_world2(tmp_path):
+    """A secondary config that fails on one rank only (here: rank 1 cannot build its scene) must neither hang the ranks
+    nor cost the main line: its local work runs under a guard, every collective is still reached by every rank."""
+    patch = ("import os\n"
+             "if os.environ.get('RANK') == '1':\n"
+             "    bench.WORKLOADS['c3']['sensor'] = 'no-such-sensor'\n")
+    script = tmp_path / "bench_worker_fail.py"
+    script.write_text(BENCH_WORKER.format(root=ROOT, workload="c0c1", patch=patch))
+    p = _torchrun([str(script)], timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and lines[0]["value"] > 0 and lines[0]["e2e"]["value"] > 0
+    oc = lines[0]["other_configs"]
+    assert "error" in oc["c3"] and "error" not in oc["c4"] and oc["c4"]["value"] > 0

@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU pass of a round: parity tests, both bench arms, ncu launch list + full captures of every kernel instance of the
+# step.  Usage (from the repo root, under gpurun):  bash tools/gpu_pass.sh TAG [quick]
+TAG=${1:-r02}
+QUICK=${2:-}
+O=gpurun_out
+mkdir -p $O
+set -x
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $O/box_$TAG.txt; nproc >> $O/box_$TAG.txt; free -g >> $O/box_$TAG.txt
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $O/pytest_gpu_$TAG.log; cat $O/pytest_gpu_$TAG.log
+timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; tail -25 $O/bench_$TAG.err
+[ -n "$QUICK" ] && exit 0
+timeout 300 python bench.py --impl reference --steps 6 --warmup 1 --ref-step-seconds 4 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err
+NCU_COMMON="--clock-control none"
+B="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --e2e-steps 1 --component 0 --other-configs none --lines 1500"
+timeout 600 ncu --metrics gpu__time_duration.sum $NCU_COMMON -c 120 --csv --log-file $O/launches_$TAG.csv python bench.py --lines 1500 --other-lines 1500 --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 --component 0 > $O/launch_bench_$TAG.log 2>&1
+FP="--metrics smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"
+K='regex:k_topo_solve|k_topo_final|k_topo_fused|k_topo_mask|k_geo2rdr|k_fp64_peak'
+timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 6 -f -o $O/full_c2_$TAG $B --workload c2 > $O/full_c2_$TAG.log 2>&1
+timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 4 -f -o $O/full_c0c1_$TAG $B --workload c0c1 > $O/full_c0c1_$TAG.log 2>&1
+timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 6 -f -o $O/full_c3_$TAG $B --workload c3 > $O/full_c3_$TAG.log 2>&1
+ls -la $O/*.ncu-rep
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
