@@ -851,6 +851,8 @@ def measure_component(args, ranks, capi, dev, name, lines=None):
                                            inc=w["inc"], mask=w["mask"], devices=[dev])
                 times.append(time.perf_counter() - t0)
                 out["bytes_written"] = info.get("bytes_written")
+                gt = info.get("gpu_timings") or []
+                out["library_call_ms"] = [round(float(g["ms_total"]), 1) for g in gt]  # inside b200_topo_geo2rdr_run
             finally:
                 shutil.rmtree(d, ignore_errors=True)
     except Exception as e:  # noqa: BLE001

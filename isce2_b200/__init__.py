@@ -46,10 +46,15 @@ def install_as_zerodop():
         sys.modules["zerodop"] = pkg
     for name, mod, factory in (("topozero", t, "createTopozero"), ("geo2rdr", g, "createGeo2rdr"),
                                ("geozero", z, "createGeozero")):
+        # zerodop.<name> is a package in the reference (its class lives in zerodop/<name>/<Name>.py): both import forms,
+        # `from zerodop.topozero import createTopozero` and `from zerodop.topozero.Topozero import Topo`, must resolve
         m = types.ModuleType(f"zerodop.{name}")
+        m.__path__ = []
         setattr(m, factory, getattr(mod, factory))
-        setattr(m, mod.__name__.rsplit(".", 1)[-1].capitalize(), mod)
-        m.__dict__.update({k: v for k, v in mod.__dict__.items() if k in ("Topo", "Geo2rdr", "Geocode")})
+        sub = mod.__name__.rsplit(".", 1)[-1].capitalize()  # Topozero / Geo2rdr / Geozero
+        setattr(m, sub, mod)
+        m.__dict__.update({k: v for k, v in mod.__dict__.items() if k in ("Topo", "Geocode")})  # (Geo2rdr names the submodule)
         sys.modules[f"zerodop.{name}"] = m
+        sys.modules[f"zerodop.{name}.{sub}"] = mod
         setattr(pkg, name, m)
     return pkg

@@ -702,15 +702,24 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
 #endif
 constexpr int kMaskKnots = B2_MASK_KNOTS;
 
+// Per line: (A) the line's cross-track positions go into shared memory once (min / max / fold-over test on the way); (B) only
+// lines with fold-over are co-sorted; (C, D) the 2 w + 1 samples of the regular cross-track grid are resampled with the
+// bracket search running on the shared-memory copy (two or three ~30-cycle probes instead of dependent L2 loads) and
+// their slant ranges are tested for order AS THEY ARE PRODUCED -- they are not stored: on a line whose ranges ascend
+// (no layover anywhere on it) neither layover scan can flag anything, so nothing else is needed; (E) shadow scans; (F)
+// only lines with range fold-over produce the samples a second time, now into the scratch arrays the sort / scan /
+// scatter stages work on.  DRAM traffic of a line without layover is the algorithmic 28 B in + 1 B out per pixel.
 template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kMaskBlock, 1024 / kMaskBlock)
 k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines, TopoLayers out,
-            float demmax, MaskScratch scr)
+            float demmax, MaskScratch scr, int stage_cs)
 {
-    extern __shared__ unsigned char s_dyn[]; // [width] mask bytes of the line being built
+    extern __shared__ unsigned char s_dyn[]; // [stage_cs ? width doubles : 0] sorted cross-track positions, then [width] mask bytes
     __shared__ SR s_warp[32];                // scan scratch (largest scan state)
     __shared__ double s_mm[2];
     __shared__ double s_knot[kMaskKnots + 1];
+    __shared__ double s_first[kMaskBlock / 32 + 1]; // first sample of every warp of the current sweep
+    __shared__ double s_carry;                      // last sample of the previous sweep
     __shared__ int s_flag;
     __shared__ LineState sL;
     const int w = C.width, ow = 2 * w + 1; // :134-135
@@ -721,10 +730,12 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
     double *pm = scr.pm + (size_t)blockIdx.x * ow, *sm = scr.sm + (size_t)blockIdx.x * ow;
     int *rank = scr.rank + (size_t)blockIdx.x * ow;
     unsigned char *oflag = scr.oflag + (size_t)blockIdx.x * ow;
-    unsigned int *smask = reinterpret_cast<unsigned int *>(s_dyn);
-    unsigned char *sbytes = s_dyn;
+    double *s_cs = reinterpret_cast<double *>(s_dyn);
+    unsigned char *sbytes = s_dyn + (stage_cs ? (size_t)w * sizeof(double) : 0);
+    unsigned int *smask = reinterpret_cast<unsigned int *>(sbytes);
     SD *s_warp_d = reinterpret_cast<SD *>(s_warp);
     SF *s_warp_f = reinterpret_cast<SF *>(s_warp);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     for (int row = blockIdx.x; row < nlines; row += gridDim.x) {
         const int line = line0 + row;
@@ -732,11 +743,12 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double *ctrack_in = out.ctrack + (size_t)row * w;
         const double *lat_in = out.lat + (size_t)row * w, *lon_in = out.lon + (size_t)row * w;
         const float *elev = out.elev + (size_t)row * w;
-        // ---- ctrack extent :730-732 and "is the line free of fold-over" in one pass over the line ----
+        // ---- (A) ctrack extent :730-732, "is the line free of fold-over", and the shared-memory copy, in one pass ----
         double mn = INFINITY, mx = -INFINITY;
         int unsorted = 0;
         for (int i = threadIdx.x; i < w; i += blockDim.x) {
             const double v = ctrack_in[i];
+            if (stage_cs) s_cs[i] = v;
             mn = fmin(mn, v);
             mx = fmax(mx, v);
             if (i > 0 && ctrack_in[i - 1] > v) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
@@ -744,19 +756,19 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         mn = warp_min(mn);
         mx = warp_max(mx);
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_warp_d[threadIdx.x >> 5].v = mn;
+        if (lane == 0) s_warp_d[wid].v = mn;
         __syncthreads();
         // two-level reduce: 32 warp minima / maxima
         if (threadIdx.x < 32) {
-            double a = threadIdx.x < (blockDim.x >> 5) ? s_warp_d[threadIdx.x].v : INFINITY;
+            double a = threadIdx.x < nwarps ? s_warp_d[threadIdx.x].v : INFINITY;
             a = warp_min(a);
             if (threadIdx.x == 0) s_mm[0] = a;
         }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_warp_d[threadIdx.x >> 5].v = mx;
+        if (lane == 0) s_warp_d[wid].v = mx;
         __syncthreads();
         if (threadIdx.x < 32) {
-            double a = threadIdx.x < (blockDim.x >> 5) ? s_warp_d[threadIdx.x].v : -INFINITY;
+            double a = threadIdx.x < nwarps ? s_warp_d[threadIdx.x].v : -INFINITY;
             a = warp_max(a);
             if (threadIdx.x == 0) s_mm[1] = a;
         }
@@ -764,27 +776,32 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double ctrackmin = s_mm[0] - demmax, ctrackmax = s_mm[1] + demmax;
         const double dctrack = (ctrackmax - ctrackmin) / (ow - 1.0);
 
-        // ---- stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
-        const double *cs = ctrack_in, *lats = lat_in, *lons = lon_in;
+        // ---- (B) stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
+        const double *cs = stage_cs ? s_cs : ctrack_in, *lats = lat_in, *lons = lon_in;
         if (!ctrack_sorted) {
             block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
             block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < w; i += blockDim.x) {
                 const int r = rank[i];
-                cs_s[r] = ctrack_in[i];
+                const double v = ctrack_in[i];
+                if (stage_cs) s_cs[r] = v; // every slot is written exactly once (ranks are a permutation): no read races
+                else cs_s[r] = v;
                 lats_s[r] = lat_in[i];
                 lons_s[r] = lon_in[i];
             }
-            cs = cs_s; lats = lats_s; lons = lons_s;
+            if (!stage_cs) cs = cs_s;
+            lats = lats_s;
+            lons = lons_s;
             __syncthreads();
         }
 
-        // ---- DEM surface on the regular cross-track grid :745-782 ----
+        // ---- (C) DEM surface on the regular cross-track grid :745-782 ----
         // The sorted cross-track positions are smooth but not uniform in the sample index (ground spacing changes across
-        // the swath), so a straight line through the end points misses the bracket by hundreds of samples and the search
-        // degenerates into ~16 dependent loads.  kMaskKnots + 1 samples of the array in shared memory give a piecewise
-        // linear inverse that lands within a sample or two; the search itself (and therefore the result) is unchanged.
+        // the swath), so a straight line through the end points misses the bracket by hundreds of samples.  kMaskKnots + 1
+        // samples of the array give a piecewise linear inverse that lands within a sample or two; the search itself (and
+        // therefore the result) is unchanged.
         for (int k = threadIdx.x; k <= kMaskKnots; k += blockDim.x) s_knot[k] = cs[(int)(((long long)k * (w - 1)) / kMaskKnots)];
+        if (threadIdx.x == 0) s_carry = -INFINITY;
         __syncthreads();
         const double cs0 = s_knot[0], csn = s_knot[kMaskKnots];
         const double kscale = (csn > cs0) ? (double)kMaskKnots / (csn - cs0) : 0.0;
@@ -800,37 +817,40 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             const double f = (b > a) ? (aa - a) / (b - a) : 0.0;
             return i0 + (int)(f * (double)(i1 - i0));
         };
-        // The slant ranges of consecutive samples are compared as they are produced: a warp owns 32 consecutive samples
-        // per sweep, so all but the first one find their predecessor in the neighbouring lane; the warp-boundary pairs
-        // (one in 32) are compared afterwards from memory.  Lines without fold-over never read orng back otherwise.
+        auto sample = [&](int p) -> double { // slant range of grid sample p (0-based), :747-782
+            const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
+            const int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, knot_guess(aa)), w);
+            return mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
+        };
+        // ---- (D) first sweep: is the slant range ascending over the grid?  Every sample is compared with its
+        // predecessor: within a warp through a shuffle, across warps through s_first, across sweeps through s_carry.
         int orng_unsorted = 0;
         for (int base = 0; base < ow; base += blockDim.x) {
             const int p = base + (int)threadIdx.x;
-            double val = 0.0;
-            if (p < ow) {
-                const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
-                int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, knot_guess(aa)), w);
-                val = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
-                orng[p] = val;
-            }
+            const double val = p < ow ? sample(p) : INFINITY; // +inf: never smaller than its predecessor
             const double prev = __shfl_up_sync(0xffffffffu, val, 1);
-            if ((threadIdx.x & 31) != 0 && p < ow && prev > val) orng_unsorted = 1;
+            if (lane != 0 && prev > val) orng_unsorted = 1;
+            if (lane == 0) s_first[wid] = val;
+            __syncthreads();
+            if (lane == 31 && wid + 1 < nwarps && val > s_first[wid + 1]) orng_unsorted = 1;
+            if (threadIdx.x == 0 && s_carry > val) orng_unsorted = 1;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) s_carry = val;
         }
-        __syncthreads();
-        for (int b = 32 * ((int)threadIdx.x + 1); b < ow; b += 32 * blockDim.x)
-            if (orng[b - 1] > orng[b]) orng_unsorted = 1;
         const bool orng_sorted_already = __syncthreads_or(orng_unsorted) == 0;
 
-        // ---- shadow (:791-809) on float32 elevang in pixel order ----
+        // ---- (E) shadow (:791-809) on float32 elevang in pixel order ----
         for (int i = threadIdx.x; i < (w + 3) / 4; i += blockDim.x) smask[i] = 0u;
         __syncthreads();
         block_prefix_max_flags<float>(elev, w, w, sbytes, (unsigned char)1, s_warp_f, OpMaxF());
         block_suffix_min_flags<float>(elev, w, nullptr, 0, sbytes, (unsigned char)1, s_warp);
 
-        // ---- stable co-sort (orng; ctrack) :787 and layover (:834-852) on the range-sorted ctrack ----
+        // ---- (F) stable co-sort (orng; ctrack) :787 and layover (:834-852) on the range-sorted ctrack ----
         // ctrack increases with the sample index by construction, so when the slant ranges are already ascending the
         // sorted ctrack is ascending too and neither layover scan can flag anything: the line is done.
         if (!orng_sorted_already) {
+            for (int p = threadIdx.x; p < ow; p += blockDim.x) orng[p] = sample(p); // the same values, now kept
+            __syncthreads();
             block_prefix_max_suffix_min(orng, ow, pm, sm, s_warp_d);
             block_stable_ranks(orng, ow, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < ow; i += blockDim.x) {
@@ -844,19 +864,19 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             // backward scan treats forward-flagged samples as resets (:847)
             block_prefix_max_flags<double>(ctr_sorted, ow, w, oflag, (unsigned char)2, s_warp_d, OpMaxD());
             block_suffix_min_flags<double>(ctr_sorted, ow, oflag, (unsigned char)2, oflag, (unsigned char)4, s_warp);
-        }
 
-        // ---- scatter to radar pixels through the slant-range line (:855-865) ----
-        const double rho0 = pixel_range(C, line, 0), rhon = pixel_range(C, line, w - 1);
-        const double rscale = (rhon > rho0) ? (double)(w - 1) / (rhon - rho0) : 0.0;
-        for (int i = threadIdx.x; i < (orng_sorted_already ? 0 : ow); i += blockDim.x) {
-            if (oflag[i]) {
-                const double val = orng_sorted[i];
-                const int guess = (int)((val - rho0) * rscale);
-                const int j = ref_search_result(search_count_le([&](int m) { return pixel_range(C, line, m); }, w, val, guess), w);
-                // mask(j) < omask(i) => mask(j) += 2  <=>  set bit 1 (mask is 0/1 before any layover hit)
-                const int bidx = j - 1;
-                atomicOr(&smask[bidx >> 2], 2u << (8 * (bidx & 3)));
+            // ---- scatter to radar pixels through the slant-range line (:855-865) ----
+            const double rho0 = pixel_range(C, line, 0), rhon = pixel_range(C, line, w - 1);
+            const double rscale = (rhon > rho0) ? (double)(w - 1) / (rhon - rho0) : 0.0;
+            for (int i = threadIdx.x; i < ow; i += blockDim.x) {
+                if (oflag[i]) {
+                    const double val = orng_sorted[i];
+                    const int guess = (int)((val - rho0) * rscale);
+                    const int j = ref_search_result(search_count_le([&](int m) { return pixel_range(C, line, m); }, w, val, guess), w);
+                    // mask(j) < omask(i) => mask(j) += 2  <=>  set bit 1 (mask is 0/1 before any layover hit)
+                    const int bidx = j - 1;
+                    atomicOr(&smask[bidx >> 2], 2u << (8 * (bidx & 3)));
+                }
             }
         }
         __syncthreads();
@@ -949,28 +969,40 @@ int mask_grid_size(int nlines)
 
 template <int METHOD>
 static void launch_mask_m(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
-                          float demmax, const MaskScratch &scr, int grid, size_t smem, cudaStream_t s)
+                          float demmax, const MaskScratch &scr, int grid, size_t smem, int stage_cs, cudaStream_t s)
 {
     if (C.ref.use_ref) {
         cudaFuncSetAttribute(k_topo_mask<METHOD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<METHOD, true><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
+        k_topo_mask<METHOD, true><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, stage_cs);
     } else {
         cudaFuncSetAttribute(k_topo_mask<METHOD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<METHOD, false><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr);
+        k_topo_mask<METHOD, false><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, stage_cs);
     }
 }
 
 int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out, float demmax,
                      const MaskScratch &scr, int grid, cudaStream_t s)
 {
-    size_t smem = (size_t)((C.width + 3) / 4) * 4;
+    // the line's sorted cross-track positions live in shared memory when they fit next to the mask bytes (227 KB per CTA on
+    // sm_100a, ~3.5 KB of it static): widths up to ~25 400 samples; wider swaths search the global copy through L1 / L2
+    const size_t bytes_mask = (size_t)((C.width + 3) / 4) * 4, bytes_cs = (size_t)C.width * sizeof(double);
+    const size_t budget = 227u * 1024u - 4096u;
+    const int stage_cs = (bytes_cs + bytes_mask <= budget) ? 1 : 0;
+#ifdef B2_MASK_NO_STAGE
+    const size_t smem = bytes_mask;
+    const int stage = 0;
+    (void)stage_cs;
+#else
+    const size_t smem = bytes_mask + (stage_cs ? bytes_cs : 0);
+    const int stage = stage_cs;
+#endif
     switch (C.method) {
-    case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
-    case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
-    case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
-    case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
-    case 4: launch_mask_m<4>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
-    case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, s); break;
+    case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 4: launch_mask_m<4>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
     default: return -1;
     }
     return 0;

@@ -109,7 +109,7 @@ class Geo2rdr(Component):
         coeffs, mean, norm = poly1d_fields(self.polyDoppler)
         single = self.outputPrecision.upper() == 'SINGLE'
         imgs = dict(azt=self.azimuthImage, rgm=self.rangeImage, azoff=self.azimuthOffsetImage, rgoff=self.rangeOffsetImage)
-        outs = {k: (v.memMap() if v is not None else None) for k, v in imgs.items()}
+        outs = {k: (IF.output_memmap(v, rows, cols) if v is not None else None) for k, v in imgs.items()}
         want = tuple(k for k, v in outs.items() if v is not None)
         devices = _devices(self.gpuDevices)
         n = len(devices)
@@ -164,7 +164,7 @@ class Geo2rdr(Component):
         t, pos, vel = export_rows(self.orbit, self.sensingStart)
         single = self.outputPrecision.upper() == 'SINGLE'
         imgs = dict(azt=self.azimuthImage, rgm=self.rangeImage, azoff=self.azimuthOffsetImage, rgoff=self.rangeOffsetImage)
-        outs = {k: (v.memMap() if v is not None else None) for k, v in imgs.items()}
+        outs = {k: (IF.output_memmap(v, rows, cols) if v is not None else None) for k, v in imgs.items()}
 
         def params(line0, nlines, device):
             return _capi.geo_params(length=int(self.length), width=int(self.width), dem_shape=(rows, cols),

@@ -16,7 +16,7 @@ import numpy as np
 # Image.py:62-63
 TO_NUMPY = {"BYTE": np.int8, "SHORT": np.int16, "INT": np.int32, "LONG": np.int64, "FLOAT": np.float32,
             "DOUBLE": np.float64, "CFLOAT": np.complex64, "CDOUBLE": np.complex128}
-VRT_TYPE = {"BYTE": "Byte", "SHORT": "Int16", "INT": "Int32", "FLOAT": "Float32", "DOUBLE": "Float64",
+VRT_TYPE = {"BYTE": "Byte", "SHORT": "Int16", "INT": "Int32", "LONG": "Int64", "FLOAT": "Float32", "DOUBLE": "Float64",
             "CFLOAT": "CFloat32", "CDOUBLE": "CFloat64"}
 SIZE = {"BYTE": 1, "SHORT": 2, "INT": 4, "LONG": 8, "FLOAT": 4, "DOUBLE": 8, "CFLOAT": 8, "CDOUBLE": 16}
 ISCE_VERSION = "b200-zerodop-geometry (ISCE2-compatible raster metadata)"
@@ -111,9 +111,14 @@ class Image:
             return (self.length, self.width, self.bands)
         return (self.bands, self.length, self.width)
 
+    def _dtype(self):
+        """numpy dtype of one sample in the file's byte order (BYTE_ORDER 'l' / 'b', Image.py:62-63; the reference's
+        DataAccessor swaps on the fly, here the memmap carries the order and consumers convert on read)."""
+        return _file_dtype(self.dataType, self.byteOrder)
+
     def createImage(self):
         """Open (read) or create (write) the raster as a numpy memmap."""
-        dt = np.dtype(TO_NUMPY[self.dataType.upper()])
+        dt = self._dtype()
         if self.accessMode.startswith("r"):
             if self.length is None:
                 self.length = os.path.getsize(self.filename) // (dt.itemsize * self.width * self.bands)
@@ -339,20 +344,62 @@ def _indent(elem, level=0):
         elem.tail = pad
 
 
+def _file_dtype(data_type, byte_order="l"):
+    dt = np.dtype(TO_NUMPY[str(data_type).upper()])
+    bo = str(byte_order or "l").lower()[:1]
+    if bo not in ("l", "b"):
+        raise ValueError(f"unknown BYTE_ORDER {byte_order!r} (expected 'l' or 'b')")
+    return dt.newbyteorder(">" if bo == "b" else "<") if dt.itemsize > 1 else dt
+
+
+def _foreign_meta(img, need_length=True):
+    """(filename, dtype, width, length, bands, scheme) of an image object that is not ours (an isceobj Image: duck-typed)."""
+    fn = img.getFilename() if hasattr(img, "getFilename") else img.filename
+    dt = _file_dtype(img.dataType, getattr(img, "byteOrder", "l"))
+    width, bands = int(img.width), int(getattr(img, "bands", 1) or 1)
+    length = getattr(img, "length", None)
+    if not length:
+        length = os.path.getsize(fn) // (dt.itemsize * width * bands) if need_length else 0
+    return fn, dt, width, int(length), bands, str(getattr(img, "scheme", "BIL") or "BIL").upper()
+
+
+def _shape(length, width, bands, scheme):
+    if bands == 1:
+        return (length, width)
+    return {"BIL": (length, bands, width), "BIP": (length, width, bands)}.get(scheme, (bands, length, width))
+
+
 def read_raster(img, as_dtype=None):
-    """Return the raster behind `img` (ours or an isceobj image: duck-typed metadata) as a numpy array."""
+    """Return the raster behind `img` (ours or an isceobj image: duck-typed metadata) as a numpy array in native byte
+    order, in the image's own interleaving (Image.py:319-335 shapes)."""
     if isinstance(img, Image):
         arr = img.memMap()
     else:
-        fn = img.getFilename() if hasattr(img, "getFilename") else img.filename
-        dt = np.dtype(TO_NUMPY[str(img.dataType).upper()])
-        width, bands = int(img.width), int(getattr(img, "bands", 1) or 1)
-        length = getattr(img, "length", None) or os.path.getsize(fn) // (dt.itemsize * width * bands)
-        shape = (int(length), width) if bands == 1 else (int(length), bands, width)
-        arr = np.memmap(fn, dtype=dt, mode="r", shape=shape)
+        fn, dt, width, length, bands, scheme = _foreign_meta(img)
+        arr = np.memmap(fn, dtype=dt, mode="r", shape=_shape(length, width, bands, scheme))
+    if not arr.dtype.isnative:
+        arr = np.asarray(arr).astype(arr.dtype.newbyteorder("="))
     if as_dtype is not None and arr.dtype != np.dtype(as_dtype):
         arr = np.asarray(arr).astype(as_dtype)
     return arr
+
+
+def output_memmap(img, length, width, bands=1):
+    """Writable [length][(bands)][width] memmap of an OUTPUT image the caller handed to a Component ('Must either pass
+    the latImage in the call or set self.latFilename', Topozero.py:274-302).  Ours: its own memmap.  A foreign (isceobj)
+    image: its memMap() defaults to read-only and shapes single-band rasters (length, 1, width), so the file it names is
+    mapped here instead, created at the right size if need be."""
+    if isinstance(img, Image):
+        return img.memMap()
+    fn, dt, w, _, b, scheme = _foreign_meta(img, need_length=False)
+    if w != width or b != bands or (bands > 1 and scheme != "BIL"):
+        raise ValueError(f"output image {fn}: {w} samples x {b} bands ({scheme}) where {width} x {bands} (BIL) are written")
+    if not dt.isnative:
+        raise ValueError(f"output image {fn}: big-endian output rasters are not supported")
+    os.makedirs(os.path.dirname(os.path.abspath(fn)), exist_ok=True)
+    need = length * width * bands * dt.itemsize
+    mode = "r+" if os.path.exists(fn) and os.path.getsize(fn) == need else "w+"
+    return np.memmap(fn, dtype=dt, mode=mode, shape=_shape(length, width, bands, "BIL"))
 
 
 def read_view(path):

@@ -67,7 +67,7 @@ class Resamp_slc(Component):
         ra, rr = resid(self.residualAzimuthImage), resid(self.residualRangeImage)
         if ra is not None and rr is not None and ra.dtype != rr.dtype:
             ra, rr = np.asarray(ra, np.float64), np.asarray(rr, np.float64)
-        out = self.imageOut.memMap()
+        out = IF.output_memmap(self.imageOut, ol, ow)  # ours, or an image object the caller handed in
         direct = out.dtype == np.complex64 and out.flags['C_CONTIGUOUS'] and out.shape == (ol, ow)
         r = _capi.resamp_slc_run(slc[:int(self.inputLines)], (ol, ow), wvl=float(self.radarWavelength),
                                  slr=float(self.slantRangePixelSpacing), r0=float(self.startingRange),

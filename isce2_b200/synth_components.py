@@ -98,4 +98,4 @@ def run_components(sc, sec, dem_img, outdir, *, dem_method="BIQUINTIC", orbit_me
     topo.topo()
     files = [f for f in os.listdir(outdir) if f.endswith((".rdr", ".off"))]
     return dict(files=sorted(files), bytes_written=sum(os.path.getsize(os.path.join(outdir, f)) for f in files),
-                snwe=topo.snwe, num_valid=getattr(grdr, "numValid", None))
+                snwe=topo.snwe, num_valid=getattr(grdr, "numValid", None), gpu_timings=getattr(topo, "gpuTimings", None))

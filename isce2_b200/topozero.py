@@ -87,10 +87,12 @@ class Topo(Component):
         devices = _devices(self.gpuDevices)
         n = len(devices)
         length, width = int(self.length), int(self.width)
-        outs = dict(lat=self.latImage.memMap(), lon=self.lonImage.memMap(), hgt=self.heightImage.memMap(),
-                    los=self.losImage.memMap() if self.losImage else None,
-                    inc=self.incImage.memMap() if self.incImage else None,
-                    mask=self.maskImage.memMap() if self.maskImage else None)
+        # output layers: this package's images, or images the caller handed in (Topozero.py:274-302), mapped writable
+        outs = dict(lat=IF.output_memmap(self.latImage, length, width), lon=IF.output_memmap(self.lonImage, length, width),
+                    hgt=IF.output_memmap(self.heightImage, length, width),
+                    los=IF.output_memmap(self.losImage, length, width, 2) if self.losImage else None,
+                    inc=IF.output_memmap(self.incImage, length, width, 2) if self.incImage else None,
+                    mask=IF.output_memmap(self.maskImage, length, width) if self.maskImage else None)
         results, errors = [None] * n, [None] * n
         chained = [g._chain_prepare(self) for g in self.chainedGeo2rdr]
         chained_results = [[None] * n for _ in chained]

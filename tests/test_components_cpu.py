@@ -195,3 +195,74 @@ def test_poly_evaluation_order_matches_reference_c():
     q.initPoly(order=2, coeffs=[0.1, 0.02, -3e-4]); q.setMean(5.0); q.setNorm(2.0)
     r1 = orc.Poly1D([0.1, 0.02, -3e-4], 5.0, 2.0)
     assert q(123.0) == r1(123.0)
+
+
+def test_install_as_zerodop_resolves_both_import_forms():
+    """zerodop.<name> is a package in the reference; the class modules must be importable too."""
+    import importlib
+    import sys
+    import isce2_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "zerodop" or k.startswith("zerodop.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        isce2_b200.install_as_zerodop()
+        from zerodop.topozero import createTopozero
+        from zerodop.geo2rdr import createGeo2rdr
+        from zerodop.topozero.Topozero import Topo
+        from zerodop.geo2rdr.Geo2rdr import Geo2rdr
+        from zerodop.geozero.Geozero import Geocode
+        assert isinstance(createTopozero(), Topo) and isinstance(createGeo2rdr(), Geo2rdr) and Geocode is not None
+        assert importlib.import_module("zerodop.geo2rdr.Geo2rdr").Geo2rdr is Geo2rdr
+    finally:
+        for k in [k for k in sys.modules if k == "zerodop" or k.startswith("zerodop.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_image_byte_order_long_vrt_and_foreign_images(tmp_path):
+    """big-endian rasters are read as such, LONG renders a VRT, foreign (isceobj-like) images are honoured
+    in their own interleaving on input and mapped writable on output."""
+    import numpy as np
+    from isce2_b200 import image as IF
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    p = str(tmp_path / "be.bin")
+    a.astype(">f4").tofile(p)
+    img = IF.createImage()
+    img.initImage(p, "read", 4, "FLOAT")
+    img.setLength(3)
+    img.byteOrder = "b"
+    got = IF.read_raster(img)
+    assert got.dtype == np.float32 and got.dtype.isnative and np.array_equal(got, a)
+    lg = IF.createImage()
+    q = str(tmp_path / "long.bin")
+    np.arange(6, dtype=np.int64).tofile(q)
+    lg.initImage(q, "read", 3, "LONG")
+    lg.setLength(2)
+    lg.renderHdr()
+    assert "Int64" in open(q + ".vrt").read()
+
+    class Foreign:  # what an isceobj Image exposes
+        def __init__(self, fn, width, length, bands, scheme, dataType):
+            self.filename, self.width, self.length, self.bands, self.scheme, self.dataType = fn, width, length, bands, scheme, dataType
+            self.byteOrder = "l"
+
+        def getFilename(self):
+            return self.filename
+
+        def memMap(self, mode="r", band=None):  # read-only, (length, 1, width) for one band: unusable as an output
+            raise AssertionError("the foreign image's own memMap must not be used")
+
+    bip = np.arange(2 * 3 * 2, dtype=np.float32).reshape(2, 3, 2)  # [line][sample][band]
+    r = str(tmp_path / "bip.bin")
+    bip.tofile(r)
+    assert np.array_equal(IF.read_raster(Foreign(r, 3, 2, 2, "BIP", "FLOAT")), bip)
+    o = str(tmp_path / "out" / "lat.rdr")
+    mm = IF.output_memmap(Foreign(o, 5, None, 1, "BIL", "DOUBLE"), 4, 5)
+    assert mm.shape == (4, 5) and mm.dtype == np.float64 and mm.flags.writeable
+    mm[:] = 7.0
+    mm.flush()
+    assert np.fromfile(o).sum() == 7.0 * 20
+    import pytest
+    with pytest.raises(ValueError):
+        IF.output_memmap(Foreign(o, 6, None, 1, "BIL", "DOUBLE"), 4, 5)

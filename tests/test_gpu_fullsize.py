@@ -184,7 +184,11 @@ def test_c3_nisar_frame_round_trip_at_full_size():
     # the oracle sees the block as an image whose first row is radar line a (offsets are relative to the row index)
     o = orc.geo2rdr(lat=c["lat"], lon=c["lon"], hgt=c["hgt"], orbit_method="LEGENDRE", doppler_coeffs=dop,
                     **dict(kw, t0=sc.t0 + a / sc.prf, length=sc.length - a))
+    # same orbit, same window: the pixels of the first / last sample sit ON the edge of the range window and the strict
+    # bounds test (geo2rdr.f90:308-316) decides them in the last bit, which the re-based description of the block moves
     v = o["azoff"] != -999999.0
-    assert np.array_equal(gblk["azoff"] != -999999.0, v) and v.mean() > 0.99
+    gv = gblk["azoff"] != -999999.0
+    assert np.array_equal(gv[:, 1:-1], v[:, 1:-1]) and v[:, 1:-1].all()
+    v = v & gv
     assert np.abs(gblk["rgoff"][v] - o["rgoff"][v]).max() < pu.TOL_OFFSET_PX
     assert np.abs(gblk["azt"][v] - o["azt"][v]).max() < pu.TOL_OFFSET_PX / sc.prf

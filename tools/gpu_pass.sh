@@ -16,8 +16,12 @@ B="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --e2e-steps 1 --compon
 timeout 600 ncu --metrics gpu__time_duration.sum $NCU_COMMON -c 120 --csv --log-file $O/launches_$TAG.csv python bench.py --lines 1500 --other-lines 1500 --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 --component 0 > $O/launch_bench_$TAG.log 2>&1
 FP="--metrics smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"
 K='regex:k_topo_solve|k_topo_final|k_topo_fused|k_topo_mask|k_geo2rdr|k_fp64_peak'
+# gpurun brings back at most 64 MiB: the c2 report (with source) comes home, the others are summarised here and dropped
 timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 6 -f -o $O/full_c2_$TAG $B --workload c2 > $O/full_c2_$TAG.log 2>&1
-timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 4 -f -o $O/full_c0c1_$TAG $B --workload c0c1 > $O/full_c0c1_$TAG.log 2>&1
-timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 6 -f -o $O/full_c3_$TAG $B --workload c3 > $O/full_c3_$TAG.log 2>&1
-ls -la $O/*.ncu-rep
+python tools/ncu_summary.py $O/full_c2_$TAG.ncu-rep $O/ncu_full_c2_$TAG.json > $O/ncu_full_c2_$TAG.txt 2>&1
+for W in c0c1 c3; do
+  timeout 900 ncu --set full $FP $NCU_COMMON -k "$K" -c 6 -f -o /tmp/full_${W}_$TAG $B --workload $W > $O/full_${W}_$TAG.log 2>&1
+  python tools/ncu_summary.py /tmp/full_${W}_$TAG.ncu-rep $O/ncu_full_${W}_$TAG.json > $O/ncu_full_${W}_$TAG.txt 2>&1
+done
+ls -la $O/*.ncu-rep; du -sh $O
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
