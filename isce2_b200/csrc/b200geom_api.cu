@@ -7,10 +7,7 @@
 
 #include <cuda_runtime.h>
 
-#include <sys/mman.h>
-
 #include <atomic>
-#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -271,7 +268,6 @@ class CopyPool {
                 cudaSetDevice(t.device);
                 cur = t.device;
             }
-            prefault(t.dst, t.bytes); // while the DMA into the slot is still in flight
             cudaEventSynchronize(t.ready);
             memcpy(t.dst, t.src, t.bytes);
             if (t.pending->fetch_sub(1) == 1) {
@@ -279,23 +275,6 @@ class CopyPool {
                 t.cv->notify_all();
             }
         }
-    }
-    // A destination that is a fresh mapping of a new file (numpy.memmap(mode='w+')) has no pages yet: populate the
-    // range in one call instead of taking a fault per 4 KB page inside memcpy (Linux >= 5.14; a hint, errors ignored)
-    static void prefault(void *dst, size_t bytes)
-    {
-#if defined(__linux__)
-#ifndef MADV_POPULATE_WRITE
-#define MADV_POPULATE_WRITE 23
-#endif
-        static std::atomic<int> usable{1};
-        if (!usable.load(std::memory_order_relaxed)) return;
-        const uintptr_t a = (uintptr_t)dst & ~(uintptr_t)4095, e = ((uintptr_t)dst + bytes) & ~(uintptr_t)4095;
-        if (e > a && madvise((void *)a, e - a, MADV_POPULATE_WRITE) != 0 && errno == EINVAL) usable.store(0);
-#else
-        (void)dst;
-        (void)bytes;
-#endif
     }
     int n_;
     std::mutex mu_;

@@ -13,6 +13,8 @@
 #include "topo_kernels.cuh"
 
 #include <cfloat>
+#include <cstdint>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -697,29 +699,80 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
     __syncthreads();
 }
 
+#ifndef B2_MASK_MODE_DEFAULT
+#define B2_MASK_MODE_DEFAULT 2
+#endif
 #ifndef B2_MASK_KNOTS
-#define B2_MASK_KNOTS 256
+#define B2_MASK_KNOTS 1024
 #endif
 constexpr int kMaskKnots = B2_MASK_KNOTS;
+// sweep windows (mode 2): capacity of one staged window of the sorted line, in samples, per array
+#ifndef B2_MASK_WCAP
+#define B2_MASK_WCAP 1024
+#endif
+constexpr int kMaskWinCap = B2_MASK_WCAP;
 
-// Per line: (A) the line's cross-track positions go into shared memory once (min / max / fold-over test on the way); (B) only
-// lines with fold-over are co-sorted; (C, D) the 2 w + 1 samples of the regular cross-track grid are resampled with the
-// bracket search running on the shared-memory copy (two or three ~30-cycle probes instead of dependent L2 loads) and
-// their slant ranges are tested for order AS THEY ARE PRODUCED -- they are not stored: on a line whose ranges ascend
-// (no layover anywhere on it) neither layover scan can flag anything, so nothing else is needed; (E) shadow scans; (F)
-// only lines with range fold-over produce the samples a second time, now into the scratch arrays the sort / scan /
-// scatter stages work on.  DRAM traffic of a line without layover is the algorithmic 28 B in + 1 B out per pixel.
+// ---- 1-D bulk copies global -> shared through the TMA unit, completion on an mbarrier (sm_90+) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// One staged window: samples [start, start + n) of one of the three sorted arrays of the line.  The bulk copy needs a
+// 16-byte aligned source and a multiple of 16 bytes, so the window starts on an even element of its array and a last odd
+// element travels as a plain load.
+struct MaskWindow {
+    int i0, i1;       // samples of the sorted line the sweep can touch: [i0, i1]
+    int start[3];     // first staged sample of cs / lats / lons (<= i0, 16-byte aligned address)
+    int use;          // 0: the window does not fit (or does not exist): this sweep searches global memory
+};
+
+// Per line: (A) min / max / fold-over test; (B) only lines with fold-over are co-sorted; (C, D) the 2 w + 1 samples of the
+// regular cross-track grid are resampled and their slant ranges tested for order AS THEY ARE PRODUCED -- they are not
+// stored: on a line whose ranges ascend (no layover anywhere on it) neither layover scan can flag anything, so nothing
+// else is needed; (E) shadow scans; (F) only lines with range fold-over produce the samples a second time, now into the
+// scratch arrays the sort / scan / scatter stages work on.  DRAM traffic of a line without layover is the algorithmic
+// 28 B in + 1 B out per pixel.
+//
+// How a sample finds its bracket in the sorted cross-track positions (`mode`, same result in every mode):
+//   0  knot guess + galloping search in global memory (L1 / L2), lat / lon read from global memory at the bracket;
+//   1  the whole sorted line staged in shared memory (fits up to ~25 400 samples; leaves ~28 KB of L1);
+//   2  sweep windows: the 1024 samples of a sweep only touch a contiguous window of ~600 entries of the sorted line; its
+//      bounds follow from the knots, thread 0 has the TMA unit copy the NEXT sweep's window of all three arrays (cs, lat,
+//      lon) into the other half of a double buffer (cp.async.bulk + mbarrier) while the CTA works on the current one, and
+//      both the search and the lat / lon interpolation read shared memory only.
 template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kMaskBlock, 1024 / kMaskBlock)
 k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines, TopoLayers out,
-            float demmax, MaskScratch scr, int stage_cs)
+            float demmax, MaskScratch scr, int mode)
 {
-    extern __shared__ unsigned char s_dyn[]; // [stage_cs ? width doubles : 0] sorted cross-track positions, then [width] mask bytes
+    // dynamic: [mode 1: width doubles | mode 2: 2 x 3 x kMaskWinCap doubles] then [width] mask bytes
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ SR s_warp[32];                // scan scratch (largest scan state)
     __shared__ double s_mm[2];
     __shared__ double s_knot[kMaskKnots + 1];
     __shared__ double s_first[kMaskBlock / 32 + 1]; // first sample of every warp of the current sweep
     __shared__ double s_carry;                      // last sample of the previous sweep
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ MaskWindow s_win[2];
     __shared__ int s_flag;
     __shared__ LineState sL;
     const int w = C.width, ow = 2 * w + 1; // :134-135
@@ -731,11 +784,21 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
     int *rank = scr.rank + (size_t)blockIdx.x * ow;
     unsigned char *oflag = scr.oflag + (size_t)blockIdx.x * ow;
     double *s_cs = reinterpret_cast<double *>(s_dyn);
-    unsigned char *sbytes = s_dyn + (stage_cs ? (size_t)w * sizeof(double) : 0);
+    double *s_wbuf = reinterpret_cast<double *>(s_dyn); // mode 2: [2][3][kMaskWinCap]
+    const size_t head = mode == 1 ? (size_t)w * sizeof(double) : (mode == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0);
+    unsigned char *sbytes = s_dyn + head;
     unsigned int *smask = reinterpret_cast<unsigned int *>(sbytes);
     SD *s_warp_d = reinterpret_cast<SD *>(s_warp);
     SF *s_warp_f = reinterpret_cast<SF *>(s_warp);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int nsweeps = (ow + (int)blockDim.x - 1) / (int)blockDim.x;
+    unsigned bar_phase[2] = {0u, 0u};
+    if (mode == 2 && threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     for (int row = blockIdx.x; row < nlines; row += gridDim.x) {
         const int line = line0 + row;
@@ -743,12 +806,12 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double *ctrack_in = out.ctrack + (size_t)row * w;
         const double *lat_in = out.lat + (size_t)row * w, *lon_in = out.lon + (size_t)row * w;
         const float *elev = out.elev + (size_t)row * w;
-        // ---- (A) ctrack extent :730-732, "is the line free of fold-over", and the shared-memory copy, in one pass ----
+        // ---- (A) ctrack extent :730-732 and "is the line free of fold-over" in one pass ----
         double mn = INFINITY, mx = -INFINITY;
         int unsorted = 0;
         for (int i = threadIdx.x; i < w; i += blockDim.x) {
             const double v = ctrack_in[i];
-            if (stage_cs) s_cs[i] = v;
+            if (mode == 1) s_cs[i] = v;
             mn = fmin(mn, v);
             mx = fmax(mx, v);
             if (i > 0 && ctrack_in[i - 1] > v) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
@@ -777,34 +840,45 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double dctrack = (ctrackmax - ctrackmin) / (ow - 1.0);
 
         // ---- (B) stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
-        const double *cs = stage_cs ? s_cs : ctrack_in, *lats = lat_in, *lons = lon_in;
+        const double *cs = mode == 1 ? s_cs : ctrack_in, *lats = lat_in, *lons = lon_in;
         if (!ctrack_sorted) {
             block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
             block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < w; i += blockDim.x) {
                 const int r = rank[i];
                 const double v = ctrack_in[i];
-                if (stage_cs) s_cs[r] = v; // every slot is written exactly once (ranks are a permutation): no read races
+                if (mode == 1) s_cs[r] = v; // every slot is written exactly once (ranks are a permutation): no read races
                 else cs_s[r] = v;
                 lats_s[r] = lat_in[i];
                 lons_s[r] = lon_in[i];
             }
-            if (!stage_cs) cs = cs_s;
+            if (mode != 1) cs = cs_s;
             lats = lats_s;
             lons = lons_s;
+            __threadfence_block();
             __syncthreads();
         }
 
         // ---- (C) DEM surface on the regular cross-track grid :745-782 ----
         // The sorted cross-track positions are smooth but not uniform in the sample index (ground spacing changes across
         // the swath), so a straight line through the end points misses the bracket by hundreds of samples.  kMaskKnots + 1
-        // samples of the array give a piecewise linear inverse that lands within a sample or two; the search itself (and
-        // therefore the result) is unchanged.
+        // samples of the array give a piecewise linear inverse that lands within a sample or two (modes 0 / 1) and the
+        // bounds of a sweep's window (mode 2); the search itself (and therefore the result) is unchanged.
         for (int k = threadIdx.x; k <= kMaskKnots; k += blockDim.x) s_knot[k] = cs[(int)(((long long)k * (w - 1)) / kMaskKnots)];
         if (threadIdx.x == 0) s_carry = -INFINITY;
         __syncthreads();
         const double cs0 = s_knot[0], csn = s_knot[kMaskKnots];
         const double kscale = (csn > cs0) ? (double)kMaskKnots / (csn - cs0) : 0.0;
+        auto knot_index = [&](int k) -> int { return (int)(((long long)k * (w - 1)) / kMaskKnots); };
+        auto knot_below = [&](double aa) -> int { // largest k with s_knot[k] <= aa, -1 if none
+            if (!(aa >= cs0)) return -1;
+            if (aa >= csn) return kMaskKnots;
+            int k = (int)((aa - cs0) * kscale);
+            k = k < 0 ? 0 : (k > kMaskKnots - 1 ? kMaskKnots - 1 : k);
+            while (k > 0 && s_knot[k] > aa) k--;
+            while (k < kMaskKnots && s_knot[k + 1] <= aa) k++;
+            return k;
+        };
         auto knot_guess = [&](double aa) -> int {
             if (!(aa > cs0)) return 0;
             if (!(aa < csn)) return w - 1;
@@ -812,22 +886,86 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             k = k < 0 ? 0 : (k > kMaskKnots - 1 ? kMaskKnots - 1 : k);
             while (k > 0 && s_knot[k] > aa) k--;
             while (k < kMaskKnots - 1 && s_knot[k + 1] <= aa) k++;
-            const int i0 = (int)(((long long)k * (w - 1)) / kMaskKnots), i1 = (int)(((long long)(k + 1) * (w - 1)) / kMaskKnots);
+            const int i0 = knot_index(k), i1 = knot_index(k + 1);
             const double a = s_knot[k], b = s_knot[k + 1];
             const double f = (b > a) ? (aa - a) / (b - a) : 0.0;
             return i0 + (int)(f * (double)(i1 - i0));
         };
-        auto sample = [&](int p) -> double { // slant range of grid sample p (0-based), :747-782
-            const double aa = ctrackmin + ((p + 1) - 1) * dctrack;
+        auto grid_pos = [&](int p) -> double { return ctrackmin + ((p + 1) - 1) * dctrack; }; // :747
+        auto sample_global = [&](int p) -> double { // slant range of grid sample p (0-based), :747-782
+            const double aa = grid_pos(p);
             const int it = ref_search_result(search_count_le([&](int m) { return cs[m]; }, w, aa, knot_guess(aa)), w);
             return mask_resample<METHOD, REF>(C, sL, cs, lats, lons, it, aa);
         };
+        // mode 2: window of sweep `sw` -- thread 0 only.  Everything at or before sample i0 is <= the sweep's first grid
+        // position, everything at or after i1 is > its last one (or i0 / i1 is an end of the line), so the bracket of every
+        // sample of the sweep lies inside [i0, i1].
+        auto stage_window = [&](int sw) {
+            MaskWindow W;
+            const int base = sw * (int)blockDim.x;
+            const int plast = base + (int)blockDim.x - 1 < ow - 1 ? base + (int)blockDim.x - 1 : ow - 1;
+            const int ka = knot_below(grid_pos(base)), kb = knot_below(grid_pos(plast)) + 1;
+            W.i0 = ka < 0 ? 0 : knot_index(ka < kMaskKnots ? ka : kMaskKnots);
+            W.i1 = kb > kMaskKnots ? w - 1 : knot_index(kb);
+            if (W.i0 > 0) W.i0 -= 1; // the bracket's lower sample may be the one just below (search result clamped to w - 1)
+            if (W.i1 < 1) W.i1 = 1;  // ... and its upper sample is never below the second one (search result clamped to 1)
+            const double *src[3] = {cs, lats, lons};
+            W.use = 1;
+            unsigned bytes = 0;
+            int nfull[3];
+            for (int a = 0; a < 3; a++) {
+                const int off = (int)((reinterpret_cast<uintptr_t>(src[a] + W.i0) >> 3) & 1);
+                W.start[a] = W.i0 - off;
+                const int n = W.i1 - W.start[a] + 1;
+                if (W.start[a] < 0 || n > kMaskWinCap) W.use = 0;
+                nfull[a] = n & ~1;
+                bytes += (unsigned)nfull[a] * 8u;
+            }
+            s_win[sw & 1] = W;
+            if (!W.use) return;
+            double *dst = s_wbuf + (size_t)(sw & 1) * 3 * kMaskWinCap;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic accesses of the buffer are done
+            mbar_arrive_expect_tx(&s_bar[sw & 1], bytes);
+            for (int a = 0; a < 3; a++) {
+                const int n = W.i1 - W.start[a] + 1;
+                if (nfull[a]) bulk_g2s(dst + (size_t)a * kMaskWinCap, src[a] + W.start[a], (unsigned)nfull[a] * 8u, &s_bar[sw & 1]);
+                if (n & 1) dst[(size_t)a * kMaskWinCap + n - 1] = src[a][W.start[a] + n - 1]; // visible after the next barrier
+            }
+        };
+        if (mode == 2) {
+            if (threadIdx.x == 0) stage_window(0);
+            __syncthreads();
+        }
         // ---- (D) first sweep: is the slant range ascending over the grid?  Every sample is compared with its
         // predecessor: within a warp through a shuffle, across warps through s_first, across sweeps through s_carry.
         int orng_unsorted = 0;
-        for (int base = 0; base < ow; base += blockDim.x) {
+        for (int sw = 0; sw < nsweeps; sw++) {
+            const int base = sw * (int)blockDim.x;
             const int p = base + (int)threadIdx.x;
-            const double val = p < ow ? sample(p) : INFINITY; // +inf: never smaller than its predecessor
+            double val = INFINITY; // +inf beyond the grid: never smaller than its predecessor
+            if (mode == 2) {
+                // the next sweep's window travels while this one is worked on (its buffer was last read two sweeps ago)
+                if (threadIdx.x == 0 && sw + 1 < nsweeps) stage_window(sw + 1);
+                const MaskWindow W = s_win[sw & 1];
+                if (W.use) {
+                    mbar_wait(&s_bar[sw & 1], bar_phase[sw & 1]);
+                    bar_phase[sw & 1] ^= 1u;
+                    if (p < ow) {
+                        const double *wb = s_wbuf + (size_t)(sw & 1) * 3 * kMaskWinCap;
+                        const double *wcs = wb - W.start[0], *wla = wb + kMaskWinCap - W.start[1], *wlo = wb + 2 * kMaskWinCap - W.start[2];
+                        const double aa = grid_pos(p);
+                        const int L = W.i1 - W.i0 + 1;
+                        const double a = wcs[W.i0], b = wcs[W.i1];
+                        const int guess = (b > a) ? (int)((aa - a) / (b - a) * (double)(L - 1)) : 0;
+                        const int cnt = W.i0 + search_count_le([&](int m) { return wcs[W.i0 + m]; }, L, aa, guess);
+                        val = mask_resample<METHOD, REF>(C, sL, wcs, wla, wlo, ref_search_result(cnt, w), aa);
+                    }
+                } else if (p < ow) {
+                    val = sample_global(p);
+                }
+            } else if (p < ow) {
+                val = sample_global(p);
+            }
             const double prev = __shfl_up_sync(0xffffffffu, val, 1);
             if (lane != 0 && prev > val) orng_unsorted = 1;
             if (lane == 0) s_first[wid] = val;
@@ -849,7 +987,7 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         // ctrack increases with the sample index by construction, so when the slant ranges are already ascending the
         // sorted ctrack is ascending too and neither layover scan can flag anything: the line is done.
         if (!orng_sorted_already) {
-            for (int p = threadIdx.x; p < ow; p += blockDim.x) orng[p] = sample(p); // the same values, now kept
+            for (int p = threadIdx.x; p < ow; p += blockDim.x) orng[p] = sample_global(p); // the same values, now kept
             __syncthreads();
             block_prefix_max_suffix_min(orng, ow, pm, sm, s_warp_d);
             block_stable_ranks(orng, ow, pm, sm, rank, &s_flag);
@@ -983,19 +1121,18 @@ static void launch_mask_m(const TopoConst &C, const LineState *states, int line0
 int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out, float demmax,
                      const MaskScratch &scr, int grid, cudaStream_t s)
 {
-    // the line's sorted cross-track positions live in shared memory when they fit next to the mask bytes (227 KB per CTA on
-    // sm_100a, ~3.5 KB of it static): widths up to ~25 400 samples; wider swaths search the global copy through L1 / L2
+    // how a sample finds its bracket in the sorted line (see k_topo_mask): sweep windows through the TMA unit by default;
+    // B200_MASK_MODE = 0 | 1 | 2 selects another one for A/B measurements (same results in every mode)
+    static const int forced = [] {
+        const char *e = getenv("B200_MASK_MODE");
+        return e ? atoi(e) : -1;
+    }();
     const size_t bytes_mask = (size_t)((C.width + 3) / 4) * 4, bytes_cs = (size_t)C.width * sizeof(double);
-    const size_t budget = 227u * 1024u - 4096u;
-    const int stage_cs = (bytes_cs + bytes_mask <= budget) ? 1 : 0;
-#ifdef B2_MASK_NO_STAGE
-    const size_t smem = bytes_mask;
-    const int stage = 0;
-    (void)stage_cs;
-#else
-    const size_t smem = bytes_mask + (stage_cs ? bytes_cs : 0);
-    const int stage = stage_cs;
-#endif
+    const size_t budget = 227u * 1024u - 12288u; // static shared memory of the kernel: knots, scan scratch, line state
+    int stage = forced >= 0 && forced <= 2 ? forced : B2_MASK_MODE_DEFAULT;
+    if (stage == 1 && bytes_cs + bytes_mask > budget) stage = 2;
+    if (stage == 2 && (size_t)6 * kMaskWinCap * sizeof(double) + bytes_mask > budget) stage = 0;
+    const size_t smem = bytes_mask + (stage == 1 ? bytes_cs : (stage == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0));
     switch (C.method) {
     case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
     case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;

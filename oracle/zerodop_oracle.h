@@ -7,16 +7,20 @@
  * --impl reference).  Nothing under isce2_b200/ may include, link or call it.
  *
  * Every function cites the reference file:line it restates (paths relative to
- * /root/reference).  Pinning status: primitives are pinned against the
- * reference's own known answers and against the reference C sources compiled
- * unchanged into oracle/_ref (orbit.c, orbitHermite.c, poly1d.c, poly2d.c,
- * linalg3.c); whole-path topo/geo2rdr output is pinned against golden vectors
- * generated by importing the reference's own Python Orbit.rdr2geo/geo2rdr
- * (tests/golden/make_golden.py), and whole images are held against the defining
- * equations of the range-Doppler geometry, the geometric definitions of the two
- * mask bits and independent implementations of the interpolators
- * (tests/test_oracle_image_properties_cpu.py).  The Fortran itself cannot be
- * compiled in this image (no gfortran), see DESIGN.md.
+ * /root/reference).  Pinning status (DESIGN.md section 2 has the table): the
+ * Fortran itself cannot be compiled in this image (no gfortran); what the
+ * reference ships in C / C++ for the same path is compiled UNCHANGED into
+ * oracle/_ref and the restatement is held to it bit for bit -- orbit.c,
+ * orbitHermite.c, poly1d.c, poly2d.c, linalg3.c (tests/test_oracle_pins.py) and
+ * the reference's own C++ restatement of topozero / geo2rdr, CPU branches
+ * (GPUtopozero/src, GPUgeo2rdr/src: DEM interpolators, geometry primitives,
+ * whole-image topo -- lat/lon/hgt/los/local incidence/shadow bit -- and
+ * whole-image geo2rdr, tests/test_oracle_cpp_pins.py).  Restatement-only, because
+ * the C++ departs from the Fortran there: the layover bit of the mask, inc
+ * channel 1 (psi), the bicubic interpolator, binarysearch; those are held
+ * against the defining equations, the geometric definitions of the mask bits
+ * and independent implementations (tests/test_oracle_image_properties_cpu.py)
+ * and golden vectors of the reference's own Python (tests/golden/).
  */
 #ifndef ZERODOP_ORACLE_H
 #define ZERODOP_ORACLE_H
