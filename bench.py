@@ -877,6 +877,7 @@ def measure_component(args, ranks, capi, dev, name, lines=None):
     # directory by the same number of host threads, no GPU involved (page allocation + zeroing + copy of the page cache)
     try:
         out["file_floor"] = file_write_floor(base, int(out.get("bytes_written") or need))
+        out["file_floor_pwrite"] = file_write_floor(base, int(out.get("bytes_written") or need), how="pwrite")
     except Exception as e:  # noqa: BLE001
         out["file_floor"] = {"error": f"{type(e).__name__}: {e}"}
     t = float(np.median(times[1:])) if len(times) > 1 else times[0]
@@ -884,9 +885,10 @@ def measure_component(args, ranks, capi, dev, name, lines=None):
     return out
 
 
-def file_write_floor(base, nbytes, nfiles=8, threads=None):
-    """Seconds to store nbytes into nfiles fresh numpy.memmap(mode='w+') files under `base` from host memory with `threads`
-    threads (numpy releases the GIL in the copies), munmap included -- what any writer of new rasters pays."""
+def file_write_floor(base, nbytes, nfiles=8, threads=None, how="mmap"):
+    """Seconds to store nbytes into nfiles fresh files under `base` from host memory with `threads` threads -- through
+    numpy.memmap(mode='w+') stores (numpy releases the GIL in the copies; munmap included) or through os.pwrite -- what
+    any writer of new rasters pays."""
     import shutil
     import tempfile
     import threading as th
@@ -896,25 +898,35 @@ def file_write_floor(base, nbytes, nfiles=8, threads=None):
     d = tempfile.mkdtemp(prefix="b200_floor_", dir=base)
     try:
         t0 = time.perf_counter()
-        maps = [np.memmap(os.path.join(d, f"f{i}.bin"), dtype=np.uint8, mode="w+", shape=(per,)) for i in range(nfiles)]
+        if how == "mmap":
+            maps = [np.memmap(os.path.join(d, f"f{i}.bin"), dtype=np.uint8, mode="w+", shape=(per,)) for i in range(nfiles)]
+        else:
+            maps = [os.open(os.path.join(d, f"f{i}.bin"), os.O_CREAT | os.O_WRONLY, 0o644) for i in range(nfiles)]
         jobs = [(m, o) for m in maps for o in range(0, per, src.size)]
 
         def work(k):
             for m, o in jobs[k::threads]:
                 n = min(src.size, per - o)
-                m[o:o + n] = src[:n]
+                if how == "mmap":
+                    m[o:o + n] = src[:n]
+                else:
+                    os.pwrite(m, memoryview(src)[:n], o)
 
         ts = [th.Thread(target=work, args=(k,)) for k in range(threads)]
         for t in ts:
             t.start()
         for t in ts:
             t.join()
+        if how != "mmap":
+            for fd in maps:
+                os.close(fd)
         del maps, jobs
         dt = time.perf_counter() - t0
     finally:
         shutil.rmtree(d, ignore_errors=True)
     return {"seconds": dt, "GBps": per * nfiles / dt / 1e9, "threads": threads, "bytes": per * nfiles,
-            "what": "numpy stores into fresh memory maps of new files in the same directory, no GPU involved"}
+            "what": ("numpy stores into fresh memory maps of" if how == "mmap" else "os.pwrite into") +
+                    " new files in the same directory, no GPU involved"}
 
 
 def run_b200(args, ranks):

@@ -1026,6 +1026,18 @@ int geo_prepare(b200_geo_plan *pl, const b200_geo_params &p, const b200_orbit *o
     C.acc_mid = Vec3{mid.acc[0], mid.acc[1], mid.acc[2]};
 
     R.use_poly = (p.orbit_method == B200_ORBIT_HERMITE || p.orbit_method == B200_ORBIT_LEGENDRE);
+    if (R.use_poly) {
+        // The reference marks a pixel invalid as soon as ANY of its 9-11 fixed-point iterates leaves the state-vector span
+        // (geo2rdr.f90:287-291).  Its iterates approach the solution from tmid with a ratio of ~0.1 per step, so those of a
+        // pixel that ends inside the acquisition window stay within ~0.1 x the half-duration of it: when the state
+        // vectors cover the window with the margin below, the span test can only hit pixels the bounds test (:308-316)
+        // rejects anyway and the Newton kernel (which sees other iterates) decides validity identically.  When they do
+        // not -- an orbit cut within a fraction of a second of the scene -- the kernel that performs the reference's own
+        // iteration runs instead.
+        const double half = 0.5 * (C.tend - C.tstart);
+        const double margin = 0.25 * half + 0.05;
+        if (orbit->t[0] > C.tstart - margin || orbit->t[orbit->nvec - 1] < C.tend + margin) R.use_poly = false;
+    }
     if (R.use_poly) { // Newton solve on per-window orbit polynomials (orbit_poly.h)
         HostOrbitPoly hp;
         if (!build_orbit_poly(p.orbit_method, orbit->nvec, orbit->t, orbit->pos, orbit->vel, hp))

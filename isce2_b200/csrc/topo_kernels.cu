@@ -753,7 +753,8 @@ struct MaskWindow {
 // 28 B in + 1 B out per pixel.
 //
 // How a sample finds its bracket in the sorted cross-track positions (`mode`, same result in every mode):
-//   0  knot guess + galloping search in global memory (L1 / L2), lat / lon read from global memory at the bracket;
+//   0  warp-sequential walk: every warp owns a contiguous run of the grid; the bracket of its previous 32 samples is the
+//      guess for the next 32, probes and lat / lon reads hit the cache lines it has just used; no barrier in the loop;
 //   1  the whole sorted line staged in shared memory (fits up to ~25 400 samples; leaves ~28 KB of L1);
 //   2  sweep windows: the 1024 samples of a sweep only touch a contiguous window of ~600 entries of the sorted line; its
 //      bounds follow from the knots, thread 0 has the TMA unit copy the NEXT sweep's window of all three arrays (cs, lat,
@@ -936,10 +937,41 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
             if (threadIdx.x == 0) stage_window(0);
             __syncthreads();
         }
-        // ---- (D) first sweep: is the slant range ascending over the grid?  Every sample is compared with its
-        // predecessor: within a warp through a shuffle, across warps through s_first, across sweeps through s_carry.
+        // ---- (D) first sweep: is the slant range ascending over the grid?  Every sample is compared with its predecessor.
         int orng_unsorted = 0;
-        for (int sw = 0; sw < nsweeps; sw++) {
+        if (mode == 0) {
+            // Warp-sequential walk: every warp owns one contiguous run of the grid and walks it 32 samples at a time, so
+            // (a) the bracket of the previous group is a one-probe guess for the next one and every probe hits the cache
+            // lines the warp has just used, (b) the predecessor of a sample lives in the neighbouring lane or in the
+            // warp's own previous group: no barrier inside the loop (the runs' end points meet once, afterwards).
+            const int chunk = (((ow + nwarps - 1) / nwarps) + 31) & ~31;
+            const int pbeg = wid * chunk, pend = pbeg + chunk < ow ? pbeg + chunk : ow;
+            double carry = -INFINITY, lastv = -INFINITY;
+            int cnt_prev = -1;
+            if (lane == 0) s_first[wid] = INFINITY;
+            for (int g0 = pbeg; g0 < pend; g0 += 32) {
+                const int p = g0 + lane;
+                double val = INFINITY; // +inf beyond the run: never smaller than its predecessor
+                int cnt = 0;
+                if (p < pend) {
+                    const double aa = grid_pos(p);
+                    const int guess = cnt_prev >= 0 ? cnt_prev + ((lane + 1) >> 1) : knot_guess(aa);
+                    cnt = search_count_le([&](int m) { return cs[m]; }, w, aa, guess);
+                    val = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, ref_search_result(cnt, w), aa);
+                }
+                double prev = __shfl_up_sync(0xffffffffu, val, 1);
+                if (lane == 0) prev = carry;
+                if (prev > val) orng_unsorted = 1;
+                if (g0 == pbeg && lane == 0) s_first[wid] = val;
+                if (p == pend - 1) lastv = val;
+                carry = __shfl_sync(0xffffffffu, val, 31);
+                cnt_prev = __shfl_sync(0xffffffffu, cnt, 31);
+            }
+            lastv = warp_max(lastv); // one lane holds the run's last sample, the others -inf
+            __syncthreads();
+            if (lane == 0 && wid + 1 < nwarps && lastv > s_first[wid + 1]) orng_unsorted = 1;
+        }
+        for (int sw = 0; mode != 0 && sw < nsweeps; sw++) {
             const int base = sw * (int)blockDim.x;
             const int p = base + (int)threadIdx.x;
             double val = INFINITY; // +inf beyond the grid: never smaller than its predecessor

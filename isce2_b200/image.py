@@ -161,10 +161,9 @@ class Image:
         return c
 
     def finalizeImage(self):
-        if self._mmap is not None:
-            if hasattr(self._mmap, "flush") and not self.accessMode.startswith("r"):
-                self._mmap.flush()
-            self._mmap = None
+        # dropping the map is what closing the reference's ofstream is: dirty pages reach the file through the page cache;
+        # no msync (it would force synchronous write-back of the whole raster on a disk file system)
+        self._mmap = None
 
     # ---- metadata ----
     def _props(self):

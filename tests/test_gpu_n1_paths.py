@@ -120,6 +120,7 @@ def test_geo2rdr_component_with_poly2d_lat_lon(tmp_path):
         p = Poly2D()
         p.initPoly(rangeOrder=1, azimuthOrder=1, coeffs=[[co[0], co[1]], [co[2], 0.0]])
         p.setMeanRange(cols / 2); p.setNormRange(float(cols)); p.setMeanAzimuth(rows / 2); p.setNormAzimuth(float(rows))
+        p.setWidth(cols); p.setLength(rows)  # Geo2rdr.setDefaults compares them with the height image (Geo2rdr.py:283-289)
         polys[k] = p
     hgt_path = str(tmp_path / "hgt.rdr")
     c["hgt"].tofile(hgt_path)
