@@ -647,6 +647,14 @@ B2_HD double eval_poly2d(const Poly2dDev &p, double azi, double rng)
 {
     double value = 0.0;
     double xval = div_r(rng - p.mean_range, p.norm_range, p.inv_norm_range);
+    if (p.azimuth_order == 0) {
+        // one row (slant range, range-only Doppler): scaley stays 1, and scalex * 1.0 * c == scalex * c, 1.0 * xval == xval
+        // exactly, so this is the same sequence of roundings without the bookkeeping of the general loop
+        value = value + p.c[0];
+        double scalex = xval;
+        for (int j = 1; j <= p.range_order; j++, scalex *= xval) value += scalex * p.c[j];
+        return value;
+    }
     double yval = div_r(azi - p.mean_azimuth, p.norm_azimuth, p.inv_norm_azimuth);
     double scaley = 1.0;
     for (int i = 0; i <= p.azimuth_order; i++, scaley *= yval) {

@@ -55,6 +55,27 @@ __device__ __forceinline__ int warp_sum(int v)
     return v;
 }
 
+// Running bounding box of the block (:712-715).  Almost no pixel extends a box that the first lines have opened, so every
+// thread first holds its own point against the box as it stands (four broadcast loads that stay in L2: a stale copy is
+// only ever LESS extreme than the truth, so the test errs on the side of updating) and a warp goes through the reduction
+// and the four contended atomics only when one of its pixels pushes an edge.
+__device__ __forceinline__ void bbox_update(TopoStats *stats, bool have, double mnlat, double mxlat, double mnlon, double mxlon)
+{
+    bool push = false;
+    if (have) {
+        const long long a = __ldcg(&stats->min_lat), b = __ldcg(&stats->max_lat), c = __ldcg(&stats->min_lon), d = __ldcg(&stats->max_lon);
+        push = order_key(mnlat) < a || order_key(mxlat) > b || order_key(mnlon) < c || order_key(mxlon) > d;
+    }
+    if (!__any_sync(0xffffffffu, push)) return;
+    mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&stats->min_lat, order_key(mnlat));
+        atomicMax(&stats->max_lat, order_key(mxlat));
+        atomicMin(&stats->min_lon, order_key(mnlon));
+        atomicMax(&stats->max_lon, order_key(mxlon));
+    }
+}
+
 __device__ __forceinline__ double line_time(const TopoConst &C, int line0based)
 {
     // tline = t0 + Nazlooks*(line - 1.0d0)/prf with the reference's 1-based line (topozero.f90:371)
@@ -422,14 +443,7 @@ k_topo_final(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
         mnlat = mxlat = R.lat;
         mnlon = mxlon = R.lon;
     }
-    // bounding box (:712-715)
-    mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&stats->min_lat, order_key(mnlat));
-        atomicMax(&stats->max_lat, order_key(mxlat));
-        atomicMin(&stats->min_lon, order_key(mnlon));
-        atomicMax(&stats->max_lon, order_key(mxlon));
-    }
+    bbox_update(stats, pix < C.width, mnlat, mxlat, mnlon, mxlon);
 }
 
 // k_topo_fused: solve + final pass in one kernel.  Used for the light interpolators (bilinear, nearest), whose whole
@@ -484,14 +498,10 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
         mnlat = fmin(mnlat, R.lat); mxlat = fmax(mxlat, R.lat);
         mnlon = fmin(mnlon, R.lon); mxlon = fmax(mxlon, R.lon);
     }
-    mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
+    bbox_update(stats, lane < strip_n, mnlat, mxlat, mnlon, mxlon);
     conv = warp_sum(conv);
     iters = warp_sum(iters);
     if (lane == 0 && strip_n > 0) {
-        atomicMin(&stats->min_lat, order_key(mnlat));
-        atomicMax(&stats->max_lat, order_key(mxlat));
-        atomicMin(&stats->min_lon, order_key(mnlon));
-        atomicMax(&stats->max_lon, order_key(mxlon));
         if (conv) atomicAdd(&stats->converged, (unsigned long long)conv);
         atomicAdd(&stats->iterations, (unsigned long long)iters);
     }
@@ -700,7 +710,7 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
 }
 
 #ifndef B2_MASK_MODE_DEFAULT
-#define B2_MASK_MODE_DEFAULT 2
+#define B2_MASK_MODE_DEFAULT 0
 #endif
 #ifndef B2_MASK_KNOTS
 #define B2_MASK_KNOTS 1024
@@ -755,7 +765,8 @@ struct MaskWindow {
 // How a sample finds its bracket in the sorted cross-track positions (`mode`, same result in every mode):
 //   0  warp-sequential walk: every warp owns a contiguous run of the grid; the bracket of its previous 32 samples is the
 //      guess for the next 32, probes and lat / lon reads hit the cache lines it has just used; no barrier in the loop;
-//   1  the whole sorted line staged in shared memory (fits up to ~25 400 samples; leaves ~28 KB of L1);
+//      (a third variant, the whole sorted line in shared memory, left ~28 KB of L1 for the DEM taps and ran the C2 line
+//      pass in 34.3 ms instead of 23.8: removed);
 //   2  sweep windows: the 1024 samples of a sweep only touch a contiguous window of ~600 entries of the sorted line; its
 //      bounds follow from the knots, thread 0 has the TMA unit copy the NEXT sweep's window of all three arrays (cs, lat,
 //      lon) into the other half of a double buffer (cp.async.bulk + mbarrier) while the CTA works on the current one, and
@@ -763,9 +774,9 @@ struct MaskWindow {
 template <int METHOD, bool REF>
 __global__ void __launch_bounds__(kMaskBlock, 1024 / kMaskBlock)
 k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ states, int line0, int nlines, TopoLayers out,
-            float demmax, MaskScratch scr, int mode)
+            float demmax, MaskScratch scr, int mode, int stage_elev)
 {
-    // dynamic: [mode 1: width doubles | mode 2: 2 x 3 x kMaskWinCap doubles] then [width] mask bytes
+    // dynamic: [mode 2: 2 x 3 x kMaskWinCap doubles] then [width] mask bytes, then (stage_elev) [width] floats
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ SR s_warp[32];                // scan scratch (largest scan state)
     __shared__ double s_mm[2];
@@ -784,9 +795,8 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
     double *pm = scr.pm + (size_t)blockIdx.x * ow, *sm = scr.sm + (size_t)blockIdx.x * ow;
     int *rank = scr.rank + (size_t)blockIdx.x * ow;
     unsigned char *oflag = scr.oflag + (size_t)blockIdx.x * ow;
-    double *s_cs = reinterpret_cast<double *>(s_dyn);
     double *s_wbuf = reinterpret_cast<double *>(s_dyn); // mode 2: [2][3][kMaskWinCap]
-    const size_t head = mode == 1 ? (size_t)w * sizeof(double) : (mode == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0);
+    const size_t head = mode == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0;
     unsigned char *sbytes = s_dyn + head;
     unsigned int *smask = reinterpret_cast<unsigned int *>(sbytes);
     SD *s_warp_d = reinterpret_cast<SD *>(s_warp);
@@ -810,9 +820,9 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         // ---- (A) ctrack extent :730-732 and "is the line free of fold-over" in one pass ----
         double mn = INFINITY, mx = -INFINITY;
         int unsorted = 0;
-        for (int i = threadIdx.x; i < w; i += blockDim.x) {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < w; i += blockDim.x) { // several loads in flight per thread: this pass is pure latency
             const double v = ctrack_in[i];
-            if (mode == 1) s_cs[i] = v;
             mn = fmin(mn, v);
             mx = fmax(mx, v);
             if (i > 0 && ctrack_in[i - 1] > v) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
@@ -841,19 +851,17 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const double dctrack = (ctrackmax - ctrackmin) / (ow - 1.0);
 
         // ---- (B) stable co-sort (ctrack; lat, lon) :735: nothing to do on a line without fold-over ----
-        const double *cs = mode == 1 ? s_cs : ctrack_in, *lats = lat_in, *lons = lon_in;
+        const double *cs = ctrack_in, *lats = lat_in, *lons = lon_in;
         if (!ctrack_sorted) {
             block_prefix_max_suffix_min(ctrack_in, w, pm, sm, s_warp_d);
             block_stable_ranks(ctrack_in, w, pm, sm, rank, &s_flag);
             for (int i = threadIdx.x; i < w; i += blockDim.x) {
                 const int r = rank[i];
-                const double v = ctrack_in[i];
-                if (mode == 1) s_cs[r] = v; // every slot is written exactly once (ranks are a permutation): no read races
-                else cs_s[r] = v;
+                cs_s[r] = ctrack_in[i];
                 lats_s[r] = lat_in[i];
                 lons_s[r] = lon_in[i];
             }
-            if (mode != 1) cs = cs_s;
+            cs = cs_s;
             lats = lats_s;
             lons = lons_s;
             __threadfence_block();
@@ -995,8 +1003,6 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
                 } else if (p < ow) {
                     val = sample_global(p);
                 }
-            } else if (p < ow) {
-                val = sample_global(p);
             }
             const double prev = __shfl_up_sync(0xffffffffu, val, 1);
             if (lane != 0 && prev > val) orng_unsorted = 1;
@@ -1010,10 +1016,19 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         const bool orng_sorted_already = __syncthreads_or(orng_unsorted) == 0;
 
         // ---- (E) shadow (:791-809) on float32 elevang in pixel order ----
+        // the scans give every thread a contiguous chunk of the line (a stride of ~25 samples between neighbouring lanes):
+        // the line is brought into shared memory with coalesced loads first when it fits behind the mask bytes
+        const float *elev_s = elev;
+        if (stage_elev) {
+            float *se = reinterpret_cast<float *>(sbytes + (((size_t)w + 15) & ~(size_t)15));
+#pragma unroll 4
+            for (int i = threadIdx.x; i < w; i += blockDim.x) se[i] = elev[i];
+            elev_s = se;
+        }
         for (int i = threadIdx.x; i < (w + 3) / 4; i += blockDim.x) smask[i] = 0u;
         __syncthreads();
-        block_prefix_max_flags<float>(elev, w, w, sbytes, (unsigned char)1, s_warp_f, OpMaxF());
-        block_suffix_min_flags<float>(elev, w, nullptr, 0, sbytes, (unsigned char)1, s_warp);
+        block_prefix_max_flags<float>(elev_s, w, w, sbytes, (unsigned char)1, s_warp_f, OpMaxF());
+        block_suffix_min_flags<float>(elev_s, w, nullptr, 0, sbytes, (unsigned char)1, s_warp);
 
         // ---- (F) stable co-sort (orng; ctrack) :787 and layover (:834-852) on the range-sorted ctrack ----
         // ctrack increases with the sample index by construction, so when the slant ranges are already ascending the
@@ -1139,39 +1154,47 @@ int mask_grid_size(int nlines)
 
 template <int METHOD>
 static void launch_mask_m(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out,
-                          float demmax, const MaskScratch &scr, int grid, size_t smem, int stage_cs, cudaStream_t s)
+                          float demmax, const MaskScratch &scr, int grid, size_t smem, int mode, int stage_elev, cudaStream_t s)
 {
     if (C.ref.use_ref) {
         cudaFuncSetAttribute(k_topo_mask<METHOD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<METHOD, true><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, stage_cs);
+        k_topo_mask<METHOD, true><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, mode, stage_elev);
     } else {
         cudaFuncSetAttribute(k_topo_mask<METHOD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_topo_mask<METHOD, false><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, stage_cs);
+        k_topo_mask<METHOD, false><<<grid, kMaskBlock, smem, s>>>(C, states, line0, nlines, out, demmax, scr, mode, stage_elev);
     }
 }
 
 int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int nlines, const TopoLayers &out, float demmax,
                      const MaskScratch &scr, int grid, cudaStream_t s)
 {
-    // how a sample finds its bracket in the sorted line (see k_topo_mask): sweep windows through the TMA unit by default;
-    // B200_MASK_MODE = 0 | 1 | 2 selects another one for A/B measurements (same results in every mode)
+    // how a sample finds its bracket in the sorted line (see k_topo_mask): warp-sequential walk by default; B200_MASK_MODE=2
+    // selects the TMA-staged sweep windows for A/B measurements (same results in both modes; measured on C2: 23.9 vs 29.9 ms)
     static const int forced = [] {
         const char *e = getenv("B200_MASK_MODE");
         return e ? atoi(e) : -1;
     }();
-    const size_t bytes_mask = (size_t)((C.width + 3) / 4) * 4, bytes_cs = (size_t)C.width * sizeof(double);
+    const size_t bytes_mask = (size_t)((C.width + 3) / 4) * 4;
     const size_t budget = 227u * 1024u - 12288u; // static shared memory of the kernel: knots, scan scratch, line state
-    int stage = forced >= 0 && forced <= 2 ? forced : B2_MASK_MODE_DEFAULT;
-    if (stage == 1 && bytes_cs + bytes_mask > budget) stage = 2;
+    int stage = (forced == 0 || forced == 2) ? forced : B2_MASK_MODE_DEFAULT;
     if (stage == 2 && (size_t)6 * kMaskWinCap * sizeof(double) + bytes_mask > budget) stage = 0;
-    const size_t smem = bytes_mask + (stage == 1 ? bytes_cs : (stage == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0));
+    size_t smem = bytes_mask + (stage == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0);
+    // the elevation line of the shadow scans (float32) behind the mask bytes when the whole stays under 160 KB, so that the
+    // L1 keeps ~90 KB for the DEM taps of the resampling pass (B200_MASK_ELEV_KB overrides the limit; 0 = never)
+    static const size_t elev_limit = [] {
+        const char *e = getenv("B200_MASK_ELEV_KB");
+        return (size_t)(e ? atoi(e) : 160) * 1024u;
+    }();
+    const size_t bytes_elev = (((size_t)C.width + 15) & ~(size_t)15) - bytes_mask + (size_t)C.width * sizeof(float) + 16;
+    const int stage_elev = (smem + bytes_elev <= elev_limit) ? 1 : 0;
+    if (stage_elev) smem += bytes_elev;
     switch (C.method) {
-    case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
-    case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
-    case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
-    case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
-    case 4: launch_mask_m<4>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
-    case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, s); break;
+    case 0: launch_mask_m<0>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
+    case 1: launch_mask_m<1>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
+    case 2: launch_mask_m<2>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
+    case 3: launch_mask_m<3>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
+    case 4: launch_mask_m<4>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
+    case 5: launch_mask_m<5>(C, states, line0, nlines, out, demmax, scr, grid, smem, stage, stage_elev, s); break;
     default: return -1;
     }
     return 0;

@@ -29,9 +29,13 @@ from tests.test_gpu_parity import _assert_topo
 pytestmark = pytest.mark.gpu
 
 
-def _same_orbit_kwargs(sc, dt0=0.0, dr0=0.0):
-    return dict(orbit_t=sc.orbit_t, orbit_pos=sc.orbit_pos, orbit_vel=sc.orbit_vel, length=sc.length, width=sc.width,
-                r0=sc.r0 + dr0, dr=sc.dr, prf=sc.prf, t0=sc.t0 + dt0, wvl=sc.wvl, side=sc.side)
+def _same_orbit_kwargs(sc, dt0=0.0, dr0=0.0, pad=0):
+    """geo2rdr window of the scene's own acquisition; pad > 0 widens it by that many lines / samples on every side, so
+    that no pixel of the scene sits ON an edge of the window (where the strict bounds tests of geo2rdr.f90:308-316 are
+    decided in the last bit)."""
+    return dict(orbit_t=sc.orbit_t, orbit_pos=sc.orbit_pos, orbit_vel=sc.orbit_vel, length=sc.length + 2 * pad,
+                width=sc.width + 2 * pad, r0=sc.r0 + dr0 - pad * sc.dr, dr=sc.dr, prf=sc.prf, t0=sc.t0 + dt0 - pad / sc.prf,
+                wvl=sc.wvl, side=sc.side)
 
 
 def test_geo2rdr_sch_orbit():
@@ -67,10 +71,10 @@ def test_topo_azimuth_varying_doppler_alone_and_fused():
                           delta_lon=sc.delta_lon, length=sc.length, width=sc.width, prf=sc.prf, t0=sc.t0, wvl=sc.wvl,
                           side=sc.side, peg_heading=sc.peg_heading, a=sc.a, e2=sc.e2, dem_method="BIQUINTIC",
                           orbit_method="LEGENDRE")
-    kw = _same_orbit_kwargs(sc)
+    kw = _same_orbit_kwargs(sc, pad=3)
     dop1d = tuple(x / sc.prf for x in sc.doppler_coeffs[0])
-    job = dict(params=_capi.geo_params(length=sc.length, width=sc.width, dem_shape=(sc.length, sc.width), r0=sc.r0, dr=sc.dr,
-                                       prf=sc.prf, t0=sc.t0, wvl=sc.wvl, side=sc.side, orbit_method="LEGENDRE"),
+    job = dict(params=_capi.geo_params(length=kw["length"], width=kw["width"], dem_shape=(sc.length, sc.width), r0=kw["r0"],
+                                       dr=sc.dr, prf=sc.prf, t0=kw["t0"], wvl=sc.wvl, side=sc.side, orbit_method="LEGENDRE"),
                orbit=(sc.orbit_t, sc.orbit_pos, sc.orbit_vel), doppler=(dop1d, 0.0, 1.0), want=("azoff", "rgoff"))
     ft, fg = _capi.topo_geo2rdr_run(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [job],
                                     [[sc.r0, sc.dr]], want_los=True, want_inc=True, want_mask=True)
@@ -78,7 +82,7 @@ def test_topo_azimuth_varying_doppler_alone_and_fused():
         assert np.array_equal(ft[k], g[k], equal_nan=True), k
     o = orc.geo2rdr(lat=c["lat"], lon=c["lon"], hgt=c["hgt"], orbit_method="LEGENDRE", doppler_coeffs=dop1d, **kw)
     st = pu.compare_geo(fg[0], o)
-    assert st["valid"]["gpu"] == st["valid"]["cpu"]
+    assert st["valid"]["gpu"] == st["valid"]["cpu"] == sc.length * sc.width
     assert st["azoff"]["max"] < pu.TOL_OFFSET_PX and st["rgoff"]["max"] < pu.TOL_OFFSET_PX
 
 
@@ -134,7 +138,7 @@ def test_geo2rdr_component_with_poly2d_lat_lon(tmp_path):
     # the oracle on the evaluated planes (evalPoly2d accumulation order, poly2d.c:92-111)
     ev = {k: np.array([[orc.Poly2D(polys[k].getCoeffs(), cols / 2, rows / 2, float(cols), float(rows))(i, j) for j in range(cols)]
                        for i in range(rows)]) for k in ("lat", "lon")}
-    o = orc.geo2rdr(lat=ev["lat"], lon=ev["lon"], hgt=c["hgt"], **_same_orbit_kwargs(sc))
+    o = orc.geo2rdr(lat=ev["lat"], lon=ev["lon"], hgt=c["hgt"], **_same_orbit_kwargs(sc))  # (same window as the component's)
     az_off = np.fromfile(tmp_path / "azimuth.off").reshape(rows, cols)
     rg_off = np.fromfile(tmp_path / "range.off").reshape(rows, cols)
     assert np.array_equal(az_off == -999999.0, o["azoff"] == -999999.0)
