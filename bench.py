@@ -658,7 +658,9 @@ def measure_config(args, ranks, capi, dev, name, *, main, steps, warmup, e2e_ste
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     bytes_px = 8 if split else (24 + 8 + (8 if w["inc"] else 0))  # solve kernel: the SCH height it hands over
-    prof = load_json(os.path.join(ROOT, "profiles", "kernel_counters.json")).get("kernels", {})
+    prof_all = load_json(os.path.join(ROOT, "profiles", "kernel_counters.json"))
+    prof = dict(prof_all.get("kernels", {}))
+    prof.update(prof_all.get("by_workload", {}).get(name, {}))  # counters of this workload's own capture where there is one
     pk = prof.get(dom_name, {})
     traffic = pk.get("dram_bytes_per_pixel")
     traffic = traffic * npix_local if traffic is not None else None

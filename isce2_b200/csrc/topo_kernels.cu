@@ -713,7 +713,7 @@ __device__ void block_suffix_min_flags(const T *v, int n, const unsigned char *r
 #define B2_MASK_MODE_DEFAULT 0
 #endif
 #ifndef B2_MASK_KNOTS
-#define B2_MASK_KNOTS 1024
+#define B2_MASK_KNOTS 256
 #endif
 constexpr int kMaskKnots = B2_MASK_KNOTS;
 // sweep windows (mode 2): capacity of one staged window of the sorted line, in samples, per array
@@ -1179,11 +1179,12 @@ int launch_topo_mask(const TopoConst &C, const LineState *states, int line0, int
     int stage = (forced == 0 || forced == 2) ? forced : B2_MASK_MODE_DEFAULT;
     if (stage == 2 && (size_t)6 * kMaskWinCap * sizeof(double) + bytes_mask > budget) stage = 0;
     size_t smem = bytes_mask + (stage == 2 ? (size_t)6 * kMaskWinCap * sizeof(double) : 0);
-    // the elevation line of the shadow scans (float32) behind the mask bytes when the whole stays under 160 KB, so that the
-    // L1 keeps ~90 KB for the DEM taps of the resampling pass (B200_MASK_ELEV_KB overrides the limit; 0 = never)
+    // the elevation line of the shadow scans (float32) can sit behind the mask bytes (B200_MASK_ELEV_KB = largest dynamic
+    // shared memory for which it does); off by default: on C2 the 100 KB it takes from the L1 cost the resampling pass
+    // more (3.40 vs 3.10 ms per 1500 lines) than the coalesced scan input gains
     static const size_t elev_limit = [] {
         const char *e = getenv("B200_MASK_ELEV_KB");
-        return (size_t)(e ? atoi(e) : 160) * 1024u;
+        return (size_t)(e ? atoi(e) : 0) * 1024u;
     }();
     const size_t bytes_elev = (((size_t)C.width + 15) & ~(size_t)15) - bytes_mask + (size_t)C.width * sizeof(float) + 16;
     const int stage_elev = (smem + bytes_elev <= elev_limit) ? 1 : 0;

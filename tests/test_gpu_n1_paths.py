@@ -82,7 +82,9 @@ def test_topo_azimuth_varying_doppler_alone_and_fused():
         assert np.array_equal(ft[k], g[k], equal_nan=True), k
     o = orc.geo2rdr(lat=c["lat"], lon=c["lon"], hgt=c["hgt"], orbit_method="LEGENDRE", doppler_coeffs=dop1d, **kw)
     st = pu.compare_geo(fg[0], o)
-    assert st["valid"]["gpu"] == st["valid"]["cpu"] == sc.length * sc.width
+    # (geo2rdr is given the range part of the Doppler only, so part of the grid solves to lines outside the short window)
+    assert st["valid"]["gpu"] == st["valid"]["cpu"] and st["valid"]["cpu"] > 0.3 * sc.length * sc.width
+    assert st["azoff"]["n_valid_mismatch"] == 0
     assert st["azoff"]["max"] < pu.TOL_OFFSET_PX and st["rgoff"]["max"] < pu.TOL_OFFSET_PX
 
 
@@ -172,6 +174,7 @@ def test_geo2rdr_orbit_barely_covering_the_scene():
     c = pu.cpu_topo(sc, want_inc=False, want_mask=False)
     dur = (sc.length - 1) / sc.prf
     n_mismatch = 0
+    diag = []
     for lo, hi in ((0.05, 0.05), (0.6, 0.3), (-0.2, 0.4), (0.3, -0.25)):
         # resample the orbit so that its first / last state vector sit lo / hi seconds outside the scene's time span
         t = np.linspace(sc.t0 - lo, sc.t0 + dur + hi, 12)
@@ -183,12 +186,17 @@ def test_geo2rdr_orbit_barely_covering_the_scene():
             o = orc.geo2rdr(lat=c["lat"], lon=c["lon"], hgt=c["hgt"], orbit_method=method, **kw)
             bad_g, bad_o = g["azoff"] == -999999.0, o["azoff"] == -999999.0
             n_mismatch += int((bad_g != bad_o).sum())
+            if (bad_g != bad_o).any():
+                ii = np.argwhere(bad_g != bad_o)
+                diag.append(dict(case=(lo, hi, method), n=len(ii), first=ii[:6].tolist(), gpu_bad=int(bad_g[bad_g != bad_o].sum()),
+                                 azt_gpu=[float(g["azt"][a, b]) for a, b in ii[:4]], azt_cpu=[float(o["azt"][a, b]) for a, b in ii[:4]],
+                                 span=(float(t[0]), float(t[-1])), window=(kw["t0"], kw["t0"] + (kw["length"] - 1) / kw["prf"])))
             both = ~bad_g & ~bad_o
             assert both.sum() > 0.5 * both.size
             assert np.abs(g["azoff"][both] - o["azoff"][both]).max() < pu.TOL_OFFSET_PX, (lo, hi, method)
             if lo < 0 or hi < 0:
                 assert bad_o.sum() > 0  # part of the scene really lies beyond the state vectors
-    assert n_mismatch == 0
+    assert n_mismatch == 0, diag
 
 
 def test_pageable_and_page_locked_destinations_agree(tmp_path):

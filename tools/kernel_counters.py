@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Build profiles/kernel_counters.json -- what bench.py needs from ncu to state executed FP64 and DRAM traffic per launch.
 
-    python tools/kernel_counters.py TAG OUT.json  SUMMARY.json:BENCH.log [SUMMARY.json:BENCH.log ...]
+    python tools/kernel_counters.py TAG OUT.json  c2=SUMMARY.json:BENCH.log [c0c1=SUMMARY.json:BENCH.log ...]
 
 SUMMARY.json: tools/ncu_summary.py output of an `ncu --set full` capture of `bench.py --lines 1500 --workload X`;
 BENCH.log: stdout + stderr of that same bench run (its JSON line gives pixels per launch and the iterations per pixel K).
@@ -51,8 +51,9 @@ def main(tag, out, pairs):
                        "tools/kernel_counters.py; fp64_flop_per_pixel = (dadd + dmul + 2 dfma thread instructions) / pixels of the "
                        "launch; dram_bytes_per_pixel = (dram__bytes_read.sum + dram__bytes_write.sum) / pixels.  bench.py multiplies "
                        "by the pixels of its own launch (and, for the iterative kernels, by K / per_iteration_K).",
-           "tag": tag, "kernels": {}}
+           "tag": tag, "kernels": {}, "by_workload": {}}
     for pair in pairs:
+        wkey, pair = pair.split("=", 1)
         summ, log = pair.split(":")
         line = None
         for ln in open(log, errors="replace"):
@@ -88,10 +89,12 @@ def main(tag, out, pairs):
                      stall_no_instruction=num(r.get("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio")))
             if nm.startswith(("k_topo_solve", "k_topo_fused")):
                 d["per_iteration_K"] = K
-            res["kernels"][nm] = d
+            res["by_workload"].setdefault(wkey, {})[nm] = d
+            res["kernels"].setdefault(nm, d)  # first workload listed wins the un-keyed entry
     json.dump(res, open(out, "w"), indent=1)
-    for k, v in res["kernels"].items():
-        print(f"{k:32s} {v['ms']:8.3f} ms  regs {v['registers']}  fp64 {v['fp64_flop_per_pixel'] and round(v['fp64_flop_per_pixel'])} flop/px  "
+    for wk, kk in res["by_workload"].items():
+      for k, v in kk.items():
+        print(f"{wk:5s} {k:32s} {v['ms']:8.3f} ms  regs {v['registers']}  fp64 {v['fp64_flop_per_pixel'] and round(v['fp64_flop_per_pixel'])} flop/px  "
               f"{v['tflops_executed'] and round(v['tflops_executed'], 2)} TF  dram {v['dram_bytes_per_pixel']:.1f} B/px  pipe {v['fp64_pipe_pct']}")
 
 
