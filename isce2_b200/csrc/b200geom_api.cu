@@ -169,24 +169,28 @@ constexpr int kSinkSlots = 6;                // ring per sink: 192 MB page-locke
 
 struct SinkRing {
     char *buf[kSinkSlots] = {};
-    cudaEvent_t ev[kSinkSlots] = {};
+    cudaEvent_t ev[kSinkSlots] = {}; // events belong to the device that was current when they were created
+    int device = -1;
     bool ok = false;
 };
 std::mutex g_ring_mu;
 std::vector<SinkRing *> g_free_rings; // rings of finished calls, handed to the next one (pinning 192 MB costs ~50 ms)
 
-SinkRing *ring_acquire()
+SinkRing *ring_acquire(int device)
 {
     {
         std::lock_guard<std::mutex> lk(g_ring_mu);
-        if (!g_free_rings.empty()) {
-            SinkRing *r = g_free_rings.back();
-            g_free_rings.pop_back();
-            return r;
-        }
+        for (size_t i = 0; i < g_free_rings.size(); i++)
+            if (g_free_rings[i]->device == device) {
+                SinkRing *r = g_free_rings[i];
+                g_free_rings[i] = g_free_rings.back();
+                g_free_rings.pop_back();
+                return r;
+            }
     }
     SinkRing *r = new (std::nothrow) SinkRing;
     if (!r) return nullptr;
+    r->device = device;
     r->ok = true;
     for (int i = 0; i < kSinkSlots && r->ok; i++) {
         r->ok = cudaHostAlloc((void **)&r->buf[i], kSinkSlotBytes, cudaHostAllocPortable) == cudaSuccess &&
@@ -296,7 +300,7 @@ class HostSink {
         if (!bytes) return cudaSuccess;
         if (!pageable(dst)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_);
         if (!ring_) {
-            ring_ = ring_acquire();
+            ring_ = ring_acquire(device_);
             if (!ring_) { // no page-locked memory to bounce through: the driver's own path still works
                 bounce_failed_ = true;
                 return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_);

@@ -20,7 +20,7 @@ K='regex:k_topo_solve|k_topo_final|k_topo_fused|k_topo_mask|k_geo2rdr'
 timeout 300 ncu --set full $FP $NCU_COMMON -k regex:k_fp64_peak -c 1 -f -o /tmp/full_peak_$TAG $B --workload c0c1 > $O/full_peak_$TAG.log 2>&1
 python tools/ncu_summary.py /tmp/full_peak_$TAG.ncu-rep $O/ncu_fp64_peak_$TAG.json > $O/ncu_fp64_peak_$TAG.txt 2>&1
 # gpurun brings back at most 64 MiB: the c2 report (with source) comes home, the others are summarised here and dropped
-timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 5 -f -o $O/full_c2_$TAG $B --workload c2 > $O/full_c2_$TAG.log 2>&1
+timeout 900 ncu --set full $FP $NCU_COMMON --import-source on -k "$K" -c 7 -f -o $O/full_c2_$TAG $B --workload c2 > $O/full_c2_$TAG.log 2>&1
 python tools/ncu_summary.py $O/full_c2_$TAG.ncu-rep $O/ncu_full_c2_$TAG.json > $O/ncu_full_c2_$TAG.txt 2>&1
 for W in c0c1 c3; do
   timeout 900 ncu --set full $FP $NCU_COMMON -k "$K" -c 8 -f -o /tmp/full_${W}_$TAG $B --workload $W > $O/full_${W}_$TAG.log 2>&1
