@@ -721,6 +721,10 @@ constexpr int kMaskKnots = B2_MASK_KNOTS;
 #define B2_MASK_WCAP 1024
 #endif
 constexpr int kMaskWinCap = B2_MASK_WCAP;
+#ifndef B2_MASK_FIRST_DEPTH
+#define B2_MASK_FIRST_DEPTH 4
+#endif
+constexpr int kMaskFirstPassDepth = B2_MASK_FIRST_DEPTH;
 
 // ---- 1-D bulk copies global -> shared through the TMA unit, completion on an mbarrier (sm_90+) ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -820,12 +824,22 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
         // ---- (A) ctrack extent :730-732 and "is the line free of fold-over" in one pass ----
         double mn = INFINITY, mx = -INFINITY;
         int unsorted = 0;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < w; i += blockDim.x) { // several loads in flight per thread: this pass is pure latency
-            const double v = ctrack_in[i];
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
-            if (i > 0 && ctrack_in[i - 1] > v) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
+        // kMaskFirstPassDepth strided samples (and their left neighbours) per trip, all loads issued before the first use: this pass is
+        // pure load latency
+        for (int i0 = threadIdx.x; i0 < w; i0 += kMaskFirstPassDepth * blockDim.x) {
+            double v[kMaskFirstPassDepth], u[kMaskFirstPassDepth];
+#pragma unroll
+            for (int q = 0; q < kMaskFirstPassDepth; q++) {
+                const int i = i0 + q * (int)blockDim.x;
+                v[q] = i < w ? ctrack_in[i] : NAN;
+                u[q] = (i < w && i > 0) ? ctrack_in[i - 1] : NAN;
+            }
+#pragma unroll
+            for (int q = 0; q < kMaskFirstPassDepth; q++) {
+                mn = fmin(mn, v[q]); // fmin / fmax skip the NaN padding
+                mx = fmax(mx, v[q]);
+                if (u[q] > v[q]) unsorted = 1; // NaNs count as ordered, like the reference's insertion sort
+            }
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -965,6 +979,15 @@ k_topo_mask(const __grid_constant__ TopoConst C, const LineState *__restrict__ s
                     const double aa = grid_pos(p);
                     const int guess = cnt_prev >= 0 ? cnt_prev + ((lane + 1) >> 1) : knot_guess(aa);
                     cnt = search_count_le([&](int m) { return cs[m]; }, w, aa, guess);
+#ifndef B2_MASK_NO_PREFETCH
+                    {   // the lane's bracket in the NEXT group sits ~16 entries further: have the three lines it will read on
+                        // their way into L1 while this group's DEM interpolation runs
+                        const int pf = cnt + 16 < w - 1 ? cnt + 16 : w - 1;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + pf));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(lats + pf));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(lons + pf));
+                    }
+#endif
                     val = mask_resample<METHOD, REF>(C, sL, cs, lats, lons, ref_search_result(cnt, w), aa);
                 }
                 double prev = __shfl_up_sync(0xffffffffu, val, 1);
