@@ -73,8 +73,8 @@ def test_topo_then_geo2rdr_through_components(tmp_path):
              hgt=np.fromfile(geom / "z.rdr").reshape(sc.length, sc.width), los=np.asarray(los.memMap()),
              inc=np.fromfile(geom / "incLocal.rdr", np.float32).reshape(sc.length, 2, sc.width),
              mask=np.fromfile(geom / "shadowMask.rdr", np.int8).reshape(sc.length, sc.width))
-    assert np.abs(g["lat"] - c["lat"]).max() < 2e-7 and (np.abs(g["lat"] - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2
-    assert np.abs(g["lon"] - c["lon"]).max() < 2e-7 and (np.abs(g["lon"] - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= 2
+    assert np.abs(g["lat"] - c["lat"]).max() < 1e-7 and (np.abs(g["lat"] - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2
+    assert np.abs(g["lon"] - c["lon"]).max() < 1e-7 and (np.abs(g["lon"] - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= 2
     assert np.abs(g["hgt"] - c["hgt"]).max() < pu.TOL_HGT_M
     assert np.array_equal(g["mask"], c["mask"])
     assert (np.abs(g["los"].astype(np.float64) - c["los"]) > pu.TOL_ANGLE_DEG).sum() <= 4
@@ -168,5 +168,5 @@ def test_topo_component_native_doppler_and_line_sharding_attribute(tmp_path):
     assert outs["one"]["snwe"] == outs["two"]["snwe"]
     c = pu.cpu_topo(sc, dem_method="BIQUINTIC", orbit_method="LEGENDRE", want_inc=False)
     lat = outs["one"]["lat.rdr"].view(np.float64).reshape(sc.length, sc.width)
-    assert np.abs(lat - c["lat"]).max() < 2e-7 and (np.abs(lat - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2
+    assert np.abs(lat - c["lat"]).max() < 1e-7 and (np.abs(lat - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= 2
     assert np.array_equal(outs["one"]["mask.rdr"].view(np.int8).reshape(sc.length, sc.width), c["mask"])

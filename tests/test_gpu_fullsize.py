@@ -124,12 +124,12 @@ def _report(name, tot):
 
 def _assert_strip_totals(tot):
     # hgt within 1 cm everywhere; lat / lon / angles within tolerance except for the float32 DEM-index flips described in
-    # tests/test_gpu_parity.py, bounded by 5x the tolerance in lat / lon and counted per 1e9 values in the report
+    # tests/test_gpu_parity.py, bounded by 10x the tolerance in lat / lon and 5e-3 deg in the angles and counted per 1e9 values in the report
     assert tot["hgt"]["n_over"] == 0, tot["hgt"]
     for k in ("lat", "lon"):
-        assert tot[k]["n_over"] <= max(2, int(2e-5 * tot[k]["n"])) and tot[k]["max"] < 2e-7, (k, tot[k])
+        assert tot[k]["n_over"] <= max(2, int(2e-5 * tot[k]["n"])) and tot[k]["max"] < 1e-7, (k, tot[k])
     for k in ("los", "inc"):
-        assert tot[k]["n_over"] <= max(4, int(4e-5 * tot[k]["n"])) and tot[k]["max"] < 2e-2, (k, tot[k])
+        assert tot[k]["n_over"] <= max(4, int(4e-5 * tot[k]["n"])) and tot[k]["max"] < 5e-3, (k, tot[k])
 
 
 def test_c3_nisar_frame_round_trip_at_full_size():

@@ -20,9 +20,14 @@ from tests import parity_util as pu
 
 pytestmark = pytest.mark.gpu
 
+# Measured on B200 boxes of this pool (profiles/r02_parity_rough_scene.json, 786k-pixel rough scene): 0 lat / lon / hgt / LOS
+# values over tolerance (largest lat / lon difference 3e-10 deg), 2 incidence values of 1.6 M over (largest 2.2e-4 deg), masks
+# and iteration counts identical.  The oracle's own last bits depend on which libm variant glibc selects for the host CPU
+# (its SCH-orbit step count moved by 1e-3 between two boxes), so the bounds keep a margin: outliers <= 2e-5 of the values,
+# none beyond 10x the lat / lon tolerance or 5e-3 deg in the slope-derived angles.
 MAX_OUTLIER_FRACTION = 2e-5
-HARD_LATLON_DEG = 2e-7
-HARD_ANGLE_DEG = 2e-2
+HARD_LATLON_DEG = 1e-7
+HARD_ANGLE_DEG = 5e-3
 
 
 def _assert_topo(st, check_mask=True):

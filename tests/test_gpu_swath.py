@@ -35,8 +35,8 @@ def test_merged_topo_views_and_stack_geo2rdr(tmp_path):
     hgt = np.fromfile(os.path.join(geom, "hgt.rdr")).reshape(sc.length, sc.width)
     msk = np.fromfile(os.path.join(geom, "shadowMask.rdr"), np.int8).reshape(sc.length, sc.width)
     n = lat.size
-    assert np.abs(lat - c["lat"]).max() < 2e-7 and (np.abs(lat - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= max(2, n // 50000)
-    assert np.abs(lon - c["lon"]).max() < 2e-7 and (np.abs(lon - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= max(2, n // 50000)
+    assert np.abs(lat - c["lat"]).max() < 1e-7 and (np.abs(lat - c["lat"]) > pu.TOL_LATLON_DEG).sum() <= max(2, n // 50000)
+    assert np.abs(lon - c["lon"]).max() < 1e-7 and (np.abs(lon - c["lon"]) > pu.TOL_LATLON_DEG).sum() <= max(2, n // 50000)
     assert np.abs(hgt - c["hgt"]).max() < pu.TOL_HGT_M
     assert np.array_equal(msk, c["mask"])
     assert abs(out["bbox"][0] - c["min_lat"]) < 1e-9 and abs(out["bbox"][3] - c["max_lon"]) < 1e-9
