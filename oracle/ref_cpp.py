@@ -224,17 +224,20 @@ def topo(*, dem, first_lat, first_lon, delta_lat, delta_lon, orbit_t, orbit_pos,
     t = np.ascontiguousarray(orbit_t, np.float64)
     pos = np.ascontiguousarray(orbit_pos, np.float64)
     vel = np.ascontiguousarray(orbit_vel, np.float64)
+    import time
+    t_call = time.perf_counter()
     with _capture_stdout() as cap:
         _lib("topo").ref_cpp_topo(first_lat, first_lon, delta_lat, delta_lon, a, e2, peg_heading, prf, t0, wvl, thresh, numiter,
                                   extraiter, nx, ny, side, length, width, 1, 1, orc.DEM_METHODS[dem_method.upper()],
                                   orc.ORBIT_METHODS[orbit_method.upper()], len(t), _d(t), _d(pos), _d(vel), _f(dem), _d(dop),
                                   _d(rho), _d(lat), _d(lon), _d(hgt), _f(los), _f(inc), _d(mask) if want_mask else None)
+    t_call = time.perf_counter() - t_call
     m = re.search(r"Actual DEM bounds used:\s*Dimensions: (\d+) (\d+).*?Lines: (\d+) (\d+)\s*Pixels: (\d+) (\d+)", cap.text, re.S)
     crop = dict(zip(("width", "length", "line0", "line1", "pixel0", "pixel1"), map(int, m.groups()))) if m else None
     m = re.search(r"Total convergence: (\d+) out of", cap.text)
     return dict(lat=lat, lon=lon, hgt=hgt, los=np.ascontiguousarray(np.moveaxis(los, 2, 1)),
                 inc=np.ascontiguousarray(np.moveaxis(inc, 2, 1)), mask=None if mask is None else mask.astype(np.int8), crop=crop,
-                totalconv=int(m.group(1)) if m else None, log=cap.text)
+                totalconv=int(m.group(1)) if m else None, log=cap.text, seconds=t_call)
 
 
 def geo2rdr(*, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, length, width, r0, dr, prf, t0, wvl, side=-1,
@@ -251,11 +254,14 @@ def geo2rdr(*, lat, lon, hgt, orbit_t, orbit_pos, orbit_vel, length, width, r0, 
     vel = np.ascontiguousarray(orbit_vel, np.float64)
     dc = np.ascontiguousarray(np.asarray(doppler_coeffs, np.float64).ravel())
     out = {k: np.zeros((demlength, demwidth)) for k in ("azt", "rgm", "azoff", "rgoff")}
+    import time
+    t_call = time.perf_counter()
     with _capture_stdout() as cap:
         _lib("geo").ref_cpp_geo2rdr(a, e2, dr, r0, wvl, t0, prf, length, width, demlength, demwidth, 1, 1, int(bool(bistatic)),
                                     orc.ORBIT_METHODS[orbit_method.upper()], len(t), _d(t), _d(pos), _d(vel), len(dc) - 1,
                                     float(doppler_mean), float(doppler_norm), _d(dc), _d(lat), _d(lon), _d(hgt),
                                     _d(out["azt"]), _d(out["rgm"]), _d(out["azoff"]), _d(out["rgoff"]))
+    out["seconds"] = time.perf_counter() - t_call
     for key, pat in (("num_outside", r"outside the image: (\d+)"), ("num_valid", r"with valid data:\s+(\d+)"),
                      ("num_conv", r"that converged:\s+(\d+)")):
         m = re.search(pat, cap.text)
