@@ -272,7 +272,7 @@ class CopyPool {
                 cudaSetDevice(t.device);
                 cur = t.device;
             }
-            cudaEventSynchronize(t.ready);
+            if (t.ready) cudaEventSynchronize(t.ready); // (host -> slot copies of HostSource have nothing to wait for)
             memcpy(t.dst, t.src, t.bytes);
             if (t.pending->fetch_sub(1) == 1) {
                 std::lock_guard<std::mutex> lk(*t.mu);
@@ -368,6 +368,83 @@ class HostSink {
     bool bounce_failed_ = false;
     const void *last_ptr_ = nullptr;
     bool last_pageable_ = false;
+};
+
+
+// HostSource: the mirror image for INPUTS that live in pageable memory (the lat / lon / hgt rasters of geo2rdr arrive as
+// numpy.memmaps of the .rdr files topo wrote, Geo2rdr.py:208-226).  The copier threads fill a page-locked slot from the
+// source in parallel (page-cache reads and page faults included), the DMA engine uploads it while they fill the next one.
+class HostSource {
+  public:
+    HostSource(cudaStream_t s, int device) : s_(s), device_(device) {}
+    ~HostSource()
+    {
+        if (ring_) {
+            for (int i = 0; i < kSinkSlots; i++)
+                if (used_[i]) cudaEventSynchronize(ring_->ev[i]); // the slots must not be reused while a DMA still reads them
+            ring_release(ring_);
+        }
+    }
+    // enqueue `bytes` from host memory `src` to device memory `dst` on the stream
+    cudaError_t copy(void *dst, const void *src, size_t bytes)
+    {
+        if (!bytes) return cudaSuccess;
+        if (!pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s_);
+        if (!ring_) {
+            ring_ = ring_acquire(device_);
+            if (!ring_) {
+                failed_ = true;
+                return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s_);
+            }
+        }
+        const int nt = CopyPool::get().size();
+        for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
+            const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
+            const int k = next_;
+            next_ = (next_ + 1) % kSinkSlots;
+            if (used_[k]) {
+                cudaError_t e = cudaEventSynchronize(ring_->ev[k]); // the slot's previous upload has left it
+                if (e != cudaSuccess) return e;
+            }
+            size_t part = (n + nt - 1) / nt;
+            part = (part + 4095) & ~(size_t)4095;
+            if (part < (1u << 20)) part = 1u << 20;
+            const int nparts = (int)((n + part - 1) / part);
+            pending_.store(nparts);
+            for (int q = 0; q < nparts; q++) {
+                const size_t po = (size_t)q * part, pn = n - po < part ? n - po : part;
+                CopyPool::get().push(CopyPool::Task{nullptr, device_, ring_->buf[k] + po, (const char *)src + o + po, pn, &pending_, &mu_, &cv_});
+            }
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return pending_.load() == 0; });
+            }
+            cudaError_t e = cudaMemcpyAsync((char *)dst + o, ring_->buf[k], n, cudaMemcpyHostToDevice, s_);
+            if (e == cudaSuccess) e = cudaEventRecord(ring_->ev[k], s_);
+            if (e != cudaSuccess) return e;
+            used_[k] = true;
+        }
+        return cudaSuccess;
+    }
+
+  private:
+    bool pageable(const void *p)
+    {
+        if (sink_threads() == 0 || failed_) return false;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) == cudaSuccess) return a.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        return false;
+    }
+    cudaStream_t s_;
+    int device_;
+    SinkRing *ring_ = nullptr;
+    bool used_[kSinkSlots] = {};
+    std::atomic<int> pending_{0};
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int next_ = 0;
+    bool failed_ = false;
 };
 
 // lines per pipeline chunk: ~8 Mpixel, so that copies of one chunk overlap the kernels of the next
@@ -904,9 +981,10 @@ extern "C" int b200_geo_plan_create(const b200_geo_params *p, const double *lat,
     int rc = geo_plan_common(pl, err, errlen);
     if (rc == B200_OK) {
         const size_t npix = (size_t)pl->nlines * (size_t)p->dem_width, off = (size_t)pl->line0 * (size_t)p->dem_width;
+        HostSource source(pl->stream, p->device); // the geometry may come as memmaps of the reference date's .rdr files
         auto up = [&](double **d, const double *h) -> int {
             CK(dmalloc(d, sizeof(double) * npix));
-            CK(cudaMemcpyAsync(*d, h + off, sizeof(double) * npix, cudaMemcpyHostToDevice, pl->stream));
+            CK(source.copy(*d, h + off, sizeof(double) * npix));
             return B200_OK;
         };
         cudaEventRecord(pl->ev0, pl->stream);
@@ -1216,6 +1294,7 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
     void *hout[4] = {out->azt, out->rgm, out->azoff, out->rgoff};
     int launches = 1;
     HostSink sink(st.d, p->device);
+    HostSource source(st.h, p->device); // lat / lon / hgt may be memmaps of the .rdr files
     for (int c0 = 0; c0 < pl->nlines; c0 += cl) {
         const int n = (c0 + cl <= pl->nlines) ? cl : pl->nlines - c0;
         const size_t o = (size_t)c0 * w, cnt = (size_t)n * w;
@@ -1224,9 +1303,9 @@ extern "C" int b200_geo2rdr_run(const b200_geo_params *p, const double *lat, con
         st.ev.push_back(eh);
         CK(cudaEventCreateWithFlags(&ek, cudaEventDisableTiming));
         st.ev.push_back(ek);
-        CK(cudaMemcpyAsync(pl->d_lat + o, lat + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
-        CK(cudaMemcpyAsync(pl->d_lon + o, lon + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
-        CK(cudaMemcpyAsync(pl->d_hgt + o, hgt + off + o, sizeof(double) * cnt, cudaMemcpyHostToDevice, st.h));
+        CK(source.copy(pl->d_lat + o, lat + off + o, sizeof(double) * cnt));
+        CK(source.copy(pl->d_lon + o, lon + off + o, sizeof(double) * cnt));
+        CK(source.copy(pl->d_hgt + o, hgt + off + o, sizeof(double) * cnt));
         CK(cudaEventRecord(eh, st.h));
         CK(cudaStreamWaitEvent(s, eh, 0));
         GeoLayers L{pl->d_lat + o, pl->d_lon + o, pl->d_hgt + o, nullptr, nullptr, nullptr, nullptr};

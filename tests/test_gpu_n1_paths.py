@@ -238,6 +238,24 @@ def test_pageable_and_page_locked_destinations_agree(tmp_path):
         assert np.array_equal(pinned[k], np.asarray(mm[k]), equal_nan=True), k
         mm[k].flush()
         assert np.array_equal(np.fromfile(tmp_path / (k + ".bin"), pinned[k].dtype).reshape(pinned[k].shape), pinned[k], equal_nan=True)
+    # inputs in pageable memory (memmaps of the rasters just written) go up through the mirror-image bounce path
+    gp64 = _capi.geo_params(length=kw["length"], width=kw["width"], dem_shape=(sc.length, sc.width), r0=kw["r0"], dr=kw["dr"],
+                            prf=kw["prf"], t0=kw["t0"], wvl=kw["wvl"], side=kw["side"])
+    ins_mm = [np.memmap(str(tmp_path / (k + ".bin")), dtype=np.float64, mode="r", shape=(sc.length, sc.width)) for k in ("lat", "lon", "hgt")]
+    ins_pin = []
+    for k in ("lat", "lon", "hgt"):
+        a = _capi.pinned_empty((sc.length, sc.width), np.float64)
+        a[...] = pinned[k]
+        ins_pin.append(a)
+    ga = _capi.geo2rdr_run(gp64, *ins_mm, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"])
+    gb = _capi.geo2rdr_run(gp64, *ins_pin, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"])
+    for k in ("azt", "rgm", "azoff", "rgoff"):
+        assert np.array_equal(ga[k], gb[k]), k
+    assert np.array_equal(ga["azoff"].astype(np.float32), pinned["azoff"])  # and they are the fused call's offsets
+    plan = _capi.GeoPlan(gp64, *ins_mm)
+    plan.execute(gp64, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"], want=("azoff",))
+    assert np.array_equal(plan.fetch()["azoff"], gb["azoff"])
+    plan.close()
     # the plan form fetches through the same sink
     tp = _capi.TopoPlan(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]], want_los=True,
                         want_inc=True, want_mask=True)
