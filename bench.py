@@ -1002,6 +1002,7 @@ def file_write_floor(base, nbytes, nfiles=8, threads=None, how="mmap"):
 
 
 def run_b200(args, ranks):
+    t_start = time.time()
     from isce2_b200 import _capi as capi
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; this arm has no CPU fallback (use --impl reference for the CPU baseline)")
@@ -1054,6 +1055,7 @@ def run_b200(args, ranks):
             ff = comp.get("file_floor") or {}
             if comp.get("ms_per_step") and ff.get("seconds"):
                 comp["frac_of_file_floor"] = ff["seconds"] * 1e3 / comp["ms_per_step"]
+        line["bench_seconds"] = round(time.time() - t_start, 1)  # whole run of this arm, all configurations and baselines
         print(json.dumps(line), flush=True)
     return line
 

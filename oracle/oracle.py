@@ -375,8 +375,9 @@ def _poly2d_or_none(p):
 
 def resamp_slc(*, slc, out_shape, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_r0=None, ref_slr=None, flatten=False,
                rg_carrier=None, az_carrier=None, rg_offsets=None, az_offsets=None, doppler=None, resid_az=None, resid_rg=None,
-               nthreads=0):
-    """resamp_slc.f90 on one complex64 image; polynomials as oracle.Poly2D / coefficient lists / None (zero)."""
+               nthreads=0, cpp_positions=False):
+    """resamp_slc.f90 on one complex64 image; polynomials as oracle.Poly2D / coefficient lists / None (zero).
+    cpp_positions (tests only): evaluate the Doppler / carrier polynomials where the reference's C++ restatement does."""
     slc = np.ascontiguousarray(slc, np.complex64)
     inlength, inwidth = slc.shape
     outlength, outwidth = out_shape
@@ -386,9 +387,13 @@ def resamp_slc(*, slc, out_shape, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_
     ra = np.ascontiguousarray(resid_az, np.float64) if resid_az is not None else None
     rr = np.ascontiguousarray(resid_rg, np.float64) if resid_rg is not None else None
     out = np.zeros((outlength, outwidth), np.complex64)
-    rc = lib().orc_resamp_slc(C.byref(p), *[(C.byref(q.c) if q is not None else None) for q in polys],
-                              slc.ctypes.data_as(_fp), _d(ra) if ra is not None else None, _d(rr) if rr is not None else None,
-                              out.ctypes.data_as(_fp), nthreads)
+    lib().orc_test_set_cpp_quirks(4 if cpp_positions else 0)
+    try:
+        rc = lib().orc_resamp_slc(C.byref(p), *[(C.byref(q.c) if q is not None else None) for q in polys],
+                                  slc.ctypes.data_as(_fp), _d(ra) if ra is not None else None, _d(rr) if rr is not None else None,
+                                  out.ctypes.data_as(_fp), nthreads)
+    finally:
+        lib().orc_test_set_cpp_quirks(0)
     if rc != 0:
         raise RuntimeError(f"orc_resamp_slc failed rc={rc}")
     return out

@@ -59,6 +59,8 @@ def _lib(kind):
             L.ref_cpp_geo2rdr.argtypes = [_D] * 7 + [_I] * 9 + [_dp, _dp, _dp, _I, _D, _D, _dp] + [_dp] * 7
         elif kind == "resamp":
             L.ref_cpp_sinc_coef.argtypes = [_D, _D, _I, _D, _I, _dp]
+            L.ref_cpp_resamp_slc.restype = _I
+            L.ref_cpp_resamp_slc.argtypes = [_I] * 4 + [_D] * 6 + [_I] + [_dp] * 5 + [_fp, _dp, _dp, _fp]
         _libs[kind] = L
     return _libs[kind]
 
@@ -122,6 +124,35 @@ def sinc_coef(beta, relfiltlen, decfactor, pedestal, weight):
     out = np.zeros(n, np.float64)
     _lib("resamp").ref_cpp_sinc_coef(beta, relfiltlen, decfactor, pedestal, weight, _d(out))
     return out
+
+
+def _poly_block(p):
+    """oracle.Poly2D -> [azimuthOrder, rangeOrder, azimuthMean, rangeMean, azimuthNorm, rangeNorm, coeffs ...] (or None)."""
+    if p is None:
+        return None
+    c = p.c
+    return np.ascontiguousarray(np.concatenate([[c.azimuth_order, c.range_order, c.mean_azimuth, c.mean_range, c.norm_azimuth,
+                                                 c.norm_range], p.coeffs.ravel()]), np.float64)
+
+
+def resamp_slc(*, slc, out_shape, wvl=0.056, slr=2.3, r0=0.0, ref_wvl=None, ref_r0=None, ref_slr=None, flatten=False,
+               rg_carrier=None, az_carrier=None, rg_offsets=None, az_offsets=None, doppler=None, resid_az=None, resid_rg=None):
+    """ResampSlc::_resamp_cpu (GPUresampslc/src/ResampSlc.cpp:164-383) on one complex64 image: same keywords as
+    oracle.resamp_slc.  Returns (out, printed text)."""
+    slc = np.ascontiguousarray(slc, np.complex64)
+    inlength, inwidth = slc.shape
+    outlength, outwidth = out_shape
+    blocks = [_poly_block(orc._poly2d_or_none(q)) for q in (rg_carrier, az_carrier, rg_offsets, az_offsets, doppler)]
+    ra = np.ascontiguousarray(resid_az, np.float64) if resid_az is not None else None
+    rr = np.ascontiguousarray(resid_rg, np.float64) if resid_rg is not None else None
+    out = np.zeros((outlength, outwidth), np.complex64)
+    with _capture_stdout() as cap:
+        _lib("resamp").ref_cpp_resamp_slc(inwidth, inlength, outwidth, outlength, wvl, slr, r0, wvl if ref_wvl is None else ref_wvl,
+                                          slr if ref_slr is None else ref_slr, r0 if ref_r0 is None else ref_r0, int(bool(flatten)),
+                                          *[(_d(b) if b is not None else None) for b in blocks], _f(slc.view(np.float32)),
+                                          _d(ra) if ra is not None else None, _d(rr) if rr is not None else None,
+                                          _f(out.view(np.float32)))
+    return out, cap.text
 
 
 def latlon(a, e2, vec, to_xyz):

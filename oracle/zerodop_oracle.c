@@ -577,7 +577,8 @@ static int g_akima_cpp_quirks = 0;
 /* (3) UniformInterp.cpp:186 forms each sinc term in double and rounds the running sum to float once per tap
  * (uniform_interp.f90:424-425 multiplies and adds in real*4). */
 static int g_sinc_cpp_arith = 0;
-void orc_test_set_cpp_quirks(int on) { g_akima_cpp_quirks = on & 1; g_sinc_cpp_arith = (on >> 1) & 1; }
+static int g_resamp_cpp_positions = 0; /* bit2, see orc_resamp_slc */
+void orc_test_set_cpp_quirks(int on) { g_akima_cpp_quirks = on & 1; g_sinc_cpp_arith = (on >> 1) & 1; g_resamp_cpp_positions = (on >> 2) & 1; }
 static int aki_almost_equal(double x, double y) { return fabs(x - y) <= (g_akima_cpp_quirks ? 0.0 : 2.220446049250313e-16); }
 static double akima_eval(const float *dem, int nx, int ny, int ix, int iy, double fx, double fy)
 {
@@ -1697,7 +1698,12 @@ int orc_resamp_slc(const orc_resamp_params *p, const orc_poly2d *rgCarrier, cons
             const int kk = (int)floor(j + r_ao);
             const double fraca = j + r_ao - kk;
             if ((kk <= sinchalf) || (kk >= (inlength - sinchalf))) continue;
-            const double r_dop = eval2d_or_zero(dopplerPoly, r_at + r_ao, r_rt + r_ro); /* :211 */
+            /* :211.  Test hook (orc_test_set_cpp_quirks bit 2): where the reference's C++ restatement evaluates its
+             * polynomials -- the Doppler at the output pixel (ResampSlc.cpp:293, the form resamp_slc.f90 had before
+             * 12-AUG-2020) and the carriers that are added back one sample / line earlier (ResampSlc.cpp:311: 0-based
+             * i+ao, j+ro against the 1-based :233-235 here) -- so that the two can be compared with polynomials that vary */
+            const double r_dop = g_resamp_cpp_positions ? eval2d_or_zero(dopplerPoly, r_at, r_rt)
+                                                        : eval2d_or_zero(dopplerPoly, r_at + r_ao, r_rt + r_ro);
             for (int jj = 1; jj <= sincone; jj++) {
                 const int chipj = kk + jj - 1 - sinchalf;
                 cx4 cval = {(float)cos((jj - 5.0) * r_dop), (float)(-sin((jj - 5.0) * r_dop))};
@@ -1709,6 +1715,10 @@ int orc_resamp_slc(const orc_resamp_params *p, const orc_poly2d *rgCarrier, cons
             double r_ph = r_dop * fraca;
             r_rt = i + r_ro;
             r_at = j + r_ao;
+            if (g_resamp_cpp_positions) {
+                r_rt = (i - 1) + r_ro;
+                r_at = (j - 1) + r_ao;
+            }
             r_ph = r_ph + eval2d_or_zero(rgCarrier, r_at, r_rt) + eval2d_or_zero(azCarrier, r_at, r_rt);
             if (p->flatten != 0)
                 r_ph = r_ph + (4.0 * PI / p->wvl) * ((p->r0 - p->refr0) + (i - 1.0) * (p->slr - p->refslr) + r_ro * p->slr) +

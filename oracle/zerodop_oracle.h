@@ -15,9 +15,11 @@
  * the reference's own C++ restatement of topozero / geo2rdr, CPU branches
  * (GPUtopozero/src, GPUgeo2rdr/src: DEM interpolators, geometry primitives,
  * whole-image topo -- lat/lon/hgt/los/local incidence/shadow bit -- and
- * whole-image geo2rdr, tests/test_oracle_cpp_pins.py).  Restatement-only, because
+ * whole-image geo2rdr; GPUresampslc/src: whole-image resamp_slc up to float32
+ * accumulation order -- tests/test_oracle_cpp_pins.py).  Restatement-only, because
  * the C++ departs from the Fortran there: the layover bit of the mask, inc
- * channel 1 (psi), the bicubic interpolator, binarysearch; those are held
+ * channel 1 (psi), the bicubic interpolator, binarysearch, and geozero (no C++
+ * form of it exists); those are held
  * against the defining equations, the geometric definitions of the mask bits
  * and independent implementations (tests/test_oracle_image_properties_cpu.py)
  * and golden vectors of the reference's own Python (tests/golden/).

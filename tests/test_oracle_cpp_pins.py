@@ -1,7 +1,7 @@
 """Hold the CPU oracle (oracle/zerodop_oracle.c) against REFERENCE-AUTHORED code for the Fortran-only arithmetic.
 
 The Fortran of the path cannot be compiled here (no gfortran).  The reference ships its own C++ restatement of it --
-components/zerodop/GPUtopozero/src/*.cpp and GPUgeo2rdr/src/*.cpp (CPU branches), GPUresampslc/src/Interpolator.cpp --
+components/zerodop/GPUtopozero/src/*.cpp, GPUgeo2rdr/src/*.cpp and GPUresampslc/src/*.cpp (CPU branches) --
 which compiles unchanged with g++ (oracle/Makefile target ref -> oracle/_ref/libisce2_cpp*_ref.so, doors in
 oracle/ref_cpp.py).  Where that C++ agrees with the Fortran as written the oracle must equal it BIT FOR BIT; where the
 C++ itself departs from the Fortran the departure is named here with both file:line's, and either emulated through the
@@ -288,3 +288,96 @@ def test_whole_image_geo2rdr_against_reference_cpp(case):
         assert got["num_valid"] == 0
     else:
         assert 0.3 * n < got["num_valid"] < n  # the scene is cut by the secondary's window: both branches are exercised
+
+
+# ------------------------------------------------------------------ resamp_slc against ResampSlc::_resamp_cpu
+# Departures of GPUresampslc/src/ResampSlc.cpp from resamp_slc.f90, each handled as stated:
+#  (1) the sinc table is used as sinc_coef delivers it (ResampMethods.cpp:31-39) and sinc_eval_2d neither normalises the
+#      weights nor divides by their sum (Interpolator.cpp:163-176); resamp_slcMethods.f:66-73 normalises every sub-sample
+#      phase of the table and uniform_interp.f90:456-484 divides by the weight sum again.  The C++ result is therefore the
+#      Fortran's times (sum of the 8 azimuth taps) x (sum of the 8 range taps) of ITS table, 1 .. 1.003: applied here from
+#      the reference's own table, per pixel.
+#  (2) Doppler at the output pixel (ResampSlc.cpp:293) against resamp_slc.f90:211 (secondary's coordinate, 12-AUG-2020),
+#      carriers added back at 0-based coordinates (ResampSlc.cpp:311) against the 1-based :233-235: the oracle's test hook
+#      evaluates them where the C++ does; everything else in the routine is the path under test.
+#  (3) the C++ admits one more line / sample at the far edge (ResampSlc.cpp:288,291: k >= n-4 on 0-based k; resamp_slc.f90:
+#      198,204: k >= n-4 on 1-based k): pixels the C++ fills and the Fortran skips must be exactly those.
+#  (4) accumulation: complex<float> products summed in float, azimuth outer (Interpolator.cpp:169-172) against real*8
+#      weights and range outer: float32 rounding, bounded below.
+#  (5) pixels outside the bounds keep whatever the previous lines left in the output line buffer (the C++ never clears
+#      it); the Fortran writes zeros.  Left out of the comparison.
+RESAMP_CASES = {
+    "identity":              dict(shape=(96, 128), out=(96, 128)),
+    "offsets+residuals":     dict(shape=(160, 220), out=(150, 200), resid=True, offsets=True),
+    "carriers+doppler":      dict(shape=(160, 220), out=(150, 200), resid=True, offsets=True, carriers=True, doppler=True),
+    "flatten":               dict(shape=(160, 220), out=(150, 200), resid=True, offsets=True, carriers=True, doppler=True, flatten=True),
+    "two tiles (1000 + 80)": dict(shape=(1100, 72), out=(1080, 64), resid=True, offsets=True, carriers=True, doppler=True, flatten=True),
+}
+
+
+def _resamp_case(c, seed=5):
+    rng = np.random.default_rng(seed)
+    L, W = c["shape"]
+    oL, oW = c["out"]
+    P = orc.Poly2D
+    kw = dict(slc=(rng.standard_normal((L, W)) + 1j * rng.standard_normal((L, W))).astype(np.complex64), out_shape=(oL, oW),
+              wvl=0.0555, slr=2.33, r0=800000.0, ref_wvl=0.0556, ref_r0=800010.0, ref_slr=2.33, flatten=bool(c.get("flatten")))
+    if c.get("offsets"):
+        kw["rg_offsets"] = P([[1.5, 0.002], [0.001, 0.0]])
+        kw["az_offsets"] = P([[-0.5, 0.0005], [0.003, 0.0]])
+    if c.get("resid"):
+        kw["resid_az"] = 0.3 * rng.standard_normal((oL, oW)) + 2.3
+        kw["resid_rg"] = 0.3 * rng.standard_normal((oL, oW)) - 1.7
+    if c.get("carriers"):
+        kw["rg_carrier"] = P([[0.1, 0.002], [0.001, 0.0]])
+        kw["az_carrier"] = P([[0.2, 0.0], [0.03, 1e-5]])
+    if c.get("doppler"):
+        kw["doppler"] = P([[0.05, 0.0004], [0.0003, 0.0]])
+    return kw
+
+
+def _np_poly(p, az, rg):
+    out = np.zeros(az.shape)
+    if p is not None:
+        for m in range(p.coeffs.shape[0]):
+            for n in range(p.coeffs.shape[1]):
+                out += p.coeffs[m, n] * az ** m * rg ** n
+    return out
+
+
+@pytest.mark.parametrize("case", list(RESAMP_CASES))
+def test_whole_image_resamp_slc_against_reference_cpp(case):
+    kw = _resamp_case(RESAMP_CASES[case])
+    ours = orc.resamp_slc(**kw, cpp_positions=True)
+    ref, text = ref_cpp.resamp_slc(**kw)
+    assert "Interpolating" in text
+    L, W = kw["slc"].shape
+    oL, oW = kw["out_shape"]
+    # (1): the reference's own unnormalised table -> per-pixel product of its tap sums
+    tab = ref_cpp.sinc_coef(1.0, 8.0, 8192, 0.0, 1).reshape(8, 8192).T.astype(np.float32)
+    S = tab.astype(np.float64).sum(axis=1)
+    ii, jj = np.meshgrid(np.arange(oL, dtype=np.float64), np.arange(oW, dtype=np.float64), indexing="ij")
+    ao = _np_poly(kw.get("az_offsets"), ii + 1, jj + 1) + (kw.get("resid_az") if kw.get("resid_az") is not None else 0.0)
+    ro = _np_poly(kw.get("rg_offsets"), ii + 1, jj + 1) + (kw.get("resid_rg") if kw.get("resid_rg") is not None else 0.0)
+    fa, ka = np.modf(ii + ao)
+    fr, kr = np.modf(jj + ro)
+    scale = S[np.clip((fa * 8192).astype(int), 0, 8191)] * S[np.clip((fr * 8192).astype(int), 0, 8191)]
+    # (3): validity from the two bounds rules; the reference fills its extra far-edge line / sample
+    inside = (ka >= 4) & (kr >= 4)
+    v_f = inside & (ka < L - 5) & (kr < W - 5)
+    v_cpp = inside & (ka < L - 4) & (kr < W - 4)
+    assert ((ours != 0) == v_f).all()
+    assert (ref[v_cpp] != 0).all()
+    # (5): outside its bounds the C++ `continue`s without clearing imgOut (ResampSlc.cpp:171,288-291), so such pixels repeat
+    # the last value written to their column; resamp_slc.f90:176 zeroes the line first.  Not compared.
+    both = v_f
+    assert both.sum() > 0.8 * (oL - 12) * (oW - 12)
+    # (4): float32 accumulation in a different order -- a few ulps of the largest of the 64 terms
+    err = np.abs(ours.astype(np.complex128) * scale - ref)[both]
+    amp = np.abs(ref)[both]
+    assert (err <= 4e-6 * np.maximum(amp, 1.0)).all(), (err / np.maximum(amp, 1.0)).max()
+    assert np.median(err / amp) < 5e-7
+    # and the hook matters exactly when the polynomials vary: without it the same comparison fails by orders of magnitude
+    if RESAMP_CASES[case].get("doppler"):
+        plain = orc.resamp_slc(**kw)
+        assert np.median(np.abs(plain.astype(np.complex128) * scale - ref)[both] / amp) > 1e-3
