@@ -183,6 +183,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
     const double t_lo = __ldg(op.t), t_hi = __ldg(op.t + op.n - 1);
     const double inv_fd = C.fd.order ? rcp_n(C.fd.norm) : 0.0, inv_fdd = C.fdd.order ? rcp_n(C.fdd.norm) : 0.0;
     unsigned int n_out = 0, n_valid = 0, n_conv = 0, n_it = 0;
+    int hint = op.n >> 1; // orbit window of this thread's previous query (poly_window)
     double nlat = 0.0, nlon = 0.0, nhgt = 0.0;
     if (pix0 < C.demwidth) {
         nlat = L.lat[rowoff + pix0];
@@ -235,7 +236,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
                 bad = true;
                 break;
             }
-            poly_state<METHOD>(op, tline, S);
+            poly_state<METHOD>(op, tline, S, hint);
             if (fabs(step) < 1.0e-10) {
                 n_conv++;
                 break;
@@ -256,7 +257,7 @@ k_geo2rdr_poly(const __grid_constant__ GeoConst C, OrbitPolyView op, int line0, 
                     else if (tline > C.tend) outside = true;
                     else if ((tline < t_lo) || (tline > t_hi)) outside = true;
                     else {
-                        poly_state<METHOD>(op, tline, S);
+                        poly_state<METHOD>(op, tline, S, hint);
                         const Vec3 d2 = sub(xyz, S.x);
                         rngpix = sqrt_p(d2.x * d2.x + d2.y * d2.y + d2.z * d2.z);
                         if (rngpix < C.rngstart) outside = true;

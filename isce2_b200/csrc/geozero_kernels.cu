@@ -75,6 +75,7 @@ k_geozero_solve(const __grid_constant__ GeozeroConst C, OrbitPolyView op, Geozer
                 OrbState S;
                 S.x = C.xyz_mid;
                 S.v = C.vel_mid;
+                int hint = op.n >> 1;
 #pragma unroll 1
                 for (int k = 1; k <= 21; k++) { // :322-356
                     n_it++;
@@ -93,7 +94,7 @@ k_geozero_solve(const __grid_constant__ GeozeroConst C, OrbitPolyView op, Geozer
                         rngpix = -10000.0;
                         break;
                     }
-                    poly_state<0>(op, tline, S);
+                    poly_state<0>(op, tline, S, hint);
                     if (fabs(tline - tprev) < 5.0e-7) break;
                 }
                 az_idx = div_n(tline - C.tstart, C.dtaz) + 1; // :359-360

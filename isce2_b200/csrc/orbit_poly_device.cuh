@@ -11,12 +11,27 @@ struct OrbState {
     Vec3 x, v, a;
 };
 
+// Window of the epoch `time`: the first i with t[i] >= time (orbit.c:203-206; epochs ascending), found by walking from
+// `hint` -- the answer of the caller's previous query.  Successive queries of one thread are the Newton iterates of one
+// pixel and then of its neighbours on the same line, a fraction of a state-vector interval apart, so the walk is two loads
+// instead of a scan from the first state vector (which was a quarter of the geo2rdr kernel's stall samples).
 template <int METHOD>
-__device__ __forceinline__ int poly_window(const OrbitPolyView &op, double time)
+__device__ __forceinline__ int poly_window(const OrbitPolyView &op, double time, int &hint)
 {
-    // first i with t[i] >= time (orbit.c:203-206); epochs are ascending
-    int i = 0;
-    while (i < op.n && __ldg(op.t + i) < time) i++;
+    const double *__restrict__ t = op.t;
+    const int n = op.n; // >= the window span (4 / 9): checked when the polynomials are built
+    int i = hint < 1 ? 1 : (hint > n - 1 ? n - 1 : hint);
+    const double below = __ldg(t + i - 1), at = __ldg(t + i); // both in flight at once; usually this is the window already
+    if (!(below < time && at >= time)) {
+        if (below >= time) {
+            i--;
+            while (i > 0 && __ldg(t + i - 1) >= time) i--;
+        } else {
+            i++;
+            while (i < n && __ldg(t + i) < time) i++;
+        }
+    }
+    hint = i;
     const int back = (METHOD == 0) ? 2 : 5, span = (METHOD == 0) ? 4 : 9;
     int w = i - back;
     w = w < 0 ? 0 : w;
@@ -25,9 +40,9 @@ __device__ __forceinline__ int poly_window(const OrbitPolyView &op, double time)
 }
 
 template <int METHOD>
-__device__ __forceinline__ void poly_state(const OrbitPolyView &op, double time, OrbState &S)
+__device__ __forceinline__ void poly_state(const OrbitPolyView &op, double time, OrbState &S, int &hint)
 {
-    const int w = poly_window<METHOD>(op, time);
+    const int w = poly_window<METHOD>(op, time, hint);
     const double ih = __ldg(op.inv_h + w);
     const double s = (time - __ldg(op.tc + w)) * ih;
     constexpr int NC = (METHOD == 0) ? 8 : 9;

@@ -56,16 +56,24 @@ __device__ __forceinline__ int warp_sum(int v)
 }
 
 // Running bounding box of the block (:712-715).  Almost no pixel extends a box that the first lines have opened, so every
-// thread first holds its own point against the box as it stands (four broadcast loads that stay in L2: a stale copy is
-// only ever LESS extreme than the truth, so the test errs on the side of updating) and a warp goes through the reduction
-// and the four contended atomics only when one of its pixels pushes an edge.
-__device__ __forceinline__ void bbox_update(TopoStats *stats, bool have, double mnlat, double mxlat, double mnlon, double mxlon)
+// thread first holds its own point against the box as it stands and a warp goes through the reduction and the four
+// contended atomics only when one of its pixels pushes an edge.  The box "as it stands" is fetched by bbox_peek at the
+// START of the kernel (lane q of each group of four loads edge q; the values ride in one register pair while the pixel
+// is computed and are handed round by shuffles at the end): a stale copy is only ever LESS extreme than the truth, so the
+// test errs on the side of updating, and the load's latency is off the kernel's tail (it was 4.5 % of the final pass's
+// stall samples when it sat in bbox_update).
+__device__ __forceinline__ long long bbox_peek(const TopoStats *stats)
 {
-    bool push = false;
-    if (have) {
-        const long long a = __ldcg(&stats->min_lat), b = __ldcg(&stats->max_lat), c = __ldcg(&stats->min_lon), d = __ldcg(&stats->max_lon);
-        push = order_key(mnlat) < a || order_key(mxlat) > b || order_key(mnlon) < c || order_key(mxlon) > d;
-    }
+    const long long *edge = &stats->min_lat + (threadIdx.x & 3); // min_lat, max_lat, min_lon, max_lon are consecutive
+    return __ldcg(edge);
+}
+__device__ __forceinline__ void bbox_update(TopoStats *stats, long long peek, bool have, double mnlat, double mxlat, double mnlon,
+                                            double mxlon)
+{
+    const int base = threadIdx.x & 28;
+    const long long a = __shfl_sync(0xffffffffu, peek, base), b = __shfl_sync(0xffffffffu, peek, base + 1),
+                    c = __shfl_sync(0xffffffffu, peek, base + 2), d = __shfl_sync(0xffffffffu, peek, base + 3);
+    const bool push = have && (order_key(mnlat) < a || order_key(mxlat) > b || order_key(mnlon) < c || order_key(mxlon) > d);
     if (!__any_sync(0xffffffffu, push)) return;
     mnlat = warp_min(mnlat); mxlat = warp_max(mxlat); mnlon = warp_min(mnlon); mxlon = warp_max(mxlon);
     if ((threadIdx.x & 31) == 0) {
@@ -416,6 +424,7 @@ k_topo_final(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
     const int row = blockIdx.x / bpl;
     const int seg = blockIdx.x - row * bpl;
     load_line_state(sL, states, row);
+    const long long peek = bbox_peek(stats);
     __syncthreads();
     const int pix = seg * blockDim.x + threadIdx.x;
     double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
@@ -443,7 +452,7 @@ k_topo_final(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
         mnlat = mxlat = R.lat;
         mnlon = mxlon = R.lon;
     }
-    bbox_update(stats, pix < C.width, mnlat, mxlat, mnlon, mxlon);
+    bbox_update(stats, peek, pix < C.width, mnlat, mxlat, mnlon, mxlon);
 }
 
 // k_topo_fused: solve + final pass in one kernel.  Used for the light interpolators (bilinear, nearest), whose whole
@@ -472,6 +481,7 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
     int conv = 0, iters = 0;
     solve_strip<METHOD, REF, false>(C, sL, line, strip0, S, strip_n, s_z[warp], conv, iters);
     __syncwarp();
+    const long long peek = bbox_peek(stats);
     // final pass over the strip, consecutive lanes on consecutive pixels (coalesced layer stores)
     double mnlat = 1e300, mxlat = -1e300, mnlon = 1e300, mxlon = -1e300;
     const size_t w = (size_t)C.width;
@@ -498,7 +508,7 @@ k_topo_fused(const __grid_constant__ TopoConst C, const LineState *__restrict__ 
         mnlat = fmin(mnlat, R.lat); mxlat = fmax(mxlat, R.lat);
         mnlon = fmin(mnlon, R.lon); mxlon = fmax(mxlon, R.lon);
     }
-    bbox_update(stats, lane < strip_n, mnlat, mxlat, mnlon, mxlon);
+    bbox_update(stats, peek, lane < strip_n, mnlat, mxlat, mnlon, mxlon);
     conv = warp_sum(conv);
     iters = warp_sum(iters);
     if (lane == 0 && strip_n > 0) {

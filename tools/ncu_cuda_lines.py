@@ -22,7 +22,7 @@ def main(rep, kernel, top=40):
     src = {}
     cur = None
     for r in rows:
-        if len(r) == 2 and r[0] == "File Name":
+        if len(r) == 2 and r[0] in ("File Name", "File Path"):
             fname = r[1].split("/")[-1]
             continue
         if r and r[0] == "Line No":
@@ -31,9 +31,10 @@ def main(rep, kernel, top=40):
         if hdr is None or len(r) < len(hdr):
             continue
         d = dict(zip(hdr, r))  # the second "Source" column (SASS text) overwrites the first: keep the CUDA text separately
-        if r[0].strip():
+        if r[0].strip():  # a CUDA line: its own row repeats the sum of the SASS rows below it, which are what is counted
             cur = (fname, int(r[0]))
             src[cur] = r[1].strip()
+            continue
         if cur is None:
             continue
         try:
