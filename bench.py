@@ -928,12 +928,15 @@ def measure_component(args, ranks, capi, dev, name, lines=None):
         for i in range(3):
             d = tempfile.mkdtemp(prefix="b200_bench_", dir=base)
             try:
+                pw0 = capi.host_file_bytes() if hasattr(capi, "host_file_bytes") else 0
                 t0 = time.perf_counter()
                 with contextlib.redirect_stdout(sys.stderr):  # the Components print like the reference's; stdout carries the JSON line
                     info = comp.run_components(sc, sec, dem_img, d, dem_method=w["dem_method"], orbit_method=w["orbit_method"],
                                                inc=w["inc"], mask=w["mask"], devices=[dev])
                 times.append(time.perf_counter() - t0)
                 out["bytes_written"] = info.get("bytes_written")
+                # of which by pwrite on the rasters' files (image.file_backed) rather than through their mappings
+                out["bytes_written_with_pwrite"] = (capi.host_file_bytes() - pw0) if hasattr(capi, "host_file_bytes") else None
                 gt = info.get("gpu_timings") or []
                 out["library_call_ms"] = [round(float(g["ms_total"]), 1) for g in gt]  # inside b200_topo_geo2rdr_run
             finally:

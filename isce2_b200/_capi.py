@@ -139,7 +139,7 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
            "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
            "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks", "b200_geo_plan_freeze_geometry",
-           "b200_d2h_floor"]
+           "b200_d2h_floor", "b200_host_file_register", "b200_host_file_unregister", "b200_host_file_bytes"]
 
 _lib = None
 
@@ -184,6 +184,10 @@ def lib():
     L.b200_free_pinned.restype = None
     L.b200_fp64_peak.argtypes = [C.c_int, _dp] + err
     L.b200_d2h_floor.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, _fp] + err
+    L.b200_host_file_register.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_longlong] + err
+    L.b200_host_file_unregister.argtypes = [C.c_void_p]
+    L.b200_host_file_bytes.restype = C.c_ulonglong
+    L.b200_host_file_bytes.argtypes = []
     L.b200_device_primitive.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Orbit), _dp, _dp] + err
     L.b200_geozero_grid.argtypes = [C.POINTER(GeozeroParams), C.POINTER(C.c_int), C.POINTER(C.c_int)] + err
     L.b200_geozero_plan_create.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d),
@@ -245,6 +249,22 @@ def d2h_floor(host, nbytes=None, chunk_bytes=0, device=0):
     e = _errbuf()
     _check(lib().b200_d2h_floor(device, host.ctypes.data_as(C.c_void_p), nbytes, int(chunk_bytes), C.byref(ms), e, 512), e)
     return float(ms.value)
+
+
+def host_file_register(address, nbytes, fd, file_offset):
+    """Tell the library that host addresses [address, address + nbytes) are a shared writable mapping of the file open as
+    `fd`, starting at file_offset: results bound for them are written with pwrite (include/b200geom.h)."""
+    e = _errbuf()
+    _check(lib().b200_host_file_register(C.c_void_p(address), int(nbytes), int(fd), int(file_offset), e, 512), e)
+
+
+def host_file_bytes():
+    """Bytes the copier threads have written with pwrite since the library was loaded."""
+    return int(lib().b200_host_file_bytes())
+
+
+def host_file_unregister(address):
+    return lib().b200_host_file_unregister(C.c_void_p(address)) == B200_OK
 
 
 def pinned_empty(shape, dtype):

@@ -16,7 +16,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <cerrno>
 #include <mutex>
+#include <unistd.h>
+#include <shared_mutex>
 #include <new>
 #include <memory>
 #include <thread>
@@ -224,7 +227,48 @@ int sink_threads()
     return n;
 }
 
-// process-wide pool of copier threads: a task is one memcpy of a part of a finished slot
+// File-backed destinations (b200_host_file_register): a range of host addresses that is a shared mapping of a file.  The
+// copier threads write results bound for such a range with pwrite on the file instead of storing through the mapping:
+// the page cache is filled without one page fault per 4 KB of a raster that does not exist yet (measured on tmpfs:
+// 16.5 GB in 1.5 s against 1.9 s through the mapping).  The mapping sees the same pages.
+struct FileRange {
+    const char *base;
+    size_t bytes;
+    int fd; // our own duplicate of the caller's descriptor
+    long long off;
+};
+std::shared_mutex g_file_mu;
+std::vector<FileRange> g_files;
+std::atomic<unsigned long long> g_file_bytes{0}; // written with pwrite so far (b200_host_file_bytes)
+bool file_lookup(const void *dst, size_t n, int &fd, long long &off)
+{
+    std::shared_lock<std::shared_mutex> lk(g_file_mu);
+    const char *p = (const char *)dst;
+    for (const FileRange &r : g_files)
+        if (p >= r.base && p + n <= r.base + r.bytes) {
+            fd = r.fd;
+            off = r.off + (long long)(p - r.base);
+            return true;
+        }
+    return false;
+}
+// pwrite of the whole part; false (nothing more written) on the first error other than EINTR
+bool pwrite_all(int fd, const char *src, size_t n, long long off, size_t &done)
+{
+    done = 0;
+    while (done < n) {
+        const ssize_t w = pwrite(fd, src + done, n - done, (off_t)(off + (long long)done));
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        if (w == 0) return false;
+        done += (size_t)w;
+    }
+    return true;
+}
+
+// process-wide pool of copier threads: a task is one memcpy (or pwrite) of a part of a finished slot
 class CopyPool {
   public:
     struct Task {
@@ -236,6 +280,8 @@ class CopyPool {
         std::atomic<int> *pending; // per slot: parts still to copy; 0 == slot reusable
         std::mutex *mu;            // owner's mutex / cv, signalled when pending reaches 0
         std::condition_variable *cv;
+        int fd = -1;               // >= 0: dst lies in a registered file mapping; write at file offset foff instead
+        long long foff = 0;
     };
     static CopyPool &get()
     {
@@ -273,7 +319,13 @@ class CopyPool {
                 cur = t.device;
             }
             if (t.ready) cudaEventSynchronize(t.ready); // (host -> slot copies of HostSource have nothing to wait for)
-            memcpy(t.dst, t.src, t.bytes);
+            size_t done = 0;
+            if (t.fd >= 0) {
+                pwrite_all(t.fd, (const char *)t.src, t.bytes, t.foff, done);
+                g_file_bytes.fetch_add(done, std::memory_order_relaxed);
+            }
+            if (done < t.bytes) memcpy((char *)t.dst + done, (const char *)t.src + done, t.bytes - done); // no file / write failed
+
             if (t.pending->fetch_sub(1) == 1) {
                 std::lock_guard<std::mutex> lk(*t.mu);
                 t.cv->notify_all();
@@ -308,6 +360,9 @@ class HostSink {
             for (int i = 0; i < kSinkSlots; i++) pending_[i].store(0);
         }
         const int nt = CopyPool::get().size();
+        int fd = -1;
+        long long foff = 0;
+        if (!file_lookup(dst, bytes, fd, foff)) fd = -1;
         for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
             const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
             const int k = next_;
@@ -328,7 +383,7 @@ class HostSink {
             for (int q = 0; q < nparts; q++) {
                 const size_t po = (size_t)q * part, pn = n - po < part ? n - po : part;
                 CopyPool::get().push(CopyPool::Task{ring_->ev[k], device_, (char *)dst + o + po, ring_->buf[k] + po, pn, &pending_[k],
-                                                    &mu_, &cv_});
+                                                    &mu_, &cv_, fd, foff + (long long)(o + po)});
             }
         }
         return cudaSuccess;
@@ -2363,6 +2418,36 @@ extern "C" void b200_free_pinned(void *p)
 
 // Device -> page-locked host copy of `bytes` from a scratch device buffer, in chunks of chunk_bytes on one stream: the
 // floor of any end-to-end call that has to deliver that many bytes of results (bench.py runs it on all ranks at once)
+extern "C" int b200_host_file_register(const void *base, size_t bytes, int fd, long long file_offset, char *err, size_t errlen)
+{
+    if (!base || !bytes || fd < 0 || file_offset < 0) return fail(err, errlen, B200_EINVAL, "b200_host_file_register: bad arguments");
+    const int mine = dup(fd);
+    if (mine < 0) return fail(err, errlen, B200_EINVAL, "b200_host_file_register: cannot duplicate descriptor %d (errno %d)", fd, errno);
+    std::unique_lock<std::shared_mutex> lk(g_file_mu);
+    for (const FileRange &r : g_files)
+        if ((const char *)base < r.base + r.bytes && r.base < (const char *)base + bytes) {
+            lk.unlock();
+            close(mine);
+            return fail(err, errlen, B200_EINVAL, "b200_host_file_register: the range overlaps a registered one");
+        }
+    g_files.push_back(FileRange{(const char *)base, bytes, mine, file_offset});
+    return B200_OK;
+}
+
+extern "C" unsigned long long b200_host_file_bytes(void) { return g_file_bytes.load(); }
+
+extern "C" int b200_host_file_unregister(const void *base)
+{
+    std::unique_lock<std::shared_mutex> lk(g_file_mu);
+    for (size_t i = 0; i < g_files.size(); i++)
+        if (g_files[i].base == (const char *)base) {
+            close(g_files[i].fd);
+            g_files.erase(g_files.begin() + (long)i);
+            return B200_OK;
+        }
+    return B200_EINVAL;
+}
+
 extern "C" int b200_d2h_floor(int device, void *host, size_t bytes, size_t chunk_bytes, float *ms, char *err, size_t errlen)
 {
     int rc = select_device(device, err, errlen);

@@ -133,14 +133,15 @@ class Geo2rdr(Component):
             except Exception as e:
                 errors[i] = e
 
-        if n == 1:
-            work(0)
-        else:
-            th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
+        with IF.file_backed(list(outs.values())):  # the .off / .rdr rasters being written are file mappings (image.file_backed)
+            if n == 1:
+                work(0)
+            else:
+                th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+                for x in th:
+                    x.start()
+                for x in th:
+                    x.join()
         for e in errors:
             if e is not None:
                 raise e

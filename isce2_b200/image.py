@@ -8,6 +8,7 @@ A real ``isceobj`` image object can be passed wherever one of these is expected:
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import xml.etree.ElementTree as ET
 
@@ -399,6 +400,41 @@ def output_memmap(img, length, width, bands=1):
     need = length * width * bands * dt.itemsize
     mode = "r+" if os.path.exists(fn) and os.path.getsize(fn) == need else "w+"
     return np.memmap(fn, dtype=dt, mode=mode, shape=_shape(length, width, bands, "BIL"))
+
+
+@contextlib.contextmanager
+def file_backed(arrays):
+    """For the duration of a library call: every writable numpy.memmap among `arrays` (None entries allowed) is declared
+    to the library as the file mapping it is (b200_host_file_register), so that results are written into the file with
+    pwrite instead of through the mapping -- the same pages, without a page fault per 4 KB of a raster that does not exist
+    yet.  B200_FILE_WRITES=0 in the environment leaves everything to the mapping."""
+    from . import _capi
+    done = []
+    try:
+        if os.environ.get("B200_FILE_WRITES", "1") != "0":
+            for a in arrays:
+                if not isinstance(a, np.memmap) or a.size == 0 or getattr(a, "mode", "r") not in ("r+", "w+") or not a.filename:
+                    continue
+                if not (a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]):
+                    continue
+                addr = a.ctypes.data
+                if addr in done:
+                    continue
+                try:
+                    fd = os.open(a.filename, os.O_RDWR)
+                except OSError:
+                    continue
+                try:
+                    _capi.host_file_register(addr, a.nbytes, fd, int(a.offset))
+                    done.append(addr)
+                except _capi.B200Error:  # e.g. two images over one file: the mapping still works
+                    pass
+                finally:
+                    os.close(fd)  # the library holds its own duplicate
+        yield
+    finally:
+        for addr in done:
+            _capi.host_file_unregister(addr)
 
 
 def read_view(path):

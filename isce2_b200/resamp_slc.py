@@ -69,14 +69,15 @@ class Resamp_slc(Component):
             ra, rr = np.asarray(ra, np.float64), np.asarray(rr, np.float64)
         out = IF.output_memmap(self.imageOut, ol, ow)  # ours, or an image object the caller handed in
         direct = out.dtype == np.complex64 and out.flags['C_CONTIGUOUS'] and out.shape == (ol, ow)
-        r = _capi.resamp_slc_run(slc[:int(self.inputLines)], (ol, ow), wvl=float(self.radarWavelength),
-                                 slr=float(self.slantRangePixelSpacing), r0=float(self.startingRange),
-                                 ref_wvl=float(self.referenceWavelength), ref_r0=float(self.referenceStartingRange),
-                                 ref_slr=float(self.referenceSlantRangePixelSpacing), flatten=bool(self.flatten),
-                                 rg_carrier=self._poly(self.rangeCarrierPoly), az_carrier=self._poly(self.azimuthCarrierPoly),
-                                 rg_offsets=self._poly(self.rangeOffsetsPoly), az_offsets=self._poly(self.azimuthOffsetsPoly),
-                                 doppler=self._poly(self.dopplerPoly), resid_az=ra, resid_rg=rr, out=out if direct else None,
-                                 device=int(self.gpuDevice or 0))
+        with IF.file_backed([out] if direct else []):
+            r = _capi.resamp_slc_run(slc[:int(self.inputLines)], (ol, ow), wvl=float(self.radarWavelength),
+                                     slr=float(self.slantRangePixelSpacing), r0=float(self.startingRange),
+                                     ref_wvl=float(self.referenceWavelength), ref_r0=float(self.referenceStartingRange),
+                                     ref_slr=float(self.referenceSlantRangePixelSpacing), flatten=bool(self.flatten),
+                                     rg_carrier=self._poly(self.rangeCarrierPoly), az_carrier=self._poly(self.azimuthCarrierPoly),
+                                     rg_offsets=self._poly(self.rangeOffsetsPoly), az_offsets=self._poly(self.azimuthOffsetsPoly),
+                                     doppler=self._poly(self.dopplerPoly), resid_az=ra, resid_rg=rr, out=out if direct else None,
+                                     device=int(self.gpuDevice or 0))
         if not direct:
             out[...] = r['slc'].reshape(out.shape)
         self.numValid = r['num_valid']

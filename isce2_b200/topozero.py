@@ -130,14 +130,16 @@ class Topo(Component):
             except Exception as e:  # surfaced below, in the caller's thread
                 errors[i] = e
 
-        if n == 1:
-            work(0)
-        else:
-            th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
+        # the rasters being written are file mappings: say so, and the library writes them with pwrite (image.file_backed)
+        with IF.file_backed(list(outs.values()) + [v for c in chained for v in c["outs"].values()]):
+            if n == 1:
+                work(0)
+            else:
+                th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+                for x in th:
+                    x.start()
+                for x in th:
+                    x.join()
         for e in errors:
             if e is not None:
                 raise e

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in include/b200geom.h but not exported by libb200geom.so"
     assert sorted(_capi.EXPORTS) == declared
-    assert lib.b200_abi_version() == 6  # 2: geozero + resamp_slc; 3: fused topo+geo2rdr; 4: looks + mask projection; 5: frozen stack geometry; 6: d2h floor, pageable sinks
+    assert lib.b200_abi_version() == 7  # 2: geozero + resamp_slc; 3: fused topo+geo2rdr; 4: looks + mask projection; 5: frozen stack geometry; 6: d2h floor, pageable sinks; 7: file-backed destinations
 
 
 def test_struct_layouts_match_header():
@@ -101,3 +101,41 @@ def test_argument_validation_precedes_device_use():
     with pytest.raises(_capi.B200Error) as ei:
         _capi.topo_run(p, sc.dem, sc.orbit_t, sc.orbit_pos, sc.orbit_vel, sc.doppler_coeffs, [[sc.r0, sc.dr]])
     assert ei.value.code == -1
+
+
+def test_file_backed_destination_registry(tmp_path):
+    """b200_host_file_register / _unregister keep a table of address ranges that are file mappings (no GPU involved):
+    overlaps and bad arguments are refused, image.file_backed registers writable memmaps only and takes everything back."""
+    import numpy as np
+
+    from isce2_b200 import _capi
+    from isce2_b200 import image as IF
+    a = np.memmap(str(tmp_path / "a.bin"), dtype=np.float64, mode="w+", shape=(64, 512))
+    b = np.memmap(str(tmp_path / "b.bin"), dtype=np.float32, mode="w+", shape=(64, 2, 512))
+    ro = np.memmap(str(tmp_path / "a.bin"), dtype=np.float64, mode="r", shape=(64, 512))
+    fd = os.open(str(tmp_path / "a.bin"), os.O_RDWR)
+    try:
+        _capi.host_file_register(a.ctypes.data, a.nbytes, fd, 0)
+        with pytest.raises(_capi.B200Error):  # overlapping range
+            _capi.host_file_register(a.ctypes.data + 4096, 4096, fd, 4096)
+        with pytest.raises(_capi.B200Error):
+            _capi.host_file_register(b.ctypes.data, b.nbytes, -1, 0)
+        assert _capi.host_file_unregister(a.ctypes.data)
+        assert not _capi.host_file_unregister(a.ctypes.data)
+    finally:
+        os.close(fd)
+    with IF.file_backed([a, None, b, ro, np.zeros(8), a]):
+        assert not _capi.host_file_unregister(ro.ctypes.data)  # read-only mappings and plain arrays are not declared
+        with pytest.raises(_capi.B200Error):                   # a and b are
+            fd = os.open(str(tmp_path / "b.bin"), os.O_RDWR)
+            try:
+                _capi.host_file_register(b.ctypes.data, b.nbytes, fd, 0)
+            finally:
+                os.close(fd)
+    assert not _capi.host_file_unregister(a.ctypes.data) and not _capi.host_file_unregister(b.ctypes.data)
+    os.environ["B200_FILE_WRITES"] = "0"
+    try:
+        with IF.file_backed([a]):
+            assert not _capi.host_file_unregister(a.ctypes.data)
+    finally:
+        del os.environ["B200_FILE_WRITES"]

@@ -28,12 +28,14 @@ def test_ragged_and_tiny_shapes(method, shape):
     assert st["mask"]["hist_gpu"] == st["mask"]["hist_cpu"]
 
 
-def test_single_pixel_image():
-    # width 1: the reference's layover pass indexes zsch(2) of a one-element line (topozero.f90:748-755), so no mask here
+def test_single_sample_lines_are_an_argument_error():
+    # width 1: the reference's layover pass indexes zsch(2) of a one-element line (topozero.f90:748-755) and its bounding box
+    # corners coincide; the library refuses such a grid instead of guessing (B200_EINVAL), with or without the mask
     sc = pu.rough_scene(1, 1)
-    g = pu.gpu_topo(sc, dem_method="BIQUINTIC", want_mask=False)
-    c = pu.cpu_topo(sc, dem_method="BIQUINTIC", want_mask=False)
-    _assert_topo(pu.compare_topo(g, c), check_mask=False)
+    for want_mask in (False, True):
+        with pytest.raises(_capi.B200Error) as ei:
+            pu.gpu_topo(sc, dem_method="BIQUINTIC", want_mask=want_mask)
+        assert ei.value.code == -1 and "bad radar grid" in str(ei.value)
 
 
 def _cut_dem(sc, frac_lat=(0.35, 0.65), frac_lon=(0.3, 0.7)):

@@ -205,6 +205,14 @@ def test_geo2rdr_orbit_barely_covering_the_scene():
     assert n_mismatch == 0, diag
 
 
+def _grow_and_map(path, dtype, shape, offset):
+    """A writable mapping that starts `offset` bytes into an existing file (grown to hold the array)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    with open(path, "r+b") as f:
+        f.truncate(offset + n)
+    return np.memmap(str(path), dtype=dtype, mode="r+", shape=shape, offset=offset)
+
+
 def test_pageable_and_page_locked_destinations_agree(tmp_path):
     """Results bound for pageable memory (plain numpy arrays, a numpy.memmap over a new file) go through the bounce ring
     and the copier threads, page-locked ones are written by DMA: same bytes.  Sized so that every layer spans several
@@ -233,11 +241,31 @@ def test_pageable_and_page_locked_destinations_agree(tmp_path):
     pinned = run(lambda k, s, d: _capi.pinned_empty(s, d))
     pageable = run(lambda k, s, d: np.full(s, 77, d))
     mm = run(lambda k, s, d: np.memmap(str(tmp_path / (k + ".bin")), dtype=d, mode="w+", shape=s))
+    # ... and memmaps declared to the library as the file mappings they are are written with pwrite (image.file_backed):
+    # the mapping sees the same pages; a mapping that starts inside its file (offset) lands where it should
+    from isce2_b200 import image as IF
+
+    def map_inside_a_file(k, s, d):
+        with open(tmp_path / (k + ".fb"), "wb") as f:
+            f.write(b"\xab" * 8192)  # a header the library must not touch
+        return _grow_and_map(tmp_path / (k + ".fb"), d, s, 8192)
+
+    pre = {k: map_inside_a_file(k, s, d) for k, (s, d) in shapes.items()}
+    pre.update({k: map_inside_a_file(k, (sc.length, sc.width), np.float32) for k in ("azoff", "rgoff")})
+    before = _capi.host_file_bytes()
+    with IF.file_backed(list(pre.values())):
+        fb = run(lambda k, s, d: pre[k])
+    assert _capi.host_file_bytes() - before == sum(a.nbytes for a in pre.values())  # every byte went through pwrite
+    assert not _capi.host_file_unregister(pre["lat"].ctypes.data)  # the context manager has taken the registrations back
     for k in pinned:
         assert np.array_equal(pinned[k], pageable[k], equal_nan=True), k
         assert np.array_equal(pinned[k], np.asarray(mm[k]), equal_nan=True), k
         mm[k].flush()
         assert np.array_equal(np.fromfile(tmp_path / (k + ".bin"), pinned[k].dtype).reshape(pinned[k].shape), pinned[k], equal_nan=True)
+        assert np.array_equal(pinned[k], np.asarray(fb[k]), equal_nan=True), k
+        raw = np.fromfile(tmp_path / (k + ".fb"), np.uint8)
+        assert (raw[:8192] == 0xab).all(), k
+        assert np.array_equal(raw[8192:].view(pinned[k].dtype).reshape(pinned[k].shape), pinned[k], equal_nan=True), k
     # inputs in pageable memory (memmaps of the rasters just written) go up through the mirror-image bounce path
     gp64 = _capi.geo_params(length=kw["length"], width=kw["width"], dem_shape=(sc.length, sc.width), r0=kw["r0"], dr=kw["dr"],
                             prf=kw["prf"], t0=kw["t0"], wvl=kw["wvl"], side=kw["side"])

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""How the Component path (createTopozero().topo() chained with createGeo2rdr(), files on tmpfs) and the file-write floors
+scale with the number of host threads (run on the GPU box):
+
+    python tools/component_threads_sweep.py [LINES]
+
+The copier pool is sized once per process (B200_COPY_THREADS), so every setting runs in its own child process."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CHILD = r"""
+import contextlib, json, os, shutil, sys, tempfile, time
+sys.path.insert(0, %r)
+import bench
+from isce2_b200 import synth_components as comp
+w, sc, sec = bench.build_workload("c2", %s)
+base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+demdir = tempfile.mkdtemp(prefix="b200_sweep_dem_", dir=base)
+times, lib = [], []
+try:
+    dem_img = comp.prepare_dem(sc, os.path.join(demdir, "dem.dem"))
+    for i in range(3):
+        d = tempfile.mkdtemp(prefix="b200_sweep_", dir=base)
+        try:
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sys.stderr):
+                info = comp.run_components(sc, sec, dem_img, d, dem_method=w["dem_method"], orbit_method=w["orbit_method"],
+                                           inc=w["inc"], mask=w["mask"], devices=[0])
+            times.append(time.perf_counter() - t0)
+            lib.append([round(float(g["ms_total"]), 1) for g in (info.get("gpu_timings") or [])])
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+finally:
+    shutil.rmtree(demdir, ignore_errors=True)
+print(json.dumps({"copy_threads": os.environ.get("B200_COPY_THREADS"), "file_writes": os.environ.get("B200_FILE_WRITES", "1"),
+                  "step_s": [round(t, 3) for t in times], "library_ms": lib}))
+"""
+
+
+def main():
+    lines = sys.argv[1] if len(sys.argv) > 1 else "None"
+    import bench
+    w, sc, sec = bench.build_workload("c2", None if lines == "None" else int(lines))
+    nbytes = sc.pixels * 49
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    for how in ("mmap", "pwrite"):
+        for th in (4, 8, 12, 16):
+            r = bench.file_write_floor(base, nbytes, threads=th, how=how)
+            print(json.dumps({"floor": how, "threads": th, "seconds": round(r["seconds"], 3), "GBps": round(r["GBps"], 2)}), flush=True)
+    for th, fw in ((4, 1), (8, 1), (12, 1), (16, 1), (8, 0), (16, 0)):
+        env = dict(os.environ, B200_COPY_THREADS=str(th), B200_FILE_WRITES=str(fw))
+        out = subprocess.run([sys.executable, "-c", CHILD % (ROOT, lines)], env=env, capture_output=True, text=True)
+        print((out.stdout.strip().splitlines() or [out.stderr[-400:]])[-1], flush=True)
+
+
+if __name__ == "__main__":
+    main()
