@@ -967,7 +967,7 @@ def file_write_floor(base, nbytes, nfiles=8, threads=None, how="mmap"):
     import shutil
     import tempfile
     import threading as th
-    threads = threads or max(2, min(8, (os.cpu_count() or 2) // 2))
+    threads = threads or max(2, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)))  # = the library's copier pool
     per = (nbytes // nfiles) & ~4095
     src = np.ones(64 << 20, np.uint8)
     d = tempfile.mkdtemp(prefix="b200_floor_", dir=base)

@@ -410,15 +410,16 @@ void b200_free_pinned(void *p);
 /* Host buffers handed to any entry point may be page-locked (b200_alloc_pinned, cudaHostRegister: copied by DMA at PCIe
  * speed) or ordinary pageable memory such as a numpy.memmap over the raster being written -- what the reference's
  * callers have (Topozero.py:274-302, Geo2rdr.py:321-384).  Results bound for pageable memory are bounced through a
- * page-locked ring and copied out by a pool of B200_COPY_THREADS host threads (environment; default half the host
- * threads, at most 8; 0 = plain cudaMemcpy), so that the page faults of a file that does not exist yet are paid in
+ * page-locked ring and copied out by a pool of B200_COPY_THREADS host threads (environment; default the CPUs of the
+ * process, at most 16; 0 = plain cudaMemcpy), so that the page faults of a file that does not exist yet are paid in
  * parallel with the DMA instead of by one thread. */
 /* File-backed destinations.  When a pageable output buffer is a shared, writable mapping of a file (numpy.memmap of the
  * raster being written: what the reference's Components hand over, Topozero.py:274-302), the caller may say so: results
  * bound for [base, base + bytes) are then written by the copier threads with pwrite(fd, ..., file_offset + (dst - base))
  * instead of stores through the mapping -- same pages of the page cache, without a page fault per 4 KB of a file that
- * does not exist yet (tmpfs: 16.5 GB in 1.5 s against 1.9 s).  The library keeps its own duplicate of fd until the range
- * is unregistered; a failed write falls back to the store.  Ranges must not overlap. */
+ * does not exist yet.  Whether that is faster depends on the file system: on the tmpfs of the B200 boxes measured it was
+ * not, so the Components use it only with B200_FILE_WRITES=1.  The library keeps its own duplicate
+ * of fd until the range is unregistered; a failed write falls back to the store.  Ranges must not overlap. */
 int b200_host_file_register(const void *base, size_t bytes, int fd, long long file_offset, char *err, size_t errlen);
 int b200_host_file_unregister(const void *base); /* B200_OK, or B200_EINVAL when base was not registered */
 unsigned long long b200_host_file_bytes(void);   /* bytes written with pwrite since the library was loaded */

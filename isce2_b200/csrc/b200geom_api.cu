@@ -18,6 +18,7 @@
 #include <deque>
 #include <cerrno>
 #include <mutex>
+#include <sched.h>
 #include <unistd.h>
 #include <shared_mutex>
 #include <new>
@@ -164,8 +165,8 @@ cudaError_t dmalloc(T **p, size_t bytes)
 // single threaded: the driver bounces every 64 KB through its own small staging buffer and one CPU thread pays all the
 // page faults of a file that does not exist yet.  For those the sink bounces through its own ring of page-locked slots
 // and a pool of copier threads that memcpy finished slots into the destination in parallel (page faults of a fresh
-// mapping included), while the DMA engine fills the next slots.  B200_COPY_THREADS (default: half the host threads, at
-// most 8) sizes the pool; B200_COPY_THREADS=0 disables the bounce path (plain cudaMemcpyAsync for everything).
+// mapping included), while the DMA engine fills the next slots.  B200_COPY_THREADS (default: the CPUs of the
+// process, at most 16) sizes the pool; B200_COPY_THREADS=0 disables the bounce path (plain cudaMemcpyAsync for everything).
 // -------------------------------------------------------------------------------------------------
 constexpr size_t kSinkSlotBytes = 32u << 20; // one bounce slot
 constexpr int kSinkSlots = 6;                // ring per sink: 192 MB page-locked, cached between calls
@@ -220,17 +221,24 @@ int sink_threads()
 {
     static const int n = [] {
         if (const char *e = getenv("B200_COPY_THREADS")) return atoi(e) < 0 ? 0 : (atoi(e) > 64 ? 64 : atoi(e));
-        unsigned hc = std::thread::hardware_concurrency();
-        int t = (int)(hc / 2);
-        return t < 2 ? 2 : (t > 8 ? 8 : t);
+        // every CPU this process may run on, at most 16: the copies are page-fault bound and scale with threads up to
+        // there (tmpfs, 16.5 GB of fresh rasters: 2.9 s with 4, 2.1 s with 8, 1.8 s with 16 -- profiles/r02_component_threads_sweep.log)
+        int t = 0;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) t = CPU_COUNT(&set);
+        if (t <= 0) t = (int)std::thread::hardware_concurrency();
+        return t < 2 ? 2 : (t > 16 ? 16 : t);
     }();
     return n;
 }
 
 // File-backed destinations (b200_host_file_register): a range of host addresses that is a shared mapping of a file.  The
 // copier threads write results bound for such a range with pwrite on the file instead of storing through the mapping:
-// the page cache is filled without one page fault per 4 KB of a raster that does not exist yet (measured on tmpfs:
-// 16.5 GB in 1.5 s against 1.9 s through the mapping).  The mapping sees the same pages.
+// the page cache is filled without one page fault per 4 KB of a raster that does not exist yet; the mapping sees the same
+// pages.  Measured (profiles/r02_component_threads_sweep.log): plain pwrite of 16.5 GB into new tmpfs files beats stores
+// into fresh mappings (1.1 s against 1.7 s with 16 threads), but from the bounce slots, next to the DMA traffic, it does
+// not: 2.6 s per swath at any thread count against 1.8-2.1 s through the mapping.  The Components therefore use it only
+// when asked to (B200_FILE_WRITES=1).
 struct FileRange {
     const char *base;
     size_t bytes;

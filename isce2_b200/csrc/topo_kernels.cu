@@ -320,10 +320,10 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
             const bool secondary = it >= nprimary;
             Vec3 xyz, xyz_prev = v3(0.0, 0.0, 0.0);
             if (secondary) xyz_prev = geodetic_to_xyz<REF>(C, lat, lon, z);
-            iters++;
             it++;
+            bool converged = false;
             if (topo_iterate<METHOD, REF>(C, sL, P, lat, lon, z, zsch, xyz)) {
-                conv++;
+                converged = true;
                 finished = true;
             } else {
                 if (secondary) {
@@ -340,7 +340,11 @@ __device__ __forceinline__ void solve_strip(const TopoConst &C, const LineState 
                 }
                 finished = it >= nmax;
             }
-            if (finished) zrow[slot] = zsch;
+            if (finished) { // the statistics are touched once per pixel, not once per iteration (they live in local memory)
+                zrow[slot] = zsch;
+                iters += it;
+                conv += converged ? 1 : 0;
+            }
         }
         // lanes without work take the next pixels of the run, in lane order
         const bool need = !active || finished;
