@@ -169,11 +169,33 @@ cudaError_t dmalloc(T **p, size_t bytes)
 // process, at most 16) sizes the pool; B200_COPY_THREADS=0 disables the bounce path (plain cudaMemcpyAsync for everything).
 // -------------------------------------------------------------------------------------------------
 constexpr size_t kSinkSlotBytes = 32u << 20; // one bounce slot
-constexpr int kSinkSlots = 6;                // ring per sink: 192 MB page-locked, cached between calls
+constexpr int kSinkSlotsMax = 24;
+// slots of the ring of one sink (32 MB each, page-locked, cached between calls).  B200_SINK_SLOTS overrides (2 .. 24).
+int sink_slots()
+{
+    static const int n = [] {
+        int v = 6;
+        if (const char *e = getenv("B200_SINK_SLOTS")) v = atoi(e);
+        return v < 2 ? 2 : (v > kSinkSlotsMax ? kSinkSlotsMax : v);
+    }();
+    return n;
+}
+// parts a slot bound for a registered file is written in (B200_FILE_PARTS; default 1: one pwrite per slot -- writers of
+// neighbouring pieces of one file mostly wait for each other, whole slots mostly belong to different rasters)
+int file_parts()
+{
+    static const int n = [] {
+        int v = 1;
+        if (const char *e = getenv("B200_FILE_PARTS")) v = atoi(e);
+        return v < 1 ? 1 : (v > 64 ? 64 : v);
+    }();
+    return n;
+}
+#define kSinkSlots sink_slots()
 
 struct SinkRing {
-    char *buf[kSinkSlots] = {};
-    cudaEvent_t ev[kSinkSlots] = {}; // events belong to the device that was current when they were created
+    char *buf[kSinkSlotsMax] = {};
+    cudaEvent_t ev[kSinkSlotsMax] = {}; // events belong to the device that was current when they were created
     int device = -1;
     bool ok = false;
 };
@@ -382,8 +404,9 @@ class HostSink {
             cudaError_t e = cudaMemcpyAsync(ring_->buf[k], (const char *)src + o, n, cudaMemcpyDeviceToHost, s_);
             if (e == cudaSuccess) e = cudaEventRecord(ring_->ev[k], s_);
             if (e != cudaSuccess) return e;
-            // parts of >= 1 MB, page aligned within the slot, one per copier thread
-            size_t part = (n + nt - 1) / nt;
+            // parts of >= 1 MB, page aligned within the slot, one per copier thread (file-backed: file_parts() per slot)
+            const int np = fd >= 0 ? file_parts() : nt;
+            size_t part = (n + np - 1) / np;
             part = (part + 4095) & ~(size_t)4095;
             if (part < (1u << 20)) part = 1u << 20;
             const int nparts = (int)((n + part - 1) / part);
@@ -424,7 +447,7 @@ class HostSink {
     cudaStream_t s_;
     int device_;
     SinkRing *ring_ = nullptr;
-    std::atomic<int> pending_[kSinkSlots];
+    std::atomic<int> pending_[kSinkSlotsMax];
     std::mutex mu_;
     std::condition_variable cv_;
     int next_ = 0;
@@ -502,7 +525,7 @@ class HostSource {
     cudaStream_t s_;
     int device_;
     SinkRing *ring_ = nullptr;
-    bool used_[kSinkSlots] = {};
+    bool used_[kSinkSlotsMax] = {};
     std::atomic<int> pending_{0};
     std::mutex mu_;
     std::condition_variable cv_;

@@ -74,7 +74,7 @@ def test_dem_with_voids_and_spikes(method):
     c = pu.cpu_topo(sc, dem_method=method)
     st = pu.compare_topo(g, c)
     _assert_topo(st)
-    assert (np.abs(c["hgt"] - clean["hgt"]) > 50.0).sum() > 100  # the voids / spikes are actually hit
+    assert (np.abs(c["hgt"] - clean["hgt"]) > 50.0).sum() >= 50  # the voids / spikes are actually hit
     assert c["totalconv"] < 0.97 * c["lat"].size  # and send pixels through the secondary iterations
 
 

@@ -1,5 +1,5 @@
 O=gpurun_out; mkdir -p $O
-timeout 1200 python -m pytest tests -m gpu -q > $O/pytest_gpu_full_r02l.log 2>&1; tail -8 $O/pytest_gpu_full_r02l.log
-timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_r02l.json 2> $O/bench_r02l.err; tail -5 $O/bench_r02l.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_r02l.json')); print(d['value'], d['ms_per_step'], d['breakdown_ms'], d['e2e']['value'], d.get('bench_seconds')); print(json.dumps(d['e2e_component'])[:1800])"
+cat /sys/kernel/mm/transparent_hugepage/shmem_enabled > $O/box_thp_r02m.txt 2>&1; uname -r >> $O/box_thp_r02m.txt; nproc >> $O/box_thp_r02m.txt
+timeout 300 python -m pytest tests/test_gpu_edge_cases.py tests/test_gpu_n1_paths.py -m gpu -q > $O/pytest_gpu_part_r02m.log 2>&1; tail -4 $O/pytest_gpu_part_r02m.log
+SWEEP=file timeout 900 python tools/component_threads_sweep.py 4000 > $O/component_file_sweep_4000lines_r02m.log 2>$O/component_file_sweep_r02m.err; cat $O/component_file_sweep_4000lines_r02m.log
+SWEEP=file timeout 900 python tools/component_threads_sweep.py > $O/component_file_sweep_r02m.log 2>>$O/component_file_sweep_r02m.err; cat $O/component_file_sweep_r02m.log

@@ -37,7 +37,8 @@ try:
             shutil.rmtree(d, ignore_errors=True)
 finally:
     shutil.rmtree(demdir, ignore_errors=True)
-print(json.dumps({"copy_threads": os.environ.get("B200_COPY_THREADS"), "file_writes": os.environ.get("B200_FILE_WRITES", "1"),
+print(json.dumps({"copy_threads": os.environ.get("B200_COPY_THREADS"), "file_writes": os.environ.get("B200_FILE_WRITES", "0"),
+                  "sink_slots": os.environ.get("B200_SINK_SLOTS"), "file_parts": os.environ.get("B200_FILE_PARTS"),
                   "step_s": [round(t, 3) for t in times], "library_ms": lib}))
 """
 
@@ -52,8 +53,13 @@ def main():
         for th in (4, 8, 12, 16):
             r = bench.file_write_floor(base, nbytes, threads=th, how=how)
             print(json.dumps({"floor": how, "threads": th, "seconds": round(r["seconds"], 3), "GBps": round(r["GBps"], 2)}), flush=True)
-    for th, fw in ((4, 1), (8, 1), (12, 1), (16, 1), (8, 0), (16, 0)):
-        env = dict(os.environ, B200_COPY_THREADS=str(th), B200_FILE_WRITES=str(fw))
+    combos = [dict(B200_COPY_THREADS=t, B200_FILE_WRITES=0) for t in (4, 8, 12, 16)]
+    if os.environ.get("SWEEP") == "file":  # pwrite variants against the default
+        combos = [dict(B200_COPY_THREADS=16, B200_FILE_WRITES=0), dict(B200_COPY_THREADS=16, B200_FILE_WRITES=0, B200_SINK_SLOTS=16)]
+        combos += [dict(B200_COPY_THREADS=t, B200_FILE_WRITES=1, B200_SINK_SLOTS=sl, B200_FILE_PARTS=pp)
+                   for t, sl, pp in ((16, 6, 1), (16, 16, 1), (16, 24, 1), (16, 16, 2), (16, 16, 4), (8, 16, 1))]
+    for combo in combos:
+        env = dict(os.environ, **{k: str(v) for k, v in combo.items()})
         out = subprocess.run([sys.executable, "-c", CHILD % (ROOT, lines)], env=env, capture_output=True, text=True)
         print((out.stdout.strip().splitlines() or [out.stderr[-400:]])[-1], flush=True)
 
