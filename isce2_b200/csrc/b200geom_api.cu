@@ -170,18 +170,20 @@ cudaError_t dmalloc(T **p, size_t bytes)
 // -------------------------------------------------------------------------------------------------
 constexpr size_t kSinkSlotBytes = 32u << 20; // one bounce slot
 constexpr int kSinkSlotsMax = 24;
-// slots of the ring of one sink (32 MB each, page-locked, cached between calls).  B200_SINK_SLOTS overrides (2 .. 24).
+// Slots of the ring of one sink (32 MB each, page-locked, cached between calls); B200_SINK_SLOTS overrides (2 .. 24).
+// Sixteen: a slot bound for a registered file is written by ONE pwrite, so the slots in flight are the writers in flight
+// (Component path, 16.5 GB swath on tmpfs: 1.29 s with 6 slots, 0.91 s with 16, 0.89 s with 24).
 int sink_slots()
 {
     static const int n = [] {
-        int v = 6;
+        int v = 16;
         if (const char *e = getenv("B200_SINK_SLOTS")) v = atoi(e);
         return v < 2 ? 2 : (v > kSinkSlotsMax ? kSinkSlotsMax : v);
     }();
     return n;
 }
-// parts a slot bound for a registered file is written in (B200_FILE_PARTS; default 1: one pwrite per slot -- writers of
-// neighbouring pieces of one file mostly wait for each other, whole slots mostly belong to different rasters)
+// Parts a slot bound for a registered file is written in (B200_FILE_PARTS).  One: writers of neighbouring pieces of one
+// file mostly wait for each other (4 parts: 1.16 s against 0.91 s), whole slots mostly belong to different rasters.
 int file_parts()
 {
     static const int n = [] {
@@ -191,7 +193,6 @@ int file_parts()
     }();
     return n;
 }
-#define kSinkSlots sink_slots()
 
 struct SinkRing {
     char *buf[kSinkSlotsMax] = {};
@@ -200,7 +201,7 @@ struct SinkRing {
     bool ok = false;
 };
 std::mutex g_ring_mu;
-std::vector<SinkRing *> g_free_rings; // rings of finished calls, handed to the next one (pinning 192 MB costs ~50 ms)
+std::vector<SinkRing *> g_free_rings; // rings of finished calls, handed to the next one (pinning 512 MB costs ~0.1 s)
 
 SinkRing *ring_acquire(int device)
 {
@@ -218,13 +219,13 @@ SinkRing *ring_acquire(int device)
     if (!r) return nullptr;
     r->device = device;
     r->ok = true;
-    for (int i = 0; i < kSinkSlots && r->ok; i++) {
+    for (int i = 0; i < sink_slots() && r->ok; i++) {
         r->ok = cudaHostAlloc((void **)&r->buf[i], kSinkSlotBytes, cudaHostAllocPortable) == cudaSuccess &&
                 cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming) == cudaSuccess;
     }
     if (!r->ok) {
         cudaGetLastError();
-        for (int i = 0; i < kSinkSlots; i++) {
+        for (int i = 0; i < sink_slots(); i++) {
             if (r->buf[i]) cudaFreeHost(r->buf[i]);
             if (r->ev[i]) cudaEventDestroy(r->ev[i]);
         }
@@ -256,11 +257,11 @@ int sink_threads()
 
 // File-backed destinations (b200_host_file_register): a range of host addresses that is a shared mapping of a file.  The
 // copier threads write results bound for such a range with pwrite on the file instead of storing through the mapping:
-// the page cache is filled without one page fault per 4 KB of a raster that does not exist yet; the mapping sees the same
-// pages.  Measured (profiles/r02_component_threads_sweep.log): plain pwrite of 16.5 GB into new tmpfs files beats stores
-// into fresh mappings (1.1 s against 1.7 s with 16 threads), but from the bounce slots, next to the DMA traffic, it does
-// not: 2.6 s per swath at any thread count against 1.8-2.1 s through the mapping.  The Components therefore use it only
-// when asked to (B200_FILE_WRITES=1).
+// the page cache is filled without one page fault (and one zeroed page) per 4 KB of a raster that does not exist yet; the
+// mapping sees the same pages.  What matters is the shape of the writes (profiles/r02_component_file_sweep.log, 16.5 GB
+// swath through the Components on tmpfs): a slot cut into one piece per thread, as the stores are, is SLOWER than the
+// stores (2.6 s against 1.8 s: writers of neighbouring pieces of one file wait for each other), one pwrite per 32 MB slot
+// with 16 slots in flight is twice as fast (0.9 s).
 struct FileRange {
     const char *base;
     size_t bytes;
@@ -387,7 +388,7 @@ class HostSink {
                 bounce_failed_ = true;
                 return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s_);
             }
-            for (int i = 0; i < kSinkSlots; i++) pending_[i].store(0);
+            for (int i = 0; i < sink_slots(); i++) pending_[i].store(0);
         }
         const int nt = CopyPool::get().size();
         int fd = -1;
@@ -396,7 +397,7 @@ class HostSink {
         for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
             const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
             const int k = next_;
-            next_ = (next_ + 1) % kSinkSlots;
+            next_ = (next_ + 1) % sink_slots();
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [&] { return pending_[k].load() == 0; });
@@ -425,7 +426,7 @@ class HostSink {
         if (!ring_) return;
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] {
-            for (int i = 0; i < kSinkSlots; i++)
+            for (int i = 0; i < sink_slots(); i++)
                 if (pending_[i].load() != 0) return false;
             return true;
         });
@@ -466,7 +467,7 @@ class HostSource {
     ~HostSource()
     {
         if (ring_) {
-            for (int i = 0; i < kSinkSlots; i++)
+            for (int i = 0; i < sink_slots(); i++)
                 if (used_[i]) cudaEventSynchronize(ring_->ev[i]); // the slots must not be reused while a DMA still reads them
             ring_release(ring_);
         }
@@ -487,7 +488,7 @@ class HostSource {
         for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
             const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
             const int k = next_;
-            next_ = (next_ + 1) % kSinkSlots;
+            next_ = (next_ + 1) % sink_slots();
             if (used_[k]) {
                 cudaError_t e = cudaEventSynchronize(ring_->ev[k]); // the slot's previous upload has left it
                 if (e != cudaSuccess) return e;

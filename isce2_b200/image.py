@@ -404,15 +404,15 @@ def output_memmap(img, length, width, bands=1):
 
 @contextlib.contextmanager
 def file_backed(arrays):
-    """With B200_FILE_WRITES=1 in the environment, for the duration of a library call: every writable numpy.memmap among
-    `arrays` (None entries allowed) is declared to the library as the file mapping it is (b200_host_file_register), so that
-    results are written into the file with pwrite instead of through the mapping -- the same pages, without a page fault
-    per 4 KB of a raster that does not exist yet.  Off by default: on the B200 boxes measured (tmpfs) the stores through
-    the mapping, spread over the copier threads, were the faster of the two (profiles/r02_component_threads_sweep.log)."""
+    """For the duration of a library call: every writable numpy.memmap among `arrays` (None entries allowed) is declared
+    to the library as the file mapping it is (b200_host_file_register), so that results are written into the file with
+    pwrite, one 32 MB slot per call, instead of through the mapping -- the same pages, without a page fault per 4 KB of a
+    raster that does not exist yet (16.5 GB swath on tmpfs: 0.9 s against 1.8 s, profiles/r02_component_file_sweep.log).
+    B200_FILE_WRITES=0 in the environment leaves everything to the mapping."""
     from . import _capi
     done = []
     try:
-        if os.environ.get("B200_FILE_WRITES", "0") == "1":
+        if os.environ.get("B200_FILE_WRITES", "1") != "0":
             for a in arrays:
                 if not isinstance(a, np.memmap) or a.size == 0 or getattr(a, "mode", "r") not in ("r+", "w+") or not a.filename:
                     continue

@@ -124,18 +124,18 @@ def test_file_backed_destination_registry(tmp_path):
         assert not _capi.host_file_unregister(a.ctypes.data)
     finally:
         os.close(fd)
-    os.environ["B200_FILE_WRITES"] = "1"
+    with IF.file_backed([a, None, b, ro, np.zeros(8), a]):
+        assert not _capi.host_file_unregister(ro.ctypes.data)  # read-only mappings and plain arrays are not declared
+        with pytest.raises(_capi.B200Error):                   # a and b are
+            fd = os.open(str(tmp_path / "b.bin"), os.O_RDWR)
+            try:
+                _capi.host_file_register(b.ctypes.data, b.nbytes, fd, 0)
+            finally:
+                os.close(fd)
+    assert not _capi.host_file_unregister(a.ctypes.data) and not _capi.host_file_unregister(b.ctypes.data)
+    os.environ["B200_FILE_WRITES"] = "0"
     try:
-        with IF.file_backed([a, None, b, ro, np.zeros(8), a]):
-            assert not _capi.host_file_unregister(ro.ctypes.data)  # read-only mappings and plain arrays are not declared
-            with pytest.raises(_capi.B200Error):                   # a and b are
-                fd = os.open(str(tmp_path / "b.bin"), os.O_RDWR)
-                try:
-                    _capi.host_file_register(b.ctypes.data, b.nbytes, fd, 0)
-                finally:
-                    os.close(fd)
-        assert not _capi.host_file_unregister(a.ctypes.data) and not _capi.host_file_unregister(b.ctypes.data)
+        with IF.file_backed([a]):  # switched off: nothing is declared
+            assert not _capi.host_file_unregister(a.ctypes.data)
     finally:
         del os.environ["B200_FILE_WRITES"]
-    with IF.file_backed([a]):  # opt-in: nothing is declared without the switch
-        assert not _capi.host_file_unregister(a.ctypes.data)

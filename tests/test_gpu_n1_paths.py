@@ -253,12 +253,8 @@ def test_pageable_and_page_locked_destinations_agree(tmp_path):
     pre = {k: map_inside_a_file(k, s, d) for k, (s, d) in shapes.items()}
     pre.update({k: map_inside_a_file(k, (sc.length, sc.width), np.float32) for k in ("azoff", "rgoff")})
     before = _capi.host_file_bytes()
-    os.environ["B200_FILE_WRITES"] = "1"
-    try:
-        with IF.file_backed(list(pre.values())):
-            fb = run(lambda k, s, d: pre[k])
-    finally:
-        del os.environ["B200_FILE_WRITES"]
+    with IF.file_backed(list(pre.values())):
+        fb = run(lambda k, s, d: pre[k])
     assert _capi.host_file_bytes() - before == sum(a.nbytes for a in pre.values())  # every byte went through pwrite
     assert not _capi.host_file_unregister(pre["lat"].ctypes.data)  # the context manager has taken the registrations back
     for k in pinned:
