@@ -9,7 +9,7 @@ set -x
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $O/box_$TAG.txt; nproc >> $O/box_$TAG.txt; free -g >> $O/box_$TAG.txt
 timeout 1800 python -m pytest tests -m gpu -q > $O/pytest_gpu_full_$TAG.log 2>&1; tail -40 $O/pytest_gpu_full_$TAG.log > $O/pytest_gpu_$TAG.log; cat $O/pytest_gpu_$TAG.log
 timeout 300 python tools/gpu_perf.py 2>&1 | tail -1 > $O/parity_rough_$TAG.json
-timeout 600 bash tools/ab_mask_modes.sh > $O/ab_mask_$TAG.log 2>&1; cat $O/ab_mask_$TAG.log
+[ -n "$AB_MASK" ] && { timeout 600 bash tools/ab_mask_modes.sh > $O/ab_mask_$TAG.log 2>&1; cat $O/ab_mask_$TAG.log; }
 timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err; tail -25 $O/bench_$TAG.err
 [ -n "$QUICK" ] && exit 0
 timeout 300 python bench.py --impl reference --steps 6 --warmup 1 --ref-step-seconds 4 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err
