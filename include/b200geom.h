@@ -424,6 +424,9 @@ void b200_free_pinned(void *p);
 int b200_host_file_register(const void *base, size_t bytes, int fd, long long file_offset, char *err, size_t errlen);
 int b200_host_file_unregister(const void *base); /* B200_OK, or B200_EINVAL when base was not registered */
 unsigned long long b200_host_file_bytes(void);   /* bytes written with pwrite since the library was loaded */
+/* The same registration serves INPUTS that are mappings of files (the lat / lon / hgt rasters geo2rdr reads,
+ * Geo2rdr.py:208-226): they are read with pread into the upload slots instead of through the mapping. */
+unsigned long long b200_host_file_bytes_read(void);
 /* device -> page-locked host copy of `bytes` (chunks of chunk_bytes, one stream), timed with CUDA events: the floor of
  * an end-to-end call that has to deliver that many bytes of results.  host must hold `bytes`. */
 int b200_d2h_floor(int device, void *host, size_t bytes, size_t chunk_bytes, float *ms, char *err, size_t errlen);

@@ -139,7 +139,8 @@ EXPORTS = ["b200_topo_run", "b200_topo_plan_create", "b200_topo_plan_execute", "
            "b200_geozero_plan_geocode", "b200_geozero_plan_fetch", "b200_geozero_plan_destroy", "b200_geozero_run",
            "b200_resamp_slc_run", "b200_resamp_slc_from_geo_plan", "b200_topo_geo2rdr_run",
            "b200_looks_run", "b200_mask_to_radar_run", "b200_topo_plan_looks", "b200_geo_plan_freeze_geometry",
-           "b200_d2h_floor", "b200_host_file_register", "b200_host_file_unregister", "b200_host_file_bytes"]
+           "b200_d2h_floor", "b200_host_file_register", "b200_host_file_unregister", "b200_host_file_bytes",
+           "b200_host_file_bytes_read"]
 
 _lib = None
 
@@ -188,6 +189,8 @@ def lib():
     L.b200_host_file_unregister.argtypes = [C.c_void_p]
     L.b200_host_file_bytes.restype = C.c_ulonglong
     L.b200_host_file_bytes.argtypes = []
+    L.b200_host_file_bytes_read.restype = C.c_ulonglong
+    L.b200_host_file_bytes_read.argtypes = []
     L.b200_device_primitive.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Orbit), _dp, _dp] + err
     L.b200_geozero_grid.argtypes = [C.POINTER(GeozeroParams), C.POINTER(C.c_int), C.POINTER(C.c_int)] + err
     L.b200_geozero_plan_create.argtypes = [C.POINTER(GeozeroParams), C.c_void_p, C.c_int, C.POINTER(Orbit), C.POINTER(Poly1d),
@@ -261,6 +264,11 @@ def host_file_register(address, nbytes, fd, file_offset):
 def host_file_bytes():
     """Bytes the copier threads have written with pwrite since the library was loaded."""
     return int(lib().b200_host_file_bytes())
+
+
+def host_file_bytes_read():
+    """Bytes the copier threads have read with pread since the library was loaded."""
+    return int(lib().b200_host_file_bytes_read())
 
 
 def host_file_unregister(address):

@@ -270,7 +270,8 @@ struct FileRange {
 };
 std::shared_mutex g_file_mu;
 std::vector<FileRange> g_files;
-std::atomic<unsigned long long> g_file_bytes{0}; // written with pwrite so far (b200_host_file_bytes)
+std::atomic<unsigned long long> g_file_bytes{0};      // written with pwrite so far (b200_host_file_bytes)
+std::atomic<unsigned long long> g_file_bytes_read{0}; // read with pread so far (b200_host_file_bytes_read)
 bool file_lookup(const void *dst, size_t n, int &fd, long long &off)
 {
     std::shared_lock<std::shared_mutex> lk(g_file_mu);
@@ -299,7 +300,23 @@ bool pwrite_all(int fd, const char *src, size_t n, long long off, size_t &done)
     return true;
 }
 
-// process-wide pool of copier threads: a task is one memcpy (or pwrite) of a part of a finished slot
+// pread of the whole part; false on the first error other than EINTR or at end of file
+bool pread_all(int fd, char *dst, size_t n, long long off, size_t &done)
+{
+    done = 0;
+    while (done < n) {
+        const ssize_t r = pread(fd, dst + done, n - done, (off_t)(off + (long long)done));
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        if (r == 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+
+// process-wide pool of copier threads: a task is one memcpy (or pwrite / pread) of a part of a slot
 class CopyPool {
   public:
     struct Task {
@@ -311,8 +328,9 @@ class CopyPool {
         std::atomic<int> *pending; // per slot: parts still to copy; 0 == slot reusable
         std::mutex *mu;            // owner's mutex / cv, signalled when pending reaches 0
         std::condition_variable *cv;
-        int fd = -1;               // >= 0: dst lies in a registered file mapping; write at file offset foff instead
-        long long foff = 0;
+        int fd = -1;               // >= 0: dst (or, with from_file, src) lies in a registered file mapping: write (read) the
+        long long foff = 0;        //       file at offset foff instead
+        bool from_file = false;
     };
     static CopyPool &get()
     {
@@ -351,7 +369,10 @@ class CopyPool {
             }
             if (t.ready) cudaEventSynchronize(t.ready); // (host -> slot copies of HostSource have nothing to wait for)
             size_t done = 0;
-            if (t.fd >= 0) {
+            if (t.fd >= 0 && t.from_file) {
+                pread_all(t.fd, (char *)t.dst, t.bytes, t.foff, done);
+                g_file_bytes_read.fetch_add(done, std::memory_order_relaxed);
+            } else if (t.fd >= 0) {
                 pwrite_all(t.fd, (const char *)t.src, t.bytes, t.foff, done);
                 g_file_bytes.fetch_add(done, std::memory_order_relaxed);
             }
@@ -485,6 +506,9 @@ class HostSource {
             }
         }
         const int nt = CopyPool::get().size();
+        int fd = -1; // the source is a registered file mapping (the .rdr rasters geo2rdr reads): pread instead of page faults
+        long long foff = 0;
+        if (!file_lookup(src, bytes, fd, foff)) fd = -1;
         for (size_t o = 0; o < bytes; o += kSinkSlotBytes) {
             const size_t n = bytes - o < kSinkSlotBytes ? bytes - o : kSinkSlotBytes;
             const int k = next_;
@@ -500,7 +524,8 @@ class HostSource {
             pending_.store(nparts);
             for (int q = 0; q < nparts; q++) {
                 const size_t po = (size_t)q * part, pn = n - po < part ? n - po : part;
-                CopyPool::get().push(CopyPool::Task{nullptr, device_, ring_->buf[k] + po, (const char *)src + o + po, pn, &pending_, &mu_, &cv_});
+                CopyPool::get().push(CopyPool::Task{nullptr, device_, ring_->buf[k] + po, (const char *)src + o + po, pn, &pending_, &mu_, &cv_,
+                                                    fd, foff + (long long)(o + po), true});
             }
             {
                 std::unique_lock<std::mutex> lk(mu_);
@@ -2467,6 +2492,7 @@ extern "C" int b200_host_file_register(const void *base, size_t bytes, int fd, l
 }
 
 extern "C" unsigned long long b200_host_file_bytes(void) { return g_file_bytes.load(); }
+extern "C" unsigned long long b200_host_file_bytes_read(void) { return g_file_bytes_read.load(); }
 
 extern "C" int b200_host_file_unregister(const void *base)
 {

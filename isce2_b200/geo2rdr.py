@@ -133,7 +133,8 @@ class Geo2rdr(Component):
             except Exception as e:
                 errors[i] = e
 
-        with IF.file_backed(list(outs.values())):  # the .off / .rdr rasters being written are file mappings (image.file_backed)
+        # the .off / .rdr rasters being written, and the lat / lon / hgt rasters being read, are file mappings (image.file_backed)
+        with IF.file_backed(list(outs.values()), inputs=[lat, lon, hgt]):
             if n == 1:
                 work(0)
             else:

@@ -402,31 +402,53 @@ def output_memmap(img, length, width, bands=1):
     return np.memmap(fn, dtype=dt, mode=mode, shape=_shape(length, width, bands, "BIL"))
 
 
+def _file_range(a, writable):
+    """(address, nbytes, filename, file offset) when the array `a` is -- or is a contiguous view of -- a numpy.memmap opened
+    for writing (writable) or at all, else None."""
+    if not isinstance(a, np.ndarray) or a.size == 0 or not a.flags["C_CONTIGUOUS"]:
+        return None
+    mm = a
+    while mm is not None and not isinstance(mm, np.memmap):
+        mm = getattr(mm, "base", None)
+    # a view of a memmap is itself a memmap whose attributes describe the parent: the mapped buffer proper is the one
+    # whose base is the mmap object
+    while isinstance(mm, np.memmap) and isinstance(mm.base, np.memmap):
+        mm = mm.base
+    if not isinstance(mm, np.memmap) or not getattr(mm, "filename", None):
+        return None
+    if writable and (getattr(mm, "mode", "r") not in ("r+", "w+") or not a.flags["WRITEABLE"]):
+        return None
+    if getattr(mm, "mode", "r") == "c":  # copy-on-write: the file is not what the mapping shows
+        return None
+    delta = a.ctypes.data - mm.ctypes.data
+    if delta < 0 or delta + a.nbytes > mm.nbytes:
+        return None
+    return a.ctypes.data, a.nbytes, str(mm.filename), int(mm.offset) + delta
+
+
 @contextlib.contextmanager
-def file_backed(arrays):
+def file_backed(arrays, inputs=()):
     """For the duration of a library call: every writable numpy.memmap among `arrays` (None entries allowed) is declared
     to the library as the file mapping it is (b200_host_file_register), so that results are written into the file with
     pwrite, one 32 MB slot per call, instead of through the mapping -- the same pages, without a page fault per 4 KB of a
     raster that does not exist yet (16.5 GB swath on tmpfs: 0.9 s against 1.8 s, profiles/r02_component_file_sweep.log).
-    B200_FILE_WRITES=0 in the environment leaves everything to the mapping."""
+    `inputs`: arrays the call READS that are (views of) memmaps of rasters; they are uploaded with pread.
+    B200_FILE_WRITES=0 in the environment leaves everything to the mappings."""
     from . import _capi
     done = []
     try:
         if os.environ.get("B200_FILE_WRITES", "1") != "0":
-            for a in arrays:
-                if not isinstance(a, np.memmap) or a.size == 0 or getattr(a, "mode", "r") not in ("r+", "w+") or not a.filename:
+            for a, writable in [(a, True) for a in arrays] + [(a, False) for a in inputs]:
+                r = _file_range(a, writable)
+                if r is None or r[0] in done:
                     continue
-                if not (a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]):
-                    continue
-                addr = a.ctypes.data
-                if addr in done:
-                    continue
+                addr, nbytes, filename, offset = r
                 try:
-                    fd = os.open(a.filename, os.O_RDWR)
+                    fd = os.open(filename, os.O_RDWR if writable else os.O_RDONLY)
                 except OSError:
                     continue
                 try:
-                    _capi.host_file_register(addr, a.nbytes, fd, int(a.offset))
+                    _capi.host_file_register(addr, nbytes, fd, offset)
                     done.append(addr)
                 except _capi.B200Error:  # e.g. two images over one file: the mapping still works
                     pass

@@ -99,3 +99,31 @@ def run_components(sc, sec, dem_img, outdir, *, dem_method="BIQUINTIC", orbit_me
     files = [f for f in os.listdir(outdir) if f.endswith((".rdr", ".off"))]
     return dict(files=sorted(files), bytes_written=sum(os.path.getsize(os.path.join(outdir, f)) for f in files),
                 snwe=topo.snwe, num_valid=getattr(grdr, "numValid", None), gpu_timings=getattr(topo, "gpuTimings", None))
+
+
+def run_components_separately(sc, sec, dem_img, outdir, *, dem_method="BIQUINTIC", orbit_method="HERMITE", inc=True, mask=True,
+                              devices=None, misreg_az=0.013, misreg_rg=1.7):
+    """The reference's own sequence (TopsProc/runTopo.py, then runGeo2rdr.py in a later step): topo() writes its rasters,
+    geo2rdr() reads lat / lon / hgt back from them.  Returns the seconds of the two calls and what was written."""
+    import time
+    from . import image as IF
+    os.makedirs(outdir, exist_ok=True)
+    topo = make_topo(sc, dem_img, outdir, dem_method=dem_method, orbit_method=orbit_method, inc=inc, mask=mask, devices=devices)
+    t0 = time.perf_counter()
+    topo.topo()
+    t1 = time.perf_counter()
+    grdr = make_geo2rdr(sc, sec, outdir, t0=sc.t0 - misreg_az, r0=sc.r0 - misreg_rg, orbit_method=orbit_method,
+                        doppler_cycles_per_prf=[c / sc.prf for c in sc.doppler_coeffs[0]])
+    if devices is not None:
+        grdr.gpuDevices = list(devices)
+    imgs = {}
+    for key, name in (("lat", "lat.rdr"), ("lon", "lon.rdr"), ("hgt", "hgt.rdr")):
+        img = IF.createImage()
+        img.load(os.path.join(outdir, name + ".xml"))
+        img.setAccessMode("READ")
+        imgs[key] = img
+    grdr.geo2rdr(latImage=imgs["lat"], lonImage=imgs["lon"], demImage=imgs["hgt"])
+    t2 = time.perf_counter()
+    files = [f for f in os.listdir(outdir) if f.endswith((".rdr", ".off"))]
+    return dict(seconds_topo=t1 - t0, seconds_geo2rdr=t2 - t1, files=sorted(files),
+                bytes_written=sum(os.path.getsize(os.path.join(outdir, f)) for f in files), num_valid=getattr(grdr, "numValid", None))

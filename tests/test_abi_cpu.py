@@ -133,6 +133,13 @@ def test_file_backed_destination_registry(tmp_path):
             finally:
                 os.close(fd)
     assert not _capi.host_file_unregister(a.ctypes.data) and not _capi.host_file_unregister(b.ctypes.data)
+    # inputs: read-only mappings and plain-ndarray views of mappings (what numpy.ascontiguousarray hands back) are declared
+    view = np.ascontiguousarray(ro[8:40])
+    assert type(view) is np.ndarray and IF._file_range(view, False) == (view.ctypes.data, view.nbytes, str(tmp_path / "a.bin"), 8 * 512 * 8)
+    assert IF._file_range(view, True) is None and IF._file_range(np.zeros(4), False) is None
+    assert IF._file_range(ro[:, 3:9], False) is None  # not contiguous
+    with IF.file_backed([b], inputs=[view, None]):
+        assert _capi.host_file_unregister(view.ctypes.data)
     os.environ["B200_FILE_WRITES"] = "0"
     try:
         with IF.file_backed([a]):  # switched off: nothing is declared

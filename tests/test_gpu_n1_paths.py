@@ -277,8 +277,13 @@ def test_pageable_and_page_locked_destinations_agree(tmp_path):
         ins_pin.append(a)
     ga = _capi.geo2rdr_run(gp64, *ins_mm, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"])
     gb = _capi.geo2rdr_run(gp64, *ins_pin, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"])
+    read0 = _capi.host_file_bytes_read()
+    with IF.file_backed([], inputs=[np.ascontiguousarray(m) for m in ins_mm]):  # ... or with pread, declared as the files they are
+        gc = _capi.geo2rdr_run(gp64, *ins_mm, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"])
+    assert _capi.host_file_bytes_read() - read0 == sum(m.nbytes for m in ins_mm)
     for k in ("azt", "rgm", "azoff", "rgoff"):
         assert np.array_equal(ga[k], gb[k]), k
+        assert np.array_equal(gc[k], gb[k]), k
     assert np.array_equal(ga["azoff"].astype(np.float32), pinned["azoff"])  # and they are the fused call's offsets
     plan = _capi.GeoPlan(gp64, *ins_mm)
     plan.execute(gp64, kw["orbit_t"], kw["orbit_pos"], kw["orbit_vel"], want=("azoff",))
