@@ -941,6 +941,23 @@ def measure_component(args, ranks, capi, dev, name, lines=None):
                 out["library_call_ms"] = [round(float(g["ms_total"]), 1) for g in gt]  # inside b200_topo_geo2rdr_run
             finally:
                 shutil.rmtree(d, ignore_errors=True)
+        # the reference's own sequence: topo() writes its rasters, a separate geo2rdr() reads lat / lon / hgt back from them
+        # (TopsProc/runTopo.py, then runGeo2rdr.py as a later step of the same application)
+        two = []
+        for i in range(3):
+            d = tempfile.mkdtemp(prefix="b200_bench_", dir=base)
+            try:
+                with contextlib.redirect_stdout(sys.stderr):
+                    info = comp.run_components_separately(sc, sec, dem_img, d, dem_method=w["dem_method"], orbit_method=w["orbit_method"],
+                                                          inc=w["inc"], mask=w["mask"], devices=[dev])
+                two.append((info["seconds_topo"], info["seconds_geo2rdr"]))
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+        tt, tg = float(np.median([a for a, _ in two[1:]])), float(np.median([b for _, b in two[1:]]))
+        out["two_calls"] = {"api": "createTopozero().topo(), then createGeo2rdr().geo2rdr(latImage, lonImage, demImage) on the rasters it wrote",
+                            "seconds_topo": round(tt, 3), "seconds_geo2rdr": round(tg, 3), "value": sc.pixels / (tt + tg) / 1e6,
+                            "unit": "Mpixels/s", "statistic": "medians of the steps after the first"}
+        log(f"[bench] {name}: component path, two calls (s): {[(round(a, 3), round(b, 3)) for a, b in two]}")
     except Exception as e:  # noqa: BLE001
         import traceback
         log(traceback.format_exc())
