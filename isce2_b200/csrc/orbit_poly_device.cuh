@@ -80,10 +80,32 @@ __device__ __forceinline__ void poly_state(const OrbitPolyView &op, double time,
     S.a = Vec3{ao[0], ao[1], ao[2]};
 }
 
+// Horner evaluation of a polynomial of the compile-time degree N: coefficients read as constant-bank operands of the FMAs
+template <int N>
+__device__ __forceinline__ double horner_fixed(const Poly1dDev &p, double xv)
+{
+    double v = p.c[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--) v = __fma_rn(v, xv, p.c[i]);
+    return v;
+}
+
+// Doppler polynomials have a handful of coefficients; the degree is uniform over the grid, so a switch on it costs a
+// uniform branch and replaces the loop with its register-indexed constant loads (14 % of the stall samples of the
+// native-Doppler geo2rdr kernel sat on that loop)
 __device__ __forceinline__ double poly1d_fast(const Poly1dDev &p, double inv_norm, double x)
 {
     if (p.order == 0) return p.c[0];
     const double xv = (x - p.mean) * inv_norm;
+    switch (p.order) {
+    case 1: return horner_fixed<1>(p, xv);
+    case 2: return horner_fixed<2>(p, xv);
+    case 3: return horner_fixed<3>(p, xv);
+    case 4: return horner_fixed<4>(p, xv);
+    case 5: return horner_fixed<5>(p, xv);
+    case 6: return horner_fixed<6>(p, xv);
+    default: break;
+    }
     double v = p.c[p.order];
     for (int i = p.order - 1; i >= 0; i--) v = __fma_rn(v, xv, p.c[i]);
     return v;
