@@ -30,8 +30,10 @@ def perf(lines=1500, width=25000, reps=3, rough=False):
             res = _capi.TopoResult()
             e = C.create_string_buffer(512)
             _capi._check(_capi.lib().b200_topo_plan_fetch(tp.handle, None, C.byref(res), e, 512), e)
-            if best is None or res.ms_pixels < best[0]:
+            if best is None:
                 best = (res.ms_pixels, res.ms_mask, res.iterations / float(lines * width), res.ms_solve)
+            else:  # every time is the best of the repetitions on its own (a first call can carry one-off costs)
+                best = (min(best[0], res.ms_pixels), min(best[1], res.ms_mask), best[2], min(best[3], res.ms_solve))
         out[method] = dict(ms_pixels=round(best[0], 3), ms_solve=round(best[3], 3), ms_mask=round(best[1], 3), K=round(best[2], 3),
                            gpix_s=round(lines * width / best[0] / 1e6, 3))
         if method == "BILINEAR":
