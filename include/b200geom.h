@@ -420,7 +420,7 @@ void b200_free_pinned(void *p);
  * and a zeroed page per 4 KB of a file that does not exist yet: 0.9 s instead of 1.8 s for the 16.5 GB of rasters of a
  * Sentinel-1 swath on tmpfs.  The Components do it for every raster they write (B200_FILE_WRITES=0
  * turns that off).  The library keeps its own duplicate of fd until the range is unregistered; a failed write falls back
- * to the store.  Ranges must not overlap. */
+ * to the store.  Ranges must not overlap; unregister a range only after the calls that use it have returned. */
 int b200_host_file_register(const void *base, size_t bytes, int fd, long long file_offset, char *err, size_t errlen);
 int b200_host_file_unregister(const void *base); /* B200_OK, or B200_EINVAL when base was not registered */
 unsigned long long b200_host_file_bytes(void);   /* bytes written with pwrite since the library was loaded */

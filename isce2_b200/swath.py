@@ -324,7 +324,9 @@ class Geo2rdrStack:
                     ms = plan.execute(p, t, pos, vel, doppler_coeffs=job["doppler"], want=("azoff", "rgoff"))
                     rg = self._out_image(job["rg"], shape)
                     az = self._out_image(job["az"], shape)
-                    r = plan.fetch(out=dict(azt=None, rgm=None, azoff=az.memMap(), rgoff=rg.memMap()))
+                    azm, rgm = az.memMap(), rg.memMap()
+                    with IF.file_backed([azm, rgm]):  # the .off rasters of this date are written with pwrite
+                        r = plan.fetch(out=dict(azt=None, rgm=None, azoff=azm, rgoff=rgm))
                     for img in (rg, az):
                         img.finalizeImage()
                         img.renderHdr()
@@ -336,14 +338,16 @@ class Geo2rdrStack:
             except Exception as e:  # surfaced in the caller's thread
                 errors[s] = e
 
-        if nd == 1:
-            work(0)
-        else:
-            th = [threading.Thread(target=work, args=(s,)) for s in range(nd)]
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
+        # the geometry rasters are mappings of the files topo wrote: declared once, for every slot's uploads (pread)
+        with IF.file_backed([], inputs=[a for g in self._geoms.values() for a in (g["lat"], g["lon"], g["hgt"])]):
+            if nd == 1:
+                work(0)
+            else:
+                th = [threading.Thread(target=work, args=(s,)) for s in range(nd)]
+                for x in th:
+                    x.start()
+                for x in th:
+                    x.join()
         for e in errors:
             if e is not None:
                 raise e
