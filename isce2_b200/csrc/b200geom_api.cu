@@ -1941,7 +1941,8 @@ extern "C" int b200_geozero_plan_geocode(b200_geozero_plan *pl, const void *imag
         CK(cudaMemcpyAsync(pl->d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
     }
-    CK(cudaMemcpyAsync(pl->d_img, image, in_bytes, cudaMemcpyHostToDevice, s));
+    HostSource source(s, pl->p.device); // the image being geocoded is usually a mapping of its file
+    CK(source.copy(pl->d_img, image, in_bytes));
     CK(cudaEventRecord(pl->ev0, s));
     for (int b = 0; b < nbands; b++) {
         BandView iv, ov;
@@ -1964,9 +1965,11 @@ extern "C" int b200_geozero_plan_geocode(b200_geozero_plan *pl, const void *imag
     CK(cudaEventRecord(pl->ev1, s));
     GeozeroStats st;
     CK(cudaMemcpyAsync(&st, pl->d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out, pl->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    HostSink sink(s, pl->p.device); // ... and so is the geocoded product
+    CK(sink.copy(out, pl->d_out, out_bytes));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
+    sink.finish();
     CK(cudaEventElapsedTime(&pl->ms_kernels, pl->ev0, pl->ev1));
     pl->num_outside_image = (long long)st.outside_image;
     pl->num_valid = (long long)st.valid;
@@ -2125,17 +2128,18 @@ static int resamp_core(const b200_resamp_params *p, const b200_poly2d *rg_carrie
     std::vector<float> tab((size_t)kSincSub * kSincLen);
     resamp_sinc_table(tab.data());
     CK(cudaMemcpyAsync(B.d_sinc, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(B.d_in, slc_in, sizeof(float2) * nin, cudaMemcpyHostToDevice, s));
+    HostSource source(s, p->device); // the SLC and the .off rasters arrive as mappings of their files (Resamp_slc.py:86-160)
+    CK(source.copy(B.d_in, slc_in, sizeof(float2) * nin));
     const void *d_raz = resid_az, *d_rrg = resid_rg;
     if (!resid_on_device) {
         if (resid_az) {
             CK(dmalloc(&B.d_raz, rsz * nout));
-            CK(cudaMemcpyAsync(B.d_raz, resid_az, rsz * nout, cudaMemcpyHostToDevice, s));
+            CK(source.copy(B.d_raz, resid_az, rsz * nout));
             d_raz = B.d_raz;
         }
         if (resid_rg) {
             CK(dmalloc(&B.d_rrg, rsz * nout));
-            CK(cudaMemcpyAsync(B.d_rrg, resid_rg, rsz * nout, cudaMemcpyHostToDevice, s));
+            CK(source.copy(B.d_rrg, resid_rg, rsz * nout));
             d_rrg = B.d_rrg;
         }
     }
@@ -2153,9 +2157,11 @@ static int resamp_core(const b200_resamp_params *p, const b200_poly2d *rg_carrie
     CK(cudaEventRecord(B.ev1, s));
     ResampStats st;
     CK(cudaMemcpyAsync(&st, B.d_stats, sizeof st, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(slc_out, B.d_out, sizeof(float2) * nout, cudaMemcpyDeviceToHost, s));
+    HostSink sink(s, p->device);
+    CK(sink.copy(slc_out, B.d_out, sizeof(float2) * nout));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
+    sink.finish();
     if (res) {
         res->num_valid = (long long)st.valid;
         CK(cudaEventElapsedTime(&res->ms_kernels, B.ev0, B.ev1));

@@ -148,7 +148,8 @@ class Geocode(Component):
         try:
             out_mm = self.geoImage.memMap()
             if out_mm.dtype == image.dtype and out_mm.flags['C_CONTIGUOUS']:
-                plan.geocode(image, method=self.method, nbands=nbands, scheme=scheme, out=out_mm)
+                with IF.file_backed([out_mm], inputs=[image]):  # both are mappings of rasters (image.file_backed)
+                    plan.geocode(image, method=self.method, nbands=nbands, scheme=scheme, out=out_mm)
             else:  # the 'write' FLOAT caster (Geozero.py:313-314): the file keeps the input's data type
                 tmp = plan.geocode(image, method=self.method, nbands=nbands, scheme=scheme)
                 out_mm[...] = tmp.reshape(out_mm.shape).astype(out_mm.dtype)

@@ -69,7 +69,7 @@ class Resamp_slc(Component):
             ra, rr = np.asarray(ra, np.float64), np.asarray(rr, np.float64)
         out = IF.output_memmap(self.imageOut, ol, ow)  # ours, or an image object the caller handed in
         direct = out.dtype == np.complex64 and out.flags['C_CONTIGUOUS'] and out.shape == (ol, ow)
-        with IF.file_backed([out] if direct else []):
+        with IF.file_backed([out] if direct else [], inputs=[slc, ra, rr]):  # rasters in, raster out (image.file_backed)
             r = _capi.resamp_slc_run(slc[:int(self.inputLines)], (ol, ow), wvl=float(self.radarWavelength),
                                      slr=float(self.slantRangePixelSpacing), r0=float(self.startingRange),
                                      ref_wvl=float(self.referenceWavelength), ref_r0=float(self.referenceStartingRange),
