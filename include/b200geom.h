@@ -411,8 +411,8 @@ void b200_free_pinned(void *p);
  * speed) or ordinary pageable memory such as a numpy.memmap over the raster being written -- what the reference's
  * callers have (Topozero.py:274-302, Geo2rdr.py:321-384).  Results bound for pageable memory are bounced through a
  * page-locked ring (B200_SINK_SLOTS slots of 32 MB, default 16) and copied out by a pool of B200_COPY_THREADS host
- * threads (environment; default the CPUs of the process, at most 16; 0 = plain cudaMemcpy), so that the page faults of a file that does not exist yet are paid in
- * parallel with the DMA instead of by one thread. */
+ * threads (environment; default the CPUs of the process, at most 16; 0 = plain cudaMemcpy), so that the page faults of
+ * a file that does not exist yet are paid in parallel with the DMA instead of by one thread. */
 /* File-backed destinations.  When a pageable output buffer is a shared, writable mapping of a file (numpy.memmap of the
  * raster being written: what the reference's Components hand over, Topozero.py:274-302), the caller may say so: results
  * bound for [base, base + bytes) are then written by the copier threads with pwrite(fd, ..., file_offset + (dst - base))
