@@ -102,3 +102,30 @@ def test_empty_line_block_is_an_argument_error():
         pu.gpu_topo(sc, line0=4, nlines=0)
     with pytest.raises(_capi.B200Error):
         pu.gpu_topo(sc, line0=4, nlines=-1)  # "to the end" from the end
+
+
+def _ridge_scene(length=24, width=8000):
+    """Flat ground with two north-south ridges of 59 and 68 degrees of slope (3000 m over 60 posts, 1500 m over 20): the slant
+    range of the layover pass's cross-track grid runs backwards over ~950 and ~300 consecutive samples of every line,
+    i.e. disorder windows far beyond the length at which the co-sort's rank counting switches to its tiled group walk
+    (B2_RANK_TILE_MIN, topo_kernels.cu)."""
+    from isce2_b200 import synth
+    sc = synth.make_scene(length, width, hmin=0.0, hmax=1.0)
+    ny, nx = sc.dem.shape
+    x = np.arange(nx)
+    dem = np.zeros((ny, nx), np.float32)
+    for x0, h, half in ((nx * 0.45, 3000.0, 60), (nx * 0.6, 1500.0, 20)):
+        dem = np.maximum(dem, np.maximum(0.0, h * (1 - np.abs(x - x0) / half)).astype(np.float32)[None, :])
+    return dataclasses.replace(sc, dem=dem)
+
+
+@pytest.mark.parametrize("method", ["BIQUINTIC", "BILINEAR"])
+def test_long_range_fold_over(method):
+    sc = _ridge_scene()
+    g = pu.gpu_topo(sc, dem_method=method)
+    c = pu.cpu_topo(sc, dem_method=method)
+    st = pu.compare_topo(g, c)
+    _assert_topo(st)
+    hist = st["mask"]["hist_cpu"]
+    assert hist[2] + hist[3] > 0.1 * c["mask"].size and hist[1] > 0.1 * c["mask"].size  # layover and shadow on every line
+    assert st["mask"]["hist_gpu"] == hist
