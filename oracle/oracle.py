@@ -132,6 +132,7 @@ def lib():
         _ip = C.POINTER(C.c_int)
         L.orc_interp_dem_batch.argtypes = [C.c_int, _fp, C.c_int, C.c_int, C.c_long, _ip, _ip, _dp, _dp, _fp]
         L.orc_test_set_cpp_quirks.argtypes = [C.c_int]
+        L.orc_test_set_sinc_table.argtypes = [_fp]
         L.orc_sinc_table.argtypes = [_fp]
         L.orc_insertion_sort.argtypes = [_dp, _dp, _dp, C.c_int]
         L.orc_binarysearch.restype = C.c_int

@@ -536,6 +536,21 @@ static const float *sinc_table(void)
     return g_fintp;
 }
 void orc_sinc_table(float *out) { memcpy(out, sinc_table(), sizeof(float) * SINC_SUB * SINC_LEN); }
+/* test hook (tests/test_oracle_cpp_pins.py): replace the topo / geozero sinc table -- with the one the reference's C++
+ * builds by its older formula (UniformInterp.cpp:150-168), so that whole images interpolated with SINC can be compared with
+ * Topo.cpp, which builds its table internally; NULL restores the table of the current formula on next use */
+void orc_test_set_sinc_table(const float *table)
+{
+#pragma omp critical(orc_sinc_table)
+    {
+        free(g_fintp);
+        g_fintp = NULL;
+        if (table) {
+            g_fintp = malloc(sizeof(float) * SINC_SUB * SINC_LEN);
+            memcpy(g_fintp, table, sizeof(float) * SINC_SUB * SINC_LEN);
+        }
+    }
+}
 
 /* uniform_interp.f90:407-430 sinc_eval_2d_f: everything in real*4, k outer / m inner */
 static float sinc_eval_2d_f(const float *dem, const float *intarr, int idec, int ilen, int intpx, int intpy, double frpx,

@@ -128,6 +128,7 @@ void orc_interp_dem_batch(int method, const float *dem, int nx, int ny, long n, 
                           const double *fx, const double *fy, float *out);
 /* test hook of the C++ pin, see zerodop_oracle.c (never set outside tests/test_oracle_cpp_pins.py) */
 void orc_test_set_cpp_quirks(int on);
+void orc_test_set_sinc_table(const float *table); /* [8192][8] real*4, or NULL for the built-in one */
 
 void orc_sinc_table(float *out /* [8192*8] fintp of topozeroMethods.f:57-61 */);
 void orc_insertion_sort(double *a, double *b, double *c, int n);

@@ -25,7 +25,9 @@ oracle's test hook (so that every other line of the routine is still compared bi
                 both C++ tables also carry the `0.0-9.0` typo in row 4 (UniformInterp.cpp:72, Interpolator.cpp:61).
                 The oracle's bicubic stays pinned by polynomial reproduction as written (tests/test_oracle_pins.py).
 
-Whole images: Topo::topo (Topo.cpp) and Geo2rdr::geo2rdr (Geo2rdr.cpp) run here on the scenes of the parity tests.
+Whole images: Topo::topo (Topo.cpp) and Geo2rdr::geo2rdr (Geo2rdr.cpp) run here on the scenes of the parity tests
+(BILINEAR, BIQUINTIC, NEAREST as they are; AKIMA and SINC with the departures above switched on in the oracle and, for
+SINC, Topo.cpp's own table handed to it: orc_test_set_cpp_quirks / orc_test_set_sinc_table).
 Known departures of Topo.cpp from topozero.f90, none of which the comparison below depends on except as stated:
 MAX_H = -1000 (Constants.h:49; topozeroState.f:74: 9000) and 0-based crop indices clamped to 1 (Topo.cpp:321-333) --
 the DEM handed over is therefore smaller than either bounding box, so both crop to the same array; inc channel 1 is the
@@ -381,3 +383,67 @@ def test_whole_image_resamp_slc_against_reference_cpp(case):
     if RESAMP_CASES[case].get("doppler"):
         plain = orc.resamp_slc(**kw)
         assert np.median(np.abs(plain.astype(np.complex128) * scale - ref)[both] / amp) > 1e-3
+
+
+def test_whole_image_topo_akima_against_reference_cpp():
+    """The AKIMA interpolator through the whole path: with the three departures of AkimaLib.cpp switched on in the oracle
+    (slope stored into slpx, integer AKI_EPS, float32 corner differences: the header of this file) and a DEM of whole metres
+    (every SRTM tile; the float32 differences are then exact), Topo::topo and the oracle agree as for the other methods."""
+    length, width = 32, 1536
+    sc = pu.rough_scene(length, width)
+    dem, flat, flon = _clamped_dem(sc)
+    dem = np.round(dem).astype(np.float32)
+    kw = orc.scene_topo_kwargs(sc, dem_method="AKIMA", orbit_method="HERMITE")
+    ref = ref_cpp.topo(**{**kw, "dem": dem, "first_lat": flat, "first_lon": flon})
+    orc.lib().orc_test_set_cpp_quirks(1)
+    try:
+        got = orc.topo(**{**kw, "dem": np.ascontiguousarray(dem[1:, 1:]), "first_lat": flat + sc.delta_lat,
+                          "first_lon": flon + sc.delta_lon})
+    finally:
+        orc.lib().orc_test_set_cpp_quirks(0)
+    plain = orc.topo(**{**kw, "dem": np.ascontiguousarray(dem[1:, 1:]), "first_lat": flat + sc.delta_lat,
+                        "first_lon": flon + sc.delta_lon})
+    n = length * width
+    assert got["totalconv"] == ref["totalconv"] and 0.5 * n < got["totalconv"] <= n
+    for k, tol in (("lat", 1e-13), ("lon", 1e-13), ("hgt", 1e-8)):
+        d = np.abs(got[k] - ref[k])
+        assert d.max() <= tol, (k, d.max())
+        assert np.mean(d == 0) > 0.999, (k, np.mean(d == 0))
+    assert np.array_equal(got["los"], ref["los"])
+    assert np.array_equal(got["inc"][:, 1, :], ref["inc"][:, 1, :])
+    assert np.array_equal(ref["mask"] & 1, got["mask"] & 1)
+    # ... and the departures are real: as the Fortran is written (akima_reg.F:95-100) the heights differ
+    assert np.abs(plain["hgt"] - ref["hgt"]).max() > 1e-3
+
+
+def test_whole_image_topo_sinc_against_reference_cpp():
+    """The SINC interpolator through the whole path.  Topo.cpp builds its table with the older UniformInterp::sinc_coef and
+    forms the products in double (header of this file): with that table handed to the oracle and the C++'s arithmetic
+    switched on, every other line of the sinc path -- window placement, the one-cell shift, index clamping, edge
+    fall-backs -- is compared through Topo::topo."""
+    length, width = 32, 1536
+    sc = pu.rough_scene(length, width)
+    dem, flat, flon = _clamped_dem(sc)
+    kw = orc.scene_topo_kwargs(sc, dem_method="SINC", orbit_method="HERMITE")
+    ref = ref_cpp.topo(**{**kw, "dem": dem, "first_lat": flat, "first_lon": flon})
+    table = np.ascontiguousarray(ref_cpp.topo_sinc_table(), np.float32)
+    assert not np.array_equal(table, orc.sinc_table())  # the two formulas do differ
+    args = {**kw, "dem": np.ascontiguousarray(dem[1:, 1:]), "first_lat": flat + sc.delta_lat, "first_lon": flon + sc.delta_lon}
+    orc.lib().orc_test_set_sinc_table(table.ctypes.data_as(orc._fp))
+    orc.lib().orc_test_set_cpp_quirks(2)
+    try:
+        got = orc.topo(**args)
+    finally:
+        orc.lib().orc_test_set_cpp_quirks(0)
+        orc.lib().orc_test_set_sinc_table(None)
+    assert np.array_equal(np.ascontiguousarray(orc.sinc_table()), orc.sinc_table()) and not np.array_equal(table, orc.sinc_table())
+    # on this terrain most pixels do not reach the 5 cm threshold with SINC and go through all primary and secondary
+    # iterations -- in both implementations alike
+    assert got["totalconv"] == ref["totalconv"] and 0 < got["totalconv"] <= length * width
+    for k, tol in (("lat", 1e-13), ("lon", 1e-13), ("hgt", 1e-8)):
+        d = np.abs(got[k] - ref[k])
+        assert d.max() <= tol, (k, d.max())
+        assert np.mean(d == 0) > 0.999, (k, np.mean(d == 0))
+    assert np.array_equal(got["los"], ref["los"])
+    assert np.array_equal(got["inc"][:, 1, :], ref["inc"][:, 1, :])
+    assert np.array_equal(ref["mask"] & 1, got["mask"] & 1)
