@@ -122,3 +122,51 @@ def test_chained_components_host_logic(tmp_path, monkeypatch, devices):
     assert (hdr.dataType, hdr.width, hdr.length) == ("FLOAT", sc.width, sc.length)
     assert grdr.numValid == gg["num_valid"] and grdr.numOutsideImage == gg["num_outside"]
     assert topo.totalConverged == o["totalconv"] and abs(topo.minimumLatitude - o["min_lat"]) < 1e-12
+
+
+def test_bench_component_runners_host_logic(tmp_path, monkeypatch):
+    """The two runners bench.py times for `e2e_component` -- topo() with geo2rdr chained, and topo() followed by a separate
+    geo2rdr() on the rasters it wrote -- produce the same offset rasters (library calls replaced by the oracle), and the
+    separate geo2rdr() really reads lat / lon / hgt back from the files, declared as the file mappings they are."""
+    from isce2_b200 import synth_components as comp
+    calls, declared = [], []
+    fused = _oracle_as_library(calls)
+    monkeypatch.setattr(_capi, "topo_geo2rdr_run", fused)
+
+    def topo_run(params, dem, t, pos, vel, dop, slr=None, rho_image=None, want_los=True, want_inc=False, want_mask=False,
+                 out=None, doppler_poly=None, slrng_poly=None):
+        return fused(params, dem, t, pos, vel, dop, [], slr, rho_image, want_los, want_inc, want_mask, out, doppler_poly,
+                     slrng_poly)[0]
+
+    def geo2rdr_run(params, lat, lon, hgt, t, pos, vel, coeffs=(0.0,), mean=0.0, norm=1.0, want=None, out=None, block_rows=False):
+        q = params
+        for a in (lat, lon, hgt):  # what the component hands over are views of the rasters' mappings
+            assert IF._file_range(a, False) is not None
+        g = orc.geo2rdr(lat=np.asarray(lat), lon=np.asarray(lon), hgt=np.asarray(hgt), orbit_t=t, orbit_pos=pos, orbit_vel=vel,
+                        length=q.length, width=q.width, r0=q.rho0, dr=q.drho, prf=q.prf, t0=q.t0, wvl=q.wvl, side=q.look_side,
+                        doppler_coeffs=coeffs, doppler_mean=mean, doppler_norm=norm, a=q.major, e2=q.e2,
+                        orbit_method=ORB_NAMES[q.orbit_method], bistatic=bool(q.bistatic))
+        for k in ("azt", "rgm", "azoff", "rgoff"):
+            if out.get(k) is not None:
+                out[k][...] = g[k][q.line0:q.line0 + q.nlines].astype(out[k].dtype)
+        return dict(num_outside=g["num_outside"], num_valid=g["num_valid"], num_converged=g["num_conv"], iterations=g["total_iters"],
+                    ms_setup=0.0, ms_kernels=0.0, ms_total=0.0, gpu_launches=2)
+
+    monkeypatch.setattr(_capi, "topo_run", topo_run)
+    monkeypatch.setattr(_capi, "geo2rdr_run", geo2rdr_run)
+    real_register = _capi.host_file_register
+    monkeypatch.setattr(_capi, "host_file_register", lambda addr, n, fd, off: (declared.append(n), real_register(addr, n, fd, off))[1])
+    sc = synth.make_scene(20, 384)
+    sec = synth.make_scene(20, 384, dem=False, perturb=dict(da=120.0, d_cross=80.0, d_along_s=0.0))
+    dem_img = comp.prepare_dem(sc, str(tmp_path / "dem.dem"))
+    a = comp.run_components(sc, sec, dem_img, str(tmp_path / "chained"), dem_method="BILINEAR", inc=True, mask=True, devices=[0])
+    n_chained = len(declared)
+    b = comp.run_components_separately(sc, sec, dem_img, str(tmp_path / "separate"), dem_method="BILINEAR", inc=True, mask=True,
+                                       devices=[0])
+    assert a["files"] == b["files"] and a["bytes_written"] == b["bytes_written"] == sc.pixels * 49
+    assert b["seconds_topo"] > 0 and b["seconds_geo2rdr"] > 0 and a["num_valid"] == b["num_valid"] > 0.5 * sc.pixels
+    for f in a["files"]:
+        x, y = np.fromfile(tmp_path / "chained" / f, np.uint8), np.fromfile(tmp_path / "separate" / f, np.uint8)
+        assert np.array_equal(x, y), f
+    # chained: 8 rasters declared for writing; separate: 6 by topo(), then 2 + the 3 it reads by geo2rdr()
+    assert n_chained == 8 and len(declared) - n_chained == 11
